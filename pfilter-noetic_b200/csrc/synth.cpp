@@ -1,0 +1,244 @@
+// Synthetic LiDAR sequence generator (host only, deterministic).
+//
+// Produces HDL-64E- / VLP-32-shaped scans of an analytic "planes + poles" street scene along a
+// known trajectory, as specified in SURVEY.md section 8 row D2.  This is test/bench DATA, not part
+// of the hot path and not part of the oracle.  The ring elevation tables are chosen so that every
+// ray lands well inside the ring bins of the reference's ring classifier
+// (/root/reference/src/laserProcessingClass.cpp:38-57), so ring ids are unambiguous.
+//
+// Output layout: float4 {x, y, z, intensity}, ring-major, azimuth ascending, rays with no return
+// inside the range gate are dropped (like a real sensor).
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "pf_synth.h"
+
+namespace {
+
+struct Rect {      // axis-aligned vertical rectangle: plane axis (0: x = c, 1: y = c), extent in the other axis and z
+    int axis;
+    double c, lo, hi, z0, z1;
+};
+struct Pole {      // vertical cylinder
+    double x, y, r, z0, z1;
+};
+struct Scene {
+    double ground_z;
+    std::vector<Rect> rects;
+    std::vector<Pole> poles;
+};
+
+inline uint64_t splitmix64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+inline double u01(uint64_t h) { return ((h >> 11) + 0.5) * (1.0 / 9007199254740992.0); }
+
+struct Rng {
+    uint64_t s;
+    explicit Rng(uint64_t seed) : s(seed) {}
+    uint64_t next() { s = splitmix64(s); return s; }
+    double uni() { return u01(next()); }
+    double uni(double a, double b) { return a + (b - a) * uni(); }
+};
+
+void add_box(Scene& sc, double x0, double x1, double y0, double y1, double z0, double z1) {
+    sc.rects.push_back({0, x0, y0, y1, z0, z1});
+    sc.rects.push_back({0, x1, y0, y1, z0, z1});
+    sc.rects.push_back({1, y0, x0, x1, z0, z1});
+    sc.rects.push_back({1, y1, x0, x1, z0, z1});
+}
+
+// "planes+poles": street corridor along +x.  Facades at y = +-12 m with 4 m deep recesses every
+// 20 m, 6 m tall; poles r = 0.15 m every 10 m at y = +-8 m; a few seeded boxes (parked vehicles).
+Scene build_street(uint64_t seed, double x_begin, double x_end) {
+    Scene sc;
+    sc.ground_z = -1.73;
+    const double zt = sc.ground_z + 6.0;
+    for (int side = -1; side <= 1; side += 2) {
+        for (double x = x_begin; x < x_end; x += 20.0) {
+            double y_front = side * 12.0, y_back = side * 16.0;
+            sc.rects.push_back({1, y_front, x, x + 10.0, sc.ground_z, zt});
+            sc.rects.push_back({1, y_back, x + 10.0, x + 20.0, sc.ground_z, zt});
+            double ylo = side > 0 ? y_front : y_back, yhi = side > 0 ? y_back : y_front;
+            sc.rects.push_back({0, x + 10.0, ylo, yhi, sc.ground_z, zt});
+            sc.rects.push_back({0, x + 20.0, ylo, yhi, sc.ground_z, zt});
+        }
+        for (double x = x_begin + 5.0; x < x_end; x += 10.0)
+            sc.poles.push_back({x, side * 8.0, 0.15, sc.ground_z, sc.ground_z + 5.0});
+    }
+    Rng rng(seed * 7919ull + 17);
+    int nbox = (int)((x_end - x_begin) / 15.0);
+    for (int i = 0; i < nbox; ++i) {
+        double cx = rng.uni(x_begin, x_end);
+        double side = rng.uni() < 0.5 ? -1.0 : 1.0;
+        double cy = side * rng.uni(4.5, 10.0);
+        double lx = rng.uni(1.5, 4.5), ly = rng.uni(1.2, 2.2), h = rng.uni(1.2, 2.8);
+        add_box(sc, cx - lx / 2, cx + lx / 2, cy - ly / 2, cy + ly / 2, sc.ground_z, sc.ground_z + h);
+    }
+    // far end walls close the corridor so that long rays terminate
+    sc.rects.push_back({0, x_begin - 1.0, -16.0, 16.0, sc.ground_z, zt});
+    sc.rects.push_back({0, x_end + 1.0, -16.0, 16.0, sc.ground_z, zt});
+    return sc;
+}
+
+// "campus": cluttered open area (random vertical walls + poles) for the slow loop trajectory.
+Scene build_campus(uint64_t seed, double half) {
+    Scene sc;
+    sc.ground_z = -1.73;
+    Rng rng(seed * 104729ull + 3);
+    int nb = 260;
+    for (int i = 0; i < nb; ++i) {
+        double cx = rng.uni(-half, half), cy = rng.uni(-half, half);
+        double r = std::sqrt(cx * cx + cy * cy);
+        if (r > 52.0 && r < 68.0) continue;          // keep the driving loop (radius 60 m) free
+        double lx = rng.uni(2.0, 14.0), ly = rng.uni(2.0, 14.0), h = rng.uni(2.0, 9.0);
+        add_box(sc, cx - lx / 2, cx + lx / 2, cy - ly / 2, cy + ly / 2, sc.ground_z, sc.ground_z + h);
+    }
+    for (int i = 0; i < 400; ++i) {
+        double cx = rng.uni(-half, half), cy = rng.uni(-half, half);
+        double r = std::sqrt(cx * cx + cy * cy);
+        if (r > 57.0 && r < 63.0) continue;
+        sc.poles.push_back({cx, cy, rng.uni(0.08, 0.3), sc.ground_z, sc.ground_z + rng.uni(2.5, 7.0)});
+    }
+    add_box(sc, -half - 1, half + 1, -half - 1, half + 1, sc.ground_z, sc.ground_z + 8.0);
+    return sc;
+}
+
+struct Pose2 { double x, y, z, yaw; };
+
+Pose2 trajectory(const pf_synth_params& p, int k) {
+    Pose2 q{0, 0, 0, 0};
+    if (p.trajectory == PF_SYNTH_TRAJ_STREET) {
+        // ~1 m/frame along +x with a gentle weave; yaw = 0.1 sin(2 pi k / 100)
+        q.x = p.speed * k;
+        q.yaw = 0.1 * std::sin(2.0 * M_PI * k / 100.0);
+        q.y = 1.5 * std::sin(2.0 * M_PI * k / 100.0);
+        q.z = 0.0;
+    } else {
+        // closed loop of radius 60 m, p.speed metres of arc per frame
+        double R = 60.0, a = p.speed * k / R;
+        q.x = R * std::sin(a);
+        q.y = R * (1.0 - std::cos(a)) - R;
+        q.yaw = a;
+    }
+    return q;
+}
+
+double elevation_deg(int sensor, int ring) {
+    if (sensor == 64) return ring < 32 ? 1.95 - ring / 3.0 : -8.68 - (ring - 32) / 2.0;
+    if (sensor == 32) return -92.0 / 3.0 + (ring + 0.5) * 4.0 / 3.0;
+    return -15.0 + 2.0 * ring;   // 16 lines: bin centres of int((ang+15)/2+0.5)
+}
+
+struct Cache {
+    pf_synth_params key;
+    bool valid = false;
+    Scene scene;
+};
+Cache g_cache;
+
+const Scene& scene_for(const pf_synth_params& p) {
+    if (!g_cache.valid || g_cache.key.seed != p.seed || g_cache.key.scene != p.scene) {
+        g_cache.scene = p.scene == PF_SYNTH_SCENE_STREET ? build_street(p.seed, -60.0, 1200.0) : build_campus(p.seed, 110.0);
+        g_cache.key = p;
+        g_cache.valid = true;
+    }
+    return g_cache.scene;
+}
+
+}  // namespace
+
+extern "C" void pf_synth_default_params(pf_synth_params* p) {
+    std::memset(p, 0, sizeof(*p));
+    p->sensor_lines = 64;
+    p->azimuth_steps = 1800;
+    p->seed = 2022;
+    p->scene = PF_SYNTH_SCENE_STREET;
+    p->trajectory = PF_SYNTH_TRAJ_STREET;
+    p->speed = 1.0;
+    p->range_sigma = 0.02;
+    p->elev_jitter_deg = 0.02;
+    p->min_range = 3.2;
+    p->max_range = 88.0;
+}
+
+extern "C" void pf_synth_pose(const pf_synth_params* p, int frame, double pose[7]) {
+    Pose2 q = trajectory(*p, frame);
+    pose[0] = 0; pose[1] = 0; pose[2] = std::sin(q.yaw / 2); pose[3] = std::cos(q.yaw / 2);
+    pose[4] = q.x; pose[5] = q.y; pose[6] = q.z;
+}
+
+extern "C" int pf_synth_scan(const pf_synth_params* p, int frame, float* out_xyzi, int cap) {
+    const Scene& sc = scene_for(*p);
+    Pose2 pose = trajectory(*p, frame);
+    const double cy = std::cos(pose.yaw), sy = std::sin(pose.yaw);
+
+    // cull primitives to those within reach of the sensor
+    const double reach = p->max_range + 30.0;
+    std::vector<Rect> rects;
+    std::vector<Pole> poles;
+    for (const Rect& r : sc.rects) {
+        double px = r.axis == 0 ? r.c : 0.5 * (r.lo + r.hi), py = r.axis == 1 ? r.c : 0.5 * (r.lo + r.hi);
+        double ext = 0.5 * (r.hi - r.lo);
+        if (std::hypot(px - pose.x, py - pose.y) < reach + ext) rects.push_back(r);
+    }
+    for (const Pole& c : sc.poles)
+        if (std::hypot(c.x - pose.x, c.y - pose.y) < reach) poles.push_back(c);
+
+    int n = 0;
+    for (int ring = 0; ring < p->sensor_lines; ++ring) {
+        const double elev0 = elevation_deg(p->sensor_lines, ring);
+        for (int a = 0; a < p->azimuth_steps; ++a) {
+            uint64_t h = splitmix64(p->seed * 0x100000001B3ull ^ ((uint64_t)frame << 40) ^ ((uint64_t)ring << 24) ^ (uint64_t)a);
+            uint64_t h1 = splitmix64(h), h2 = splitmix64(h1), h3 = splitmix64(h2);
+            double elev = (elev0 + p->elev_jitter_deg * (2.0 * u01(h1) - 1.0)) * M_PI / 180.0;
+            double az = 2.0 * M_PI * (a + 0.5) / p->azimuth_steps - M_PI;
+            // ray in sensor frame
+            double ce = std::cos(elev), dxs = ce * std::cos(az), dys = ce * std::sin(az), dz = std::sin(elev);
+            // to world
+            double dx = cy * dxs - sy * dys, dy = sy * dxs + cy * dys;
+            double ox = pose.x, oy = pose.y, oz = pose.z;
+            double tbest = 1e30;
+            if (dz < -1e-9) {
+                double t = (sc.ground_z - oz) / dz;
+                if (t > 0 && t < tbest) tbest = t;
+            }
+            for (const Rect& r : rects) {
+                double d = r.axis == 0 ? dx : dy, o = r.axis == 0 ? ox : oy;
+                if (std::fabs(d) < 1e-12) continue;
+                double t = (r.c - o) / d;
+                if (t <= 0 || t >= tbest) continue;
+                double u = r.axis == 0 ? oy + t * dy : ox + t * dx, z = oz + t * dz;
+                if (u >= r.lo && u <= r.hi && z >= r.z0 && z <= r.z1) tbest = t;
+            }
+            for (const Pole& c : poles) {
+                double fx = ox - c.x, fy = oy - c.y;
+                double A = dx * dx + dy * dy, B = fx * dx + fy * dy, C = fx * fx + fy * fy - c.r * c.r;
+                double disc = B * B - A * C;
+                if (disc <= 0 || A < 1e-14) continue;
+                double t = (-B - std::sqrt(disc)) / A;
+                if (t <= 0 || t >= tbest) continue;
+                double z = oz + t * dz;
+                if (z >= c.z0 && z <= c.z1) tbest = t;
+            }
+            if (tbest > 1e29) continue;
+            // Box-Muller range noise along the ray (also breaks exact curvature ties)
+            double g = std::sqrt(-2.0 * std::log(u01(h2))) * std::cos(2.0 * M_PI * u01(h3));
+            double range = tbest + p->range_sigma * g;
+            double rxy = range * ce;
+            if (rxy < p->min_range || rxy > p->max_range) continue;    // keep clear of the 3-90 m gate edges
+            if (n >= cap) return -1;
+            out_xyzi[4 * n + 0] = (float)(range * dxs);
+            out_xyzi[4 * n + 1] = (float)(range * dys);
+            out_xyzi[4 * n + 2] = (float)(range * dz);
+            out_xyzi[4 * n + 3] = (float)(u01(splitmix64(h3)));
+            ++n;
+        }
+    }
+    return n;
+}
