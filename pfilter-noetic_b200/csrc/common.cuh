@@ -1,0 +1,89 @@
+// Shared helpers for the pfilter_b200 CUDA sources (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "pfilter_b200.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "pfilter_b200 is written for sm_100a (B200) only"
+#endif
+
+namespace pf {
+
+void set_error(const char* fmt, ...);
+
+#define PF_CUDA(call)                                                                              \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            pf::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_));    \
+            return PF_ERR_CUDA;                                                                    \
+        }                                                                                          \
+    } while (0)
+
+#define PF_CHECK(expr)                                                                             \
+    do {                                                                                           \
+        int s_ = (expr);                                                                           \
+        if (s_ != PF_OK) return s_;                                                                \
+    } while (0)
+
+#define PF_REQUIRE(cond, ...)                                                                      \
+    do {                                                                                           \
+        if (!(cond)) {                                                                             \
+            pf::set_error(__VA_ARGS__);                                                            \
+            return PF_ERR_INVALID;                                                                 \
+        }                                                                                          \
+    } while (0)
+
+constexpr int kSMs = 148;   // B200
+
+// 16-byte map / feature point viewed as raw words: {x, y, z, rgba}
+struct __align__(16) Pt {
+    float x, y, z;
+    uint32_t rgba;   // r | g << 8 | b << 16 | a << 24 (little endian layout of pf_point)
+};
+static_assert(sizeof(Pt) == 16, "Pt must be 16 bytes");
+static_assert(sizeof(pf_point) == 16, "pf_point must be 16 bytes");
+
+__host__ __device__ inline uint32_t pack_rgba(uint32_t r, uint32_t g, uint32_t b, uint32_t a) {
+    return r | (g << 8) | (b << 16) | (a << 24);
+}
+__host__ __device__ inline uint32_t pt_r(uint32_t rgba) { return rgba & 0xffu; }
+__host__ __device__ inline uint32_t pt_g(uint32_t rgba) { return (rgba >> 8) & 0xffu; }
+
+inline int div_up(int a, int b) { return (a + b - 1) / b; }
+inline int64_t div_up64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+#ifdef __CUDACC__
+__device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31u; }
+__device__ __forceinline__ unsigned lanemask_lt() {
+    unsigned m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+// streaming 16-byte load that does not pollute L1 (data is touched once per CTA)
+__device__ __forceinline__ float4 ld_stream_f4(const float4* p) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void st_stream_f4(float4* p, float4 v) {
+    asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                 : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+#endif
+
+}  // namespace pf
