@@ -69,3 +69,143 @@ def extract(xyzi, num_lines=64, min_d=3.0, max_d=90.0, order=1):
                                 label.ctypes.data_as(C.c_void_p), ring.ctypes.data_as(C.c_void_p))
     assert rc == 0
     return dict(edge_idx=e[:ne.value].copy(), surf_idx=s[:ns.value].copy(), label=label[:n].copy(), ring=ring[:n].copy())
+
+
+# ------------------------------------------------------------------------------------------------------------
+# odometry / map restatement (oracle_odom.cpp)
+# ------------------------------------------------------------------------------------------------------------
+POINT_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("z", "<f4"), ("r", "u1"), ("g", "u1"), ("b", "u1"), ("a", "u1")])
+
+
+def _vp(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _pts(a):
+    a = np.ascontiguousarray(a)
+    assert a.dtype == POINT_DTYPE
+    return a
+
+
+def voxel_downsample(pts, leaf):
+    p = _pts(pts)
+    out = np.empty(max(len(p), 1), POINT_DTYPE)
+    n = C.c_int()
+    lib().pforacle_voxel_downsample(_vp(p), len(p), C.c_float(leaf), _vp(out), C.byref(n))
+    return out[:n.value].copy()
+
+
+def map_update(pts, center, leaf, k_new, theta_p, theta_max):
+    p = _pts(pts)
+    out = np.empty(max(len(p), 1), POINT_DTYPE)
+    n = C.c_int()
+    c = np.asarray(center, np.float64)
+    lib().pforacle_map_update(_vp(p), len(p), _vp(c), C.c_float(leaf), k_new, C.c_float(theta_p), theta_max, _vp(out), C.byref(n))
+    return out[:n.value].copy()
+
+
+def knn5(map_pts, queries_xyz4, mode=1):
+    m = _pts(map_pts)
+    q = np.ascontiguousarray(queries_xyz4, np.float32)
+    idx = np.empty((len(q), 5), np.int32)
+    d2 = np.empty((len(q), 5), np.float32)
+    lib().pforacle_knn5(_vp(m), len(m), _vp(q), len(q), mode, _vp(idx), _vp(d2))
+    return idx, d2
+
+
+def associate(kind, map_pts, queries, pose, k_new, theta_p, theta_max):
+    """Returns (map_after, queries_after, flag, geom8)."""
+    m = _pts(map_pts).copy()
+    q = _pts(queries).copy()
+    flag = np.zeros(len(q), np.uint8)
+    geom = np.zeros((len(q), 8), np.float64)
+    pose = np.ascontiguousarray(pose, np.float64)
+    lib().pforacle_associate(kind, _vp(m), len(m), _vp(q), len(q), _vp(pose), k_new, C.c_float(theta_p), theta_max, _vp(flag), _vp(geom))
+    return m, q, flag, geom
+
+
+def eval_normal_eq(pose, edge9, surf7):
+    pose = np.ascontiguousarray(pose, np.float64)
+    e = np.ascontiguousarray(edge9, np.float64).reshape(-1, 9)
+    s = np.ascontiguousarray(surf7, np.float64).reshape(-1, 7)
+    H = np.zeros(21); g = np.zeros(6); cost = C.c_double()
+    lib().pforacle_eval_normal_eq(_vp(pose), _vp(e), len(e), _vp(s), len(s), _vp(H), _vp(g), C.byref(cost))
+    return H, g, cost.value
+
+
+def lm_solve(pose, edge9, surf7):
+    x = np.array(pose, np.float64)
+    e = np.ascontiguousarray(edge9, np.float64).reshape(-1, 9)
+    s = np.ascontiguousarray(surf7, np.float64).reshape(-1, 7)
+    it = C.c_int(); cost = C.c_double()
+    lib().pforacle_lm_solve(_vp(x), _vp(e), len(e), _vp(s), len(s), C.byref(it), C.byref(cost))
+    return x, it.value, cost.value
+
+
+def se3_plus(x, d):
+    x = np.ascontiguousarray(x, np.float64); d = np.ascontiguousarray(d, np.float64)
+    out = np.zeros(7)
+    lib().pforacle_se3_plus(_vp(x), _vp(d), _vp(out))
+    return out
+
+
+def eig3(A):
+    A = np.ascontiguousarray(A, np.float64)
+    w = np.zeros(3); V = np.zeros((3, 3))
+    lib().pforacle_eig3(_vp(A), _vp(w), _vp(V))
+    return w, V
+
+
+def qr_solve(A, b):
+    A = np.ascontiguousarray(A, np.float64); b = np.ascontiguousarray(b, np.float64)
+    x = np.zeros(3)
+    lib().pforacle_qr_solve(_vp(A), _vp(b), A.shape[0], _vp(x))
+    return x
+
+
+def residual(kind, geom, pose):
+    geom = np.ascontiguousarray(geom, np.float64); pose = np.ascontiguousarray(pose, np.float64)
+    r = C.c_double(); J = np.zeros(6)
+    lib().pforacle_residual(kind, _vp(geom), _vp(pose), C.byref(r), _vp(J))
+    return r.value, J
+
+
+class Odom:
+    """Restated Odom_ES_EstimationClass (CPU)."""
+
+    def __init__(self, map_resolution=0.4, k_new=0, theta_p=0.4, theta_max=75, weight_type=0.0):
+        L = lib()
+        L.pforacle_odom_create.restype = C.c_void_p
+        self.h = C.c_void_p(L.pforacle_odom_create(C.c_double(map_resolution), k_new, C.c_float(theta_p), theta_max, C.c_double(weight_type)))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().pforacle_odom_destroy(self.h)
+            self.h = None
+
+    def init_map(self, edge4, surf4):
+        e = np.ascontiguousarray(edge4, np.float32); s = np.ascontiguousarray(surf4, np.float32)
+        lib().pforacle_odom_init_map(self.h, _vp(e), len(e), _vp(s), len(s))
+
+    def update(self, edge4, surf4):
+        e = np.ascontiguousarray(edge4, np.float32); s = np.ascontiguousarray(surf4, np.float32)
+        pose = np.zeros(7)
+        lib().pforacle_odom_update(self.h, _vp(e), len(e), _vp(s), len(s), _vp(pose))
+        return pose
+
+    def get_map(self, which):
+        n = lib().pforacle_odom_map_size(self.h, which)
+        out = np.empty(max(n, 1), POINT_DTYPE)
+        lib().pforacle_odom_get_map(self.h, which, _vp(out))
+        return out[:n].copy()
+
+    def iter_poses(self):
+        out = np.zeros((16, 7))
+        n = lib().pforacle_odom_iter_poses(self.h, _vp(out), 16)
+        return out[:n].copy()
+
+    def stats(self):
+        out = np.zeros(8, np.int32)
+        lib().pforacle_odom_stats(self.h, _vp(out))
+        return dict(zip(("n_edge_ds", "n_surf_ds", "n_edge_res", "n_surf_res", "map_edge", "map_surf", "passes", "lm_iterations"),
+                        out.tolist()))
