@@ -172,3 +172,30 @@ class Extractor:
         v = C.c_uint64()
         check(lib().pf_extract_kernel_launches(self.h, C.byref(v)))
         return v.value
+
+
+# ------------------------------------------------------------------------------------------------------------
+# stage taps
+# ------------------------------------------------------------------------------------------------------------
+def _pts(a):
+    a = np.ascontiguousarray(a)
+    assert a.dtype == POINT_DTYPE, a.dtype
+    return a
+
+
+def voxel_downsample(pts, leaf, device=0):
+    p = _pts(pts)
+    out = np.empty(max(len(p), 1), POINT_DTYPE)
+    n = C.c_int()
+    check(lib().pf_voxel_downsample(device, _vp(p), len(p), C.c_float(leaf), _vp(out), C.byref(n)))
+    return out[:n.value].copy()
+
+
+def map_update(pts, center, leaf, k_new, theta_p, theta_max, device=0):
+    p = _pts(pts)
+    out = np.empty(max(len(p), 1), POINT_DTYPE)
+    n = C.c_int()
+    c = np.ascontiguousarray(center, np.float64)
+    check(lib().pf_map_update(device, _vp(p), len(p), _vp(c), C.c_float(leaf), k_new, C.c_float(theta_p), theta_max, _vp(out),
+                              C.byref(n)))
+    return out[:n.value].copy()

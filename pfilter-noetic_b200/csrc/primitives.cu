@@ -1,0 +1,167 @@
+// Stable LSD radix sort (8-bit digits) of (u32 key, u32 value) pairs with a device-resident element count,
+// plus workspace management.  Three kernels per digit: per-tile digit histogram, per-digit scan across tiles,
+// stable scatter (warp-private digit counters keep the input order inside a tile).
+#include "primitives.cuh"
+
+namespace pf {
+
+__global__ void __launch_bounds__(kSortThreads) k_sort_hist(const uint32_t* __restrict__ keys, const int* __restrict__ n_dev, int shift,
+                                                            uint32_t* __restrict__ hist, int nb_cap) {
+    const int n = *n_dev;
+    const int b = blockIdx.x, start = b * kSortTile;
+    if (start >= n) return;
+    __shared__ unsigned h[kRadix];
+    h[threadIdx.x] = 0;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < kSortItems; ++k) {
+        int i = start + k * kSortThreads + threadIdx.x;
+        const bool ok = i < n;
+        const unsigned act = __ballot_sync(0xffffffffu, ok);
+        if (ok) {
+            unsigned d = (keys[i] >> shift) & (kRadix - 1);
+            // warp-aggregated shared atomic: one add per distinct digit in the warp
+            unsigned m = __match_any_sync(act, d);
+            if ((int)lane_id() == __ffs(m) - 1) atomicAdd(&h[d], (unsigned)__popc(m));
+        }
+    }
+    __syncthreads();
+    hist[(size_t)threadIdx.x * nb_cap + b] = h[threadIdx.x];
+}
+
+// one warp per digit: exclusive scan of hist[d][0..nb) in place, totals[d] = sum
+__global__ void __launch_bounds__(256) k_sort_scan(uint32_t* __restrict__ hist, const int* __restrict__ n_dev, int nb_cap,
+                                                   uint32_t* __restrict__ totals) {
+    const int n = *n_dev;
+    const int nb = (n + kSortTile - 1) / kSortTile;
+    const int d = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    uint32_t* row = hist + (size_t)d * nb_cap;
+    unsigned carry = 0;
+    for (int base = 0; base < nb; base += 32) {
+        int i = base + lane;
+        unsigned v = i < nb ? row[i] : 0u, x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            unsigned y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += y;
+        }
+        if (i < nb) row[i] = carry + x - v;
+        carry += __shfl_sync(0xffffffffu, x, 31);
+    }
+    if (lane == 0) totals[d] = carry;
+}
+
+__global__ void __launch_bounds__(kSortThreads) k_sort_scatter(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
+                                                               uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
+                                                               const int* __restrict__ n_dev, int shift, const uint32_t* __restrict__ hist,
+                                                               const uint32_t* __restrict__ totals, int nb_cap) {
+    const int n = *n_dev;
+    const int b = blockIdx.x, start = b * kSortTile;
+    if (start >= n) return;
+    __shared__ unsigned wc[kSortThreads / 32][kRadix];   // warp-private digit counters -> exclusive bases
+    __shared__ int tmp[9];
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    for (int k = 0; k < kSortThreads / 32; ++k) wc[k][tid] = 0;
+    __syncthreads();
+    // warp w owns the contiguous sub-chunk [start + w*256, +256), processed in 8 ordered rounds of 32 keys
+    unsigned key[kSortItems], val[kSortItems], rank[kSortItems];
+    const int wstart = start + w * (kSortTile / (kSortThreads / 32));
+#pragma unroll
+    for (int k = 0; k < kSortItems; ++k) {
+        int i = wstart + k * 32 + lane;
+        bool ok = i < n;
+        key[k] = ok ? keys_in[i] : 0xffffffffu;
+        val[k] = ok ? (vals_in ? vals_in[i] : (unsigned)i) : 0u;
+        unsigned d = (key[k] >> shift) & (kRadix - 1);
+        unsigned act = __ballot_sync(0xffffffffu, ok);
+        rank[k] = 0;
+        if (ok) {
+            unsigned m = __match_any_sync(act, d);
+            unsigned before = wc[w][d];
+            rank[k] = before + __popc(m & lanemask_lt());
+            __syncwarp(act);
+            if (lane == __ffs(m) - 1) wc[w][d] = before + __popc(m);
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+    // digit tid: exclusive prefix over the 8 warps, plus the global base of the digit for this tile
+    {
+        int tot;
+        unsigned t = totals[tid];
+        int dbase = block_scan_excl_256((int)t, tmp, &tot);
+        unsigned run = (unsigned)dbase + hist[(size_t)tid * nb_cap + b];
+#pragma unroll
+        for (int k = 0; k < kSortThreads / 32; ++k) {
+            unsigned c = wc[k][tid];
+            wc[k][tid] = run;
+            run += c;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < kSortItems; ++k) {
+        int i = wstart + k * 32 + lane;
+        if (i < n) {
+            unsigned d = (key[k] >> shift) & (kRadix - 1);
+            unsigned pos = wc[w][d] + rank[k];
+            keys_out[pos] = key[k];
+            vals_out[pos] = val[k];
+        }
+    }
+}
+
+__global__ void k_begin_step(unsigned int* ctrl) {
+    if (threadIdx.x == 0) ctrl[0] += 1;
+    else if (threadIdx.x < kCtrlWords) ctrl[threadIdx.x] = 0;
+}
+
+int workspace_create(Workspace& ws, int cap, cudaStream_t stream) {
+    ws.stream = stream;
+    ws.cap = cap;
+    ws.nb_cap = div_up(cap, kSortTile);
+    for (int k = 0; k < 2; ++k) {
+        PF_CUDA(cudaMalloc(&ws.keys[k], sizeof(uint32_t) * cap));
+        PF_CUDA(cudaMalloc(&ws.vals[k], sizeof(uint32_t) * cap));
+    }
+    PF_CUDA(cudaMalloc(&ws.hist, sizeof(uint32_t) * kRadix * ws.nb_cap));
+    PF_CUDA(cudaMalloc(&ws.totals, sizeof(uint32_t) * kRadix));
+    ws.status_stride = ws.nb_cap * 8 + 8;
+    PF_CUDA(cudaMalloc(&ws.scan_status, sizeof(unsigned long long) * 4 * ws.status_stride));
+    PF_CUDA(cudaMemset(ws.scan_status, 0, sizeof(unsigned long long) * 4 * ws.status_stride));
+    PF_CUDA(cudaMalloc(&ws.ctrl, sizeof(unsigned) * kCtrlWords));
+    PF_CUDA(cudaMemset(ws.ctrl, 0, sizeof(unsigned) * kCtrlWords));
+    return PF_OK;
+}
+
+void workspace_destroy(Workspace& ws) {
+    for (int k = 0; k < 2; ++k) { cudaFree(ws.keys[k]); cudaFree(ws.vals[k]); }
+    cudaFree(ws.hist); cudaFree(ws.totals); cudaFree(ws.scan_status); cudaFree(ws.ctrl);
+    ws = Workspace();
+}
+
+int workspace_begin_step(Workspace& ws) {
+    k_begin_step<<<1, kCtrlWords, 0, ws.stream>>>(ws.ctrl);
+    ws.launches += 1;
+    PF_CUDA(cudaGetLastError());
+    return PF_OK;
+}
+
+int radix_sort(Workspace& ws, const int* n_dev, int n_cap, int passes, bool vals_iota) {
+    PF_REQUIRE(n_cap <= ws.cap, "radix_sort: %d items exceed workspace capacity %d", n_cap, ws.cap);
+    PF_REQUIRE(passes % 2 == 0 && passes >= 2 && passes <= 4, "radix_sort: passes must be 2 or 4");
+    const int nb = div_up(n_cap, kSortTile);
+    if (nb == 0) return PF_OK;
+    for (int p = 0; p < passes; ++p) {
+        const int src = p & 1, dst = src ^ 1, shift = p * kRadixBits;
+        k_sort_hist<<<nb, kSortThreads, 0, ws.stream>>>(ws.keys[src], n_dev, shift, ws.hist, ws.nb_cap);
+        k_sort_scan<<<kRadix / 8, 256, 0, ws.stream>>>(ws.hist, n_dev, ws.nb_cap, ws.totals);
+        k_sort_scatter<<<nb, kSortThreads, 0, ws.stream>>>(ws.keys[src], (p == 0 && vals_iota) ? nullptr : ws.vals[src], ws.keys[dst],
+                                                           ws.vals[dst], n_dev, shift, ws.hist, ws.totals, ws.nb_cap);
+        ws.launches += 3;
+    }
+    PF_CUDA(cudaGetLastError());
+    return PF_OK;
+}
+
+}  // namespace pf
