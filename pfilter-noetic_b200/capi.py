@@ -199,3 +199,129 @@ def map_update(pts, center, leaf, k_new, theta_p, theta_max, device=0):
     check(lib().pf_map_update(device, _vp(p), len(p), _vp(c), C.c_float(leaf), k_new, C.c_float(theta_p), theta_max, _vp(out),
                               C.byref(n)))
     return out[:n.value].copy()
+
+
+def knn5(map_pts, queries_xyz4, device=0):
+    m = _pts(map_pts)
+    q = np.ascontiguousarray(queries_xyz4, np.float32)
+    assert q.ndim == 2 and q.shape[1] == 4
+    idx = np.empty((max(len(q), 1), 5), np.int32)
+    d2 = np.empty((max(len(q), 1), 5), np.float32)
+    check(lib().pf_knn5(device, _vp(m), len(m), _vp(q), len(q), _vp(idx), _vp(d2)))
+    return idx[:len(q)], d2[:len(q)]
+
+
+def associate(kind, map_pts, queries, pose, k_new, theta_p, theta_max, device=0):
+    """One association pass; returns (map_after, queries_after, flag, geom8)."""
+    m = _pts(map_pts).copy()
+    q = _pts(queries).copy()
+    flag = np.zeros(max(len(q), 1), np.uint8)
+    geom = np.zeros((max(len(q), 1), 8), np.float64)
+    pose = np.ascontiguousarray(pose, np.float64)
+    check(lib().pf_associate(device, kind, _vp(m), len(m), _vp(q), len(q), _vp(pose), k_new, C.c_float(theta_p), theta_max, _vp(flag),
+                             _vp(geom)))
+    return m, q, flag[:len(q)], geom[:len(q)]
+
+
+def eval_normal_eq(pose, edge9, surf7, device=0):
+    pose = np.ascontiguousarray(pose, np.float64)
+    e = np.ascontiguousarray(edge9, np.float64).reshape(-1, 9)
+    s = np.ascontiguousarray(surf7, np.float64).reshape(-1, 7)
+    H = np.zeros(21); g = np.zeros(6); cost = C.c_double()
+    check(lib().pf_eval_normal_eq(device, _vp(pose), _vp(e), len(e), _vp(s), len(s), _vp(H), _vp(g), C.byref(cost)))
+    return H, g, cost.value
+
+
+def lm_solve(pose, edge9, surf7, device=0):
+    x = np.array(pose, np.float64)
+    e = np.ascontiguousarray(edge9, np.float64).reshape(-1, 9)
+    s = np.ascontiguousarray(surf7, np.float64).reshape(-1, 7)
+    it = C.c_int(); cost = C.c_double()
+    check(lib().pf_lm_solve(device, _vp(x), _vp(e), len(e), _vp(s), len(s), C.byref(it), C.byref(cost)))
+    return x, it.value, cost.value
+
+
+class Odometry:
+    """Handle of pf_odom_* (replaces Odom_ES_EstimationClass)."""
+
+    def __init__(self, map_resolution=0.4, k_new=0, theta_p=0.4, theta_max=75, weight_type=0.0, max_map_points=0, max_features=0,
+                 device=0):
+        self.prm = OdomParams(map_resolution, k_new, theta_p, theta_max, weight_type, max_map_points, max_features)
+        self.h = C.c_void_p()
+        check(lib().pf_odom_create(C.byref(self.prm), device, C.byref(self.h)))
+
+    def close(self):
+        if self.h:
+            lib().pf_odom_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def init_map(self, edge4, surf4):
+        e, s = as_points(edge4), as_points(surf4)
+        check(lib().pf_odom_init_map(self.h, _vp(e), len(e), _vp(s), len(s)))
+
+    def update(self, edge4, surf4):
+        e, s = as_points(edge4), as_points(surf4)
+        pose = np.zeros(7)
+        check(lib().pf_odom_update(self.h, _vp(e), len(e), _vp(s), len(s), _vp(pose)))
+        return pose
+
+    def process_extracted(self, extractor):
+        pose = np.zeros(7)
+        check(lib().pf_odom_process_extracted(self.h, extractor.h, _vp(pose)))
+        return pose
+
+    def pose(self):
+        pose = np.zeros(7)
+        check(lib().pf_odom_get_pose(self.h, _vp(pose)))
+        return pose
+
+    def map_part(self, which):
+        n = C.c_int()
+        check(lib().pf_odom_map_size(self.h, which, C.byref(n)))
+        out = np.empty(max(n.value, 1), POINT_DTYPE)
+        check(lib().pf_odom_get_map_part(self.h, which, _vp(out), len(out), C.byref(n)))
+        return out[:n.value].copy()
+
+    def get_map(self):
+        ne, ns = C.c_int(), C.c_int()
+        check(lib().pf_odom_map_size(self.h, 0, C.byref(ne)))
+        check(lib().pf_odom_map_size(self.h, 1, C.byref(ns)))
+        out = np.empty(max(ne.value + ns.value, 1), POINT_DTYPE)
+        n = C.c_int()
+        check(lib().pf_odom_get_map(self.h, _vp(out), len(out), C.byref(n)))
+        return out[:n.value].copy()
+
+    def iter_poses(self):
+        out = np.zeros((16, 7))
+        n = C.c_int()
+        check(lib().pf_odom_get_iter_poses(self.h, _vp(out), 16, C.byref(n)))
+        return out[:n.value].copy()
+
+    def stats(self):
+        s = OdomStats()
+        check(lib().pf_odom_get_stats(self.h, C.byref(s)))
+        return {k: getattr(s, k) for k, _ in OdomStats._fields_}
+
+    @property
+    def stream(self):
+        return lib().pf_odom_stream(self.h)
+
+    @property
+    def launches(self):
+        v = C.c_uint64()
+        check(lib().pf_odom_kernel_launches(self.h, C.byref(v)))
+        return v.value
+
+
+def frame_process(extractor, odometry, xyzi):
+    """pf_frame_process: H2D scan -> extract -> (init | update) -> pose."""
+    a = as_points(xyzi)
+    pose = np.zeros(7)
+    check(lib().pf_frame_process(extractor.h, odometry.h, _vp(a), len(a), _vp(pose)))
+    return pose

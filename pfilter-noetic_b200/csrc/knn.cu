@@ -1,0 +1,209 @@
+// K3: search-grid build (cell sort) for the two local maps, and the pf_knn5 stage tap.  See knn.cuh.
+#include "knn.cuh"
+
+namespace pf {
+
+__device__ __forceinline__ unsigned f2ord_k(float f) {
+    unsigned u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ord2f_k(unsigned k) {
+    unsigned u = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
+    return __uint_as_float(u);
+}
+
+// state slot: [0..5] map0 {~min, max}, [6..11] map1, [12..13] counts n0, n1, [14] n_total, [15] error
+__global__ void __launch_bounds__(256) k_grid_bounds(GridBuild G) {
+    const int kind = blockIdx.y;
+    const int n = *G.n_map[kind];
+    const Pt* m = G.map[kind];
+    unsigned mn[3] = {0u, 0u, 0u}, mx[3] = {0u, 0u, 0u};
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        Pt p = m[i];
+        unsigned kx = f2ord_k(p.x), ky = f2ord_k(p.y), kz = f2ord_k(p.z);
+        mn[0] = max(mn[0], ~kx); mn[1] = max(mn[1], ~ky); mn[2] = max(mn[2], ~kz);
+        mx[0] = max(mx[0], kx); mx[1] = max(mx[1], ky); mx[2] = max(mx[2], kz);
+    }
+    __shared__ unsigned red[8][6];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        mn[a] = __reduce_max_sync(0xffffffffu, mn[a]);
+        mx[a] = __reduce_max_sync(0xffffffffu, mx[a]);
+    }
+    if (lane == 0) for (int a = 0; a < 3; ++a) { red[w][a] = mn[a]; red[w][3 + a] = mx[a]; }
+    __syncthreads();
+    if (threadIdx.x < 6) {
+        unsigned v = 0;
+        for (int k = 0; k < 8; ++k) v = max(v, red[k][threadIdx.x]);
+        if (v) atomicMax(&G.state[kind * 6 + threadIdx.x], v);
+    }
+}
+
+// one block per map: origin / dims from the bounds
+__global__ void k_grid_geom(GridBuild G) {
+    const int kind = blockIdx.x;
+    if (threadIdx.x != 0) return;
+    const unsigned* s = G.state + kind * 6;
+    int* geom = G.geom[kind];
+    const int n = *G.n_map[kind];
+    if (kind == 0) reinterpret_cast<int*>(G.state)[14] = *G.n_map[0] + *G.n_map[1];
+    if (n == 0 || s[3] == 0u) {
+        for (int a = 0; a < 3; ++a) { geom[a] = 0; geom[3 + a] = 0; }
+        return;
+    }
+    long long prod = 1;
+    for (int a = 0; a < 3; ++a) {
+        const float lo = floorf(ord2f_k(~s[a])), hi = floorf(ord2f_k(s[3 + a]));
+        const long long o = (long long)fminf(fmaxf(lo, -1.0e9f), 1.0e9f), e = (long long)fminf(fmaxf(hi, -1.0e9f), 1.0e9f);
+        const long long d = e - o + 1;
+        geom[a] = (int)o;
+        geom[3 + a] = (int)(d > 0x7fffffff ? 0x7fffffff : d);
+        prod = (d > (1ll << 40) || prod > (1ll << 40)) ? (1ll << 41) : prod * d;
+    }
+    if (prod > kGridCellCap) {   // map extent larger than the search grid capacity
+        atomicOr(&G.state[15], 1u);
+        for (int a = 0; a < 3; ++a) geom[3 + a] = 0;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_grid_keys_clear(GridBuild G, uint32_t* __restrict__ keys) {
+    const int kind = blockIdx.y;
+    const int n = *G.n_map[kind];
+    const int base = kind == 0 ? 0 : *G.n_map[0];
+    const int* geom = G.geom[kind];
+    const int ox = geom[0], oy = geom[1], oz = geom[2], dx = geom[3], dy = geom[4], dz = geom[5];
+    const long long cells = (long long)dx * dy * dz;
+    const Pt* m = G.map[kind];
+    const int stride = gridDim.x * blockDim.x, t0 = blockIdx.x * blockDim.x + threadIdx.x;
+    for (int i = t0; i < n; i += stride) {
+        Pt p = m[i];
+        unsigned key = 0xffffffffu;
+        if (cells > 0) {
+            const int cx = (int)floorf(p.x) - ox, cy = (int)floorf(p.y) - oy, cz = (int)floorf(p.z) - oz;
+            key = (unsigned)(cx + (cy + cz * dy) * dx) | ((unsigned)kind << 23);
+        }
+        keys[base + i] = key;
+    }
+    int* cs = G.cell_start[kind];
+    int* ce = G.cell_end[kind];
+    for (long long c = t0; c < cells; c += stride) { cs[c] = 0; ce[c] = 0; }
+}
+
+__global__ void __launch_bounds__(256) k_grid_fill(GridBuild G, const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals) {
+    const int kind = blockIdx.y;
+    const int n = *G.n_map[kind];
+    const int n0 = *G.n_map[0];
+    const int start = kind == 0 ? 0 : n0;     // both maps are sorted jointly: map 0 first (bit 23 clear)
+    const Pt* m = G.map[kind];
+    if (G.geom[kind][3] == 0) return;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int p = start + i;
+        const unsigned key = keys[p];
+        const int orig = (int)vals[p] - start;
+        const Pt v = m[orig];
+        G.pts[kind][i] = make_float4(v.x, v.y, v.z, __int_as_float(orig));
+        const unsigned cell = key & ((1u << 23) - 1u);
+        if (i == 0 || keys[p - 1] != key) G.cell_start[kind][cell] = i;
+        if (i == n - 1 || keys[p + 1] != key) G.cell_end[kind][cell] = i + 1;
+    }
+}
+
+int build_grids(Workspace& ws, const GridBuild& G_in, int slot, int cap0, int cap1) {
+    GridBuild G = G_in;
+    G.state = ws.ctrl + kSlotBase + slot * kSlotWords;
+    const int cap = cap0 + cap1;
+    PF_REQUIRE(cap <= ws.cap, "build_grids: %d points exceed workspace capacity %d", cap, ws.cap);
+    const int capmax = cap0 > cap1 ? cap0 : cap1;
+    int nblk = div_up(capmax, 256 * 4);
+    if (nblk > 4 * kSMs) nblk = 4 * kSMs;
+    if (nblk < 1) nblk = 1;
+    k_grid_bounds<<<dim3(nblk, 2), 256, 0, ws.stream>>>(G);
+    k_grid_geom<<<2, 32, 0, ws.stream>>>(G);
+    k_grid_keys_clear<<<dim3(4 * kSMs, 2), 256, 0, ws.stream>>>(G, ws.keys[0]);
+    ws.launches += 3;
+    int rb = 0;
+    PF_CHECK(radix_sort(ws, reinterpret_cast<const int*>(G.state) + 14, cap, 3, true, &rb));
+    k_grid_fill<<<dim3(nblk, 2), 256, 0, ws.stream>>>(G, ws.keys[rb], ws.vals[rb]);
+    ws.launches += 1;
+    PF_CUDA(cudaGetLastError());
+    return PF_OK;
+}
+
+__global__ void __launch_bounds__(256) k_knn5_tap(KnnGrid g, const float4* __restrict__ q, int nq, int* __restrict__ idx_out,
+                                                  float* __restrict__ d2_out) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (warp >= nq) return;
+    const float4 p = q[warp];
+    int idx[5];
+    float d2[5];
+    const bool ok = knn5_warp(g, p.x, p.y, p.z, idx, d2);
+    const unsigned lane = lane_id();
+    if (lane < 5) {
+        idx_out[5 * warp + lane] = ok ? idx[lane] : -1;
+        d2_out[5 * warp + lane] = ok ? d2[lane] : __int_as_float(0x7f800000);
+    }
+}
+
+}  // namespace pf
+
+using namespace pf;
+
+namespace {
+struct KnnTap {
+    cudaStream_t stream = nullptr;
+    Workspace ws;
+    Pt* d_map = nullptr;
+    float4 *d_pts = nullptr, *d_q = nullptr;
+    int *d_cs = nullptr, *d_ce = nullptr, *d_geom = nullptr, *d_counts = nullptr, *d_idx = nullptr;
+    float* d_d2 = nullptr;
+    ~KnnTap() {
+        workspace_destroy(ws);
+        cudaFree(d_map); cudaFree(d_pts); cudaFree(d_q); cudaFree(d_cs); cudaFree(d_ce); cudaFree(d_geom); cudaFree(d_counts);
+        cudaFree(d_idx); cudaFree(d_d2);
+        if (stream) cudaStreamDestroy(stream);
+    }
+};
+}  // namespace
+
+extern "C" int pf_knn5(int device, const pf_point* map, int m, const float* queries_xyz4, int q, int32_t* idx, float* d2) {
+    PF_REQUIRE(m >= 0 && q >= 0 && (map || m == 0) && (queries_xyz4 || q == 0) && idx && d2, "bad argument");
+    PF_CUDA(cudaSetDevice(device));
+    KnnTap t;
+    PF_CUDA(cudaStreamCreateWithFlags(&t.stream, cudaStreamNonBlocking));
+    const int mc = m > 0 ? m : 1, qc = q > 0 ? q : 1;
+    PF_CHECK(workspace_create(t.ws, mc, t.stream));
+    PF_CUDA(cudaMalloc(&t.d_map, sizeof(Pt) * mc));
+    PF_CUDA(cudaMalloc(&t.d_pts, sizeof(float4) * mc));
+    PF_CUDA(cudaMalloc(&t.d_q, sizeof(float4) * qc));
+    PF_CUDA(cudaMalloc(&t.d_cs, sizeof(int) * (size_t)kGridCellCap));
+    PF_CUDA(cudaMalloc(&t.d_ce, sizeof(int) * (size_t)kGridCellCap));
+    PF_CUDA(cudaMalloc(&t.d_geom, sizeof(int) * 12));
+    PF_CUDA(cudaMalloc(&t.d_counts, sizeof(int) * 2));
+    PF_CUDA(cudaMalloc(&t.d_idx, sizeof(int) * 5 * qc));
+    PF_CUDA(cudaMalloc(&t.d_d2, sizeof(float) * 5 * qc));
+    int counts[2] = {m, 0};
+    PF_CUDA(cudaMemcpyAsync(t.d_counts, counts, sizeof(counts), cudaMemcpyHostToDevice, t.stream));
+    if (m) PF_CUDA(cudaMemcpyAsync(t.d_map, map, sizeof(Pt) * m, cudaMemcpyHostToDevice, t.stream));
+    if (q) PF_CUDA(cudaMemcpyAsync(t.d_q, queries_xyz4, sizeof(float4) * q, cudaMemcpyHostToDevice, t.stream));
+    GridBuild G{};
+    G.map[0] = t.d_map; G.map[1] = t.d_map;
+    G.n_map[0] = t.d_counts; G.n_map[1] = t.d_counts + 1;
+    G.pts[0] = t.d_pts; G.pts[1] = t.d_pts;
+    G.cell_start[0] = t.d_cs; G.cell_start[1] = t.d_cs;
+    G.cell_end[0] = t.d_ce; G.cell_end[1] = t.d_ce;
+    G.geom[0] = t.d_geom; G.geom[1] = t.d_geom + 6;
+    PF_CHECK(workspace_begin_step(t.ws));
+    PF_CHECK(build_grids(t.ws, G, 0, mc, 0));
+    KnnGrid g{t.d_pts, t.d_cs, t.d_ce, t.d_geom};
+    if (q) k_knn5_tap<<<div_up(q, 8), 256, 0, t.stream>>>(g, t.d_q, q, t.d_idx, t.d_d2);
+    unsigned err = 0;
+    PF_CUDA(cudaMemcpyAsync(&err, t.ws.ctrl + kSlotBase + 15, sizeof(unsigned), cudaMemcpyDeviceToHost, t.stream));
+    if (q) {
+        PF_CUDA(cudaMemcpyAsync(idx, t.d_idx, sizeof(int) * 5 * q, cudaMemcpyDeviceToHost, t.stream));
+        PF_CUDA(cudaMemcpyAsync(d2, t.d_d2, sizeof(float) * 5 * q, cudaMemcpyDeviceToHost, t.stream));
+    }
+    PF_CUDA(cudaStreamSynchronize(t.stream));
+    if (err) { set_error("map extent exceeds the search grid capacity (%d cells of 1 m)", kGridCellCap); return PF_ERR_CAPACITY; }
+    return PF_OK;
+}

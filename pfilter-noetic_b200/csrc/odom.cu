@@ -1,0 +1,469 @@
+// Odometry + persistence filter + local map: device-resident replacement of Odom_ES_EstimationClass
+// (/root/reference/include/odomEstimationClass.h:140-167, src/odomEstimationClass.cpp:182-282, :589-647).
+//
+// One pf_odom_update enqueues, on the handle's stream and without any host round trip in between:
+//   k_predict        constant-velocity prediction odom * (last^-1 * odom)                         (:235-240)
+//   voxelize(PCL)    VoxelGrid down-sampling of both feature clouds, leaf 0.4 / 0.8                (:244-245)
+//   build_grids      1 m search grids over both local maps (stands in for the two kd-tree builds)  (:249-250)
+//   optimization_count x { associate_pass (kNN + line/plane fit + persistence counters), 5 x k_lm_eval }   (:252-272)
+//   k_append         transform all down-sampled points with the final pose and append them to the maps      (:592-604)
+//   voxelize(MAP)    CropBox + rgbds + extractstablepoint + r += 2                                 (:606-647)
+// and finally copies the 7-double pose to the host.  Maps, counters and the pose stay in HBM between frames.
+#include <vector>
+
+#include "match.cuh"
+#include "math.cuh"
+#include "solve.cuh"
+#include "voxel.cuh"
+
+namespace pf {
+
+struct IsoDev { double R[9]; double t[3]; };
+
+struct OdomShared {   // small device-resident block
+    IsoDev odom, last_odom;
+    double pose[7];        // pose of the last finished update (what the caller reads)
+    int n_app[2];          // map sizes after appending the new points
+    int err;               // bit 0: map capacity exceeded
+    int pad;
+};
+
+__global__ void k_odom_reset(OdomShared* sh, LmState* S) {
+    if (threadIdx.x != 0) return;
+    for (int i = 0; i < 9; ++i) { sh->odom.R[i] = (i % 4 == 0) ? 1.0 : 0.0; sh->last_odom.R[i] = sh->odom.R[i]; }
+    for (int i = 0; i < 3; ++i) { sh->odom.t[i] = 0; sh->last_odom.t[i] = 0; }
+    const double id[7] = {0, 0, 0, 1, 0, 0, 0};
+    for (int i = 0; i < 7; ++i) { sh->pose[i] = id[i]; S->x[i] = id[i]; }
+    sh->n_app[0] = sh->n_app[1] = 0;
+    sh->err = 0;
+}
+
+// odom_prediction = odom * (last_odom.inverse() * odom); last_odom = odom; odom = prediction;
+// q_w_curr = Quaterniond(odom.rotation()); t_w_curr = odom.translation()                     (:235-240)
+__global__ void k_predict(OdomShared* sh, LmState* S) {
+    if (threadIdx.x != 0) return;
+    const IsoDev a = sh->odom, l = sh->last_odom;
+    IsoDev li, m, p;
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) li.R[3 * i + j] = l.R[3 * j + i];
+    for (int i = 0; i < 3; ++i) li.t[i] = -(li.R[3 * i] * l.t[0] + li.R[3 * i + 1] * l.t[1] + li.R[3 * i + 2] * l.t[2]);
+    auto mul = [](const IsoDev& x, const IsoDev& y, IsoDev& o) {
+        for (int i = 0; i < 3; ++i) {
+            for (int j = 0; j < 3; ++j) o.R[3 * i + j] = x.R[3 * i] * y.R[j] + x.R[3 * i + 1] * y.R[3 + j] + x.R[3 * i + 2] * y.R[6 + j];
+            o.t[i] = x.R[3 * i] * y.t[0] + x.R[3 * i + 1] * y.t[1] + x.R[3 * i + 2] * y.t[2] + x.t[i];
+        }
+    };
+    mul(li, a, m);
+    mul(a, m, p);
+    sh->last_odom = a;
+    sh->odom = p;
+    double q[4];
+    mat_to_quat(p.R, q);
+    for (int i = 0; i < 4; ++i) S->x[i] = q[i];
+    for (int i = 0; i < 3; ++i) S->x[4 + i] = p.t[i];
+}
+
+struct AppendParams {
+    const Pt* ds[2]; const int* n_ds[2];
+    Pt* map[2]; const int* n_map[2];
+    OdomShared* sh; const LmState* S;
+    int map_cap;      // capacity of the map buffers (points)
+};
+
+// odom <- (q_w_curr, t_w_curr) (:278-280) and addPointsToMap's append loop (:592-604)
+__global__ void __launch_bounds__(256) k_append(AppendParams A) {
+    const int kind = blockIdx.y;
+    __shared__ double s_pose[7];
+    if (threadIdx.x < 7) s_pose[threadIdx.x] = A.S->x[threadIdx.x];
+    __syncthreads();
+    const int n = *A.n_ds[kind], m = *A.n_map[kind];
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        int tot = m + n;
+        if (tot > A.map_cap) { atomicOr(&A.sh->err, 1); tot = A.map_cap; }
+        A.sh->n_app[kind] = tot;
+        if (kind == 0) {
+            quat_to_mat(s_pose, A.sh->odom.R);
+            for (int i = 0; i < 3; ++i) A.sh->odom.t[i] = s_pose[4 + i];
+            for (int i = 0; i < 7; ++i) A.sh->pose[i] = s_pose[i];
+        }
+    }
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        if (m + i >= A.map_cap) break;
+        const Pt q = A.ds[kind][i];
+        const D3 w = pose_apply(s_pose, d3((double)q.x, (double)q.y, (double)q.z));
+        Pt o;
+        o.x = (float)w.x; o.y = (float)w.y; o.z = (float)w.z;
+        o.rgba = (q.rgba & 0x00ffffffu) | 0xff000000u;   // r, g, b copied (:169-171), a = 255 of a fresh PointXYZRGB
+        A.map[kind][m + i] = o;
+    }
+}
+
+struct InitParams { const float4* feat[2]; const int* n_feat[2]; Pt* map[2]; int* n_map[2]; int map_cap; OdomShared* sh; };
+
+// initMapWithPoints (:217-222): the raw first-frame clouds become the maps
+__global__ void __launch_bounds__(256) k_init_map(InitParams I) {
+    const int kind = blockIdx.y;
+    int n = *I.n_feat[kind];
+    if (n > I.map_cap) { n = I.map_cap; if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(&I.sh->err, 1); }
+    if (blockIdx.x == 0 && threadIdx.x == 0) *I.n_map[kind] = n;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float4 f = I.feat[kind][i];
+        Pt o;
+        o.x = f.x; o.y = f.y; o.z = f.z; o.rgba = pack_rgba(0, 0, 0, 255);
+        I.map[kind][i] = o;
+    }
+}
+
+__global__ void k_check_map_cap(const int* n_map0, const int* n_map1, int cap, OdomShared* sh) {
+    if (threadIdx.x == 0 && (*n_map0 > cap || *n_map1 > cap)) atomicOr(&sh->err, 1);
+}
+
+}  // namespace pf
+
+using namespace pf;
+
+// accessors implemented in extract.cu
+void pf_extract_device_outputs(pf_extract* h, const float4** edge, const int** n_edge, const float4** surf, const int** n_surf,
+                               cudaStream_t* stream, int* edge_cap, int* surf_cap);
+int pf_extract_enqueue_single(pf_extract* h, const float* xyzi, int n);
+
+struct pf_odom {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev = nullptr;
+    pf_odom_params prm{};
+    int fcap = 0, mcap = 0, bufcap = 0;
+    Workspace ws;
+    float4* d_feat[2] = {nullptr, nullptr};
+    int* d_nfeat = nullptr;              // [2]
+    Pt* d_ds[2] = {nullptr, nullptr};
+    int* d_nds = nullptr;                // [2]
+    Pt* d_map[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // [buffer][kind]
+    int* d_nmap[2] = {nullptr, nullptr}; // [buffer] -> 2 ints
+    int cur = 0;
+    float4* d_gpts[2] = {nullptr, nullptr};
+    int *d_cs[2] = {nullptr, nullptr}, *d_ce[2] = {nullptr, nullptr}, *d_geom = nullptr;
+    int *d_head[2] = {nullptr, nullptr}, *d_hits[2] = {nullptr, nullptr}, *d_next[2] = {nullptr, nullptr}, *d_nn[2] = {nullptr, nullptr};
+    uint8_t* d_flag[2] = {nullptr, nullptr};
+    double* d_g8[2] = {nullptr, nullptr};
+    LmState* d_state = nullptr;
+    double *d_partials = nullptr, *d_iter_poses = nullptr;
+    unsigned* d_ticket = nullptr;
+    OdomShared* d_sh = nullptr;
+    // pinned host mirrors
+    OdomShared* h_sh = nullptr;
+    LmState* h_state = nullptr;
+    int* h_counts = nullptr;             // [8]
+    double* h_iter = nullptr;            // [16*7]
+    bool inited = false;
+    int optimization_count = 2;          // :198
+    int last_passes = 0;
+};
+
+namespace {
+
+int odom_alloc(pf_odom* h) {
+    const int fcap = h->fcap, bufcap = h->bufcap;
+    PF_CHECK(workspace_create(h->ws, 2 * bufcap, h->stream));
+    PF_CUDA(cudaMalloc(&h->d_nfeat, sizeof(int) * 2));
+    PF_CUDA(cudaMalloc(&h->d_nds, sizeof(int) * 2));
+    PF_CUDA(cudaMalloc(&h->d_geom, sizeof(int) * 12));
+    for (int k = 0; k < 2; ++k) {
+        PF_CUDA(cudaMalloc(&h->d_feat[k], sizeof(float4) * fcap));
+        PF_CUDA(cudaMalloc(&h->d_ds[k], sizeof(Pt) * fcap));
+        for (int b = 0; b < 2; ++b) PF_CUDA(cudaMalloc(&h->d_map[b][k], sizeof(Pt) * bufcap));
+        PF_CUDA(cudaMalloc(&h->d_nmap[k], sizeof(int) * 2));
+        PF_CUDA(cudaMemset(h->d_nmap[k], 0, sizeof(int) * 2));
+        PF_CUDA(cudaMalloc(&h->d_gpts[k], sizeof(float4) * bufcap));
+        PF_CUDA(cudaMalloc(&h->d_cs[k], sizeof(int) * (size_t)kGridCellCap));
+        PF_CUDA(cudaMalloc(&h->d_ce[k], sizeof(int) * (size_t)kGridCellCap));
+        PF_CUDA(cudaMalloc(&h->d_head[k], sizeof(int) * bufcap));
+        PF_CUDA(cudaMalloc(&h->d_hits[k], sizeof(int) * bufcap));
+        PF_CUDA(cudaMemset(h->d_head[k], 0xff, sizeof(int) * bufcap));
+        PF_CUDA(cudaMemset(h->d_hits[k], 0, sizeof(int) * bufcap));
+        PF_CUDA(cudaMalloc(&h->d_next[k], sizeof(int) * 5 * fcap));
+        PF_CUDA(cudaMalloc(&h->d_nn[k], sizeof(int) * 5 * fcap));
+        PF_CUDA(cudaMalloc(&h->d_flag[k], fcap));
+        PF_CUDA(cudaMemset(h->d_flag[k], 0, fcap));
+        PF_CUDA(cudaMalloc(&h->d_g8[k], sizeof(double) * 8 * fcap));
+    }
+    PF_CUDA(cudaMalloc(&h->d_state, sizeof(LmState)));
+    PF_CUDA(cudaMemset(h->d_state, 0, sizeof(LmState)));
+    PF_CUDA(cudaMalloc(&h->d_partials, sizeof(double) * 32 * kLmBlocks));
+    PF_CUDA(cudaMalloc(&h->d_iter_poses, sizeof(double) * 16 * 7));
+    PF_CUDA(cudaMemset(h->d_iter_poses, 0, sizeof(double) * 16 * 7));
+    PF_CUDA(cudaMalloc(&h->d_ticket, sizeof(unsigned)));
+    PF_CUDA(cudaMemset(h->d_ticket, 0, sizeof(unsigned)));
+    PF_CUDA(cudaMalloc(&h->d_sh, sizeof(OdomShared)));
+    PF_CUDA(cudaMallocHost(&h->h_sh, sizeof(OdomShared)));
+    PF_CUDA(cudaMallocHost(&h->h_state, sizeof(LmState)));
+    PF_CUDA(cudaMallocHost(&h->h_counts, sizeof(int) * 8));
+    PF_CUDA(cudaMallocHost(&h->h_iter, sizeof(double) * 16 * 7));
+    k_odom_reset<<<1, 32, 0, h->stream>>>(h->d_sh, h->d_state);
+    PF_CUDA(cudaStreamSynchronize(h->stream));
+    return PF_OK;
+}
+
+int upload_features(pf_odom* h, const float* edge, int ne, const float* surf, int ns) {
+    PF_REQUIRE(ne >= 0 && ns >= 0 && (edge || ne == 0) && (surf || ns == 0), "bad feature arrays");
+    PF_REQUIRE(ne <= h->fcap && ns <= h->fcap, "feature cloud (%d / %d points) exceeds max_features %d", ne, ns, h->fcap);
+    h->h_counts[0] = ne; h->h_counts[1] = ns;
+    PF_CUDA(cudaMemcpyAsync(h->d_nfeat, h->h_counts, sizeof(int) * 2, cudaMemcpyHostToDevice, h->stream));
+    if (ne) PF_CUDA(cudaMemcpyAsync(h->d_feat[0], edge, sizeof(float4) * ne, cudaMemcpyHostToDevice, h->stream));
+    if (ns) PF_CUDA(cudaMemcpyAsync(h->d_feat[1], surf, sizeof(float4) * ns, cudaMemcpyHostToDevice, h->stream));
+    return PF_OK;
+}
+
+int enqueue_init(pf_odom* h, const float4* const feat[2], const int* const n_feat[2]) {
+    InitParams I{};
+    for (int k = 0; k < 2; ++k) { I.feat[k] = feat[k]; I.n_feat[k] = n_feat[k]; I.map[k] = h->d_map[h->cur][k]; I.n_map[k] = h->d_nmap[h->cur] + k; }
+    I.map_cap = h->mcap;
+    I.sh = h->d_sh;
+    k_init_map<<<dim3(2 * kSMs, 2), 256, 0, h->stream>>>(I);
+    h->ws.launches += 1;
+    PF_CUDA(cudaGetLastError());
+    h->optimization_count = 12;   // :221
+    h->inited = true;
+    return PF_OK;
+}
+
+int enqueue_update(pf_odom* h, const float4* const feat[2], const int* const n_feat[2], int fcap_in) {
+    if (h->optimization_count > 2) h->optimization_count--;   // :232-233
+    const int passes = h->optimization_count;
+    h->last_passes = passes;
+    Workspace& ws = h->ws;
+    const int cur = h->cur, nxt = cur ^ 1;
+    PF_CHECK(workspace_begin_step(ws));
+    k_predict<<<1, 32, 0, h->stream>>>(h->d_sh, h->d_state);
+    ws.launches += 1;
+    // VoxelGrid down-sampling, leaf sizes as set by init (:189-190): setLeafSize takes floats
+    VoxParams V{};
+    V.mode = VOX_PCL;
+    const float leaf[2] = {(float)h->prm.map_resolution, (float)(h->prm.map_resolution * 2)};
+    for (int k = 0; k < 2; ++k)
+        V.c[k] = VoxCloud{reinterpret_cast<const Pt*>(feat[k]), n_feat[k], h->d_ds[k], h->d_nds + k, leaf[k], 1};
+    PF_CHECK(voxelize(ws, V, 0, fcap_in, fcap_in));
+    // search grids over the current maps
+    GridBuild G{};
+    for (int k = 0; k < 2; ++k) {
+        G.map[k] = h->d_map[cur][k]; G.n_map[k] = h->d_nmap[cur] + k; G.pts[k] = h->d_gpts[k];
+        G.cell_start[k] = h->d_cs[k]; G.cell_end[k] = h->d_ce[k]; G.geom[k] = h->d_geom + 6 * k;
+    }
+    PF_CHECK(build_grids(ws, G, 2, h->mcap, h->mcap));
+    // optimisation passes
+    AssocParams A{};
+    LmParams L{};
+    for (int k = 0; k < 2; ++k) {
+        A.c[k] = AssocCloud{h->d_ds[k], h->d_nds + k, h->d_map[cur][k], h->d_nmap[cur] + k,
+                            KnnGrid{h->d_gpts[k], h->d_cs[k], h->d_ce[k], h->d_geom + 6 * k},
+                            h->d_head[k], h->d_hits[k], h->d_next[k], h->d_nn[k], h->d_flag[k], h->d_g8[k]};
+        L.src[k] = ResidualSrc{h->d_ds[k], nullptr, h->d_flag[k], h->d_g8[k], h->d_nds + k};
+    }
+    A.pose = h->d_state->x;
+    A.k_new = h->prm.k_new; A.theta_p = h->prm.theta_p; A.theta_max = h->prm.theta_max;
+    A.min_edge_map = 10; A.min_surf_map = 50;   // :247
+    L.state = h->d_state; L.partials = h->d_partials; L.ticket = h->d_ticket; L.iter_poses = h->d_iter_poses; L.eval_only = 0;
+    for (int it = 0; it < passes; ++it) {
+        PF_CHECK(lm_begin(h->stream, L, nullptr, it == 0, &ws.launches));
+        PF_CHECK(associate_pass(h->stream, A, fcap_in, fcap_in, &ws.launches));
+        for (int e = 0; e < kLmEvalsPerSolve; ++e) PF_CHECK(lm_eval(h->stream, L, &ws.launches));
+    }
+    // append + map maintenance
+    AppendParams P{};
+    for (int k = 0; k < 2; ++k) { P.ds[k] = h->d_ds[k]; P.n_ds[k] = h->d_nds + k; P.map[k] = h->d_map[cur][k]; P.n_map[k] = h->d_nmap[cur] + k; }
+    P.sh = h->d_sh; P.S = h->d_state; P.map_cap = h->bufcap;
+    k_append<<<dim3(kSMs, 2), 256, 0, h->stream>>>(P);
+    ws.launches += 1;
+    VoxParams M{};
+    M.mode = VOX_MAP;
+    // rgbds(tmpSurf, map_resolution * 2) / rgbds(tmpCorner, map_resolution) with the float member map_resolution (:625-626)
+    const float mres = (float)h->prm.map_resolution;
+    const float mleaf[2] = {mres, mres * 2};
+    for (int k = 0; k < 2; ++k)
+        M.c[k] = VoxCloud{h->d_map[cur][k], h->d_sh->n_app + k, h->d_map[nxt][k], h->d_nmap[nxt] + k, mleaf[k], 0};
+    M.center = h->d_sh->odom.t;
+    M.k_new = h->prm.k_new; M.theta_p = h->prm.theta_p; M.theta_max = h->prm.theta_max;
+    PF_CHECK(voxelize(ws, M, 1, h->bufcap, h->bufcap));
+    k_check_map_cap<<<1, 32, 0, h->stream>>>(h->d_nmap[nxt], h->d_nmap[nxt] + 1, h->mcap, h->d_sh);
+    ws.launches += 1;
+    PF_CUDA(cudaGetLastError());
+    h->cur = nxt;
+    return PF_OK;
+}
+
+int finish_frame(pf_odom* h, double pose_out[7]) {
+    PF_CUDA(cudaMemcpyAsync(h->h_sh, h->d_sh, sizeof(OdomShared), cudaMemcpyDeviceToHost, h->stream));
+    PF_CUDA(cudaStreamSynchronize(h->stream));
+    if (h->h_sh->err & 1) {
+        set_error("local map exceeded max_map_points = %d", h->mcap);
+        return PF_ERR_CAPACITY;
+    }
+    if (pose_out) memcpy(pose_out, h->h_sh->pose, sizeof(double) * 7);
+    return PF_OK;
+}
+
+}  // namespace
+
+extern "C" int pf_odom_create(const pf_odom_params* p, int device, pf_odom** out) {
+    PF_REQUIRE(p && out, "null argument");
+    PF_REQUIRE(p->map_resolution > 0, "map_resolution must be positive");
+    PF_REQUIRE(p->weight_type == 0.0, "weight_type %g: only 0 (the class default) is implemented in this round", p->weight_type);
+    int ndev = 0;
+    PF_CUDA(cudaGetDeviceCount(&ndev));
+    PF_REQUIRE(device >= 0 && device < ndev, "device %d not available (%d devices)", device, ndev);
+    PF_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    PF_CUDA(cudaGetDeviceProperties(&prop, device));
+    PF_REQUIRE(prop.major == 10, "pfilter_b200 needs an sm_100a device, found sm_%d%d", prop.major, prop.minor);
+    pf_odom* h = new pf_odom();
+    h->device = device;
+    h->prm = *p;
+    h->fcap = p->max_features > 0 ? p->max_features : 131072;
+    h->mcap = p->max_map_points > 0 ? p->max_map_points : (2 << 20);
+    if (h->mcap < h->fcap) h->mcap = h->fcap;   // the raw first-frame clouds become the maps (:217-222)
+    h->bufcap = h->mcap + h->fcap;
+    PF_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    PF_CUDA(cudaEventCreateWithFlags(&h->ev, cudaEventDisableTiming));
+    int rc = odom_alloc(h);
+    if (rc != PF_OK) { pf_odom_destroy(h); return rc; }
+    *out = h;
+    return PF_OK;
+}
+
+extern "C" int pf_odom_destroy(pf_odom* h) {
+    if (!h) return PF_OK;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    workspace_destroy(h->ws);
+    cudaFree(h->d_nfeat); cudaFree(h->d_nds); cudaFree(h->d_geom);
+    for (int k = 0; k < 2; ++k) {
+        cudaFree(h->d_feat[k]); cudaFree(h->d_ds[k]); cudaFree(h->d_map[0][k]); cudaFree(h->d_map[1][k]); cudaFree(h->d_nmap[k]);
+        cudaFree(h->d_gpts[k]); cudaFree(h->d_cs[k]); cudaFree(h->d_ce[k]); cudaFree(h->d_head[k]); cudaFree(h->d_hits[k]);
+        cudaFree(h->d_next[k]); cudaFree(h->d_nn[k]); cudaFree(h->d_flag[k]); cudaFree(h->d_g8[k]);
+    }
+    cudaFree(h->d_state); cudaFree(h->d_partials); cudaFree(h->d_iter_poses); cudaFree(h->d_ticket); cudaFree(h->d_sh);
+    cudaFreeHost(h->h_sh); cudaFreeHost(h->h_state); cudaFreeHost(h->h_counts); cudaFreeHost(h->h_iter);
+    if (h->ev) cudaEventDestroy(h->ev);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return PF_OK;
+}
+
+extern "C" int pf_odom_init_map(pf_odom* h, const float* edge, int n_edge, const float* surf, int n_surf) {
+    PF_REQUIRE(h, "null handle");
+    PF_CUDA(cudaSetDevice(h->device));
+    PF_CHECK(upload_features(h, edge, n_edge, surf, n_surf));
+    const float4* feat[2] = {h->d_feat[0], h->d_feat[1]};
+    const int* nf[2] = {h->d_nfeat, h->d_nfeat + 1};
+    PF_CHECK(enqueue_init(h, feat, nf));
+    return finish_frame(h, nullptr);
+}
+
+extern "C" int pf_odom_update(pf_odom* h, const float* edge, int n_edge, const float* surf, int n_surf, double pose_out[7]) {
+    PF_REQUIRE(h, "null handle");
+    if (!h->inited) { set_error("pf_odom_update before pf_odom_init_map"); return PF_ERR_STATE; }
+    PF_CUDA(cudaSetDevice(h->device));
+    PF_CHECK(upload_features(h, edge, n_edge, surf, n_surf));
+    const float4* feat[2] = {h->d_feat[0], h->d_feat[1]};
+    const int* nf[2] = {h->d_nfeat, h->d_nfeat + 1};
+    PF_CHECK(enqueue_update(h, feat, nf, h->fcap));
+    return finish_frame(h, pose_out);
+}
+
+extern "C" int pf_odom_process_extracted(pf_odom* h, pf_extract* ex, double pose_out[7]) {
+    PF_REQUIRE(h && ex, "null handle");
+    PF_CUDA(cudaSetDevice(h->device));
+    const float4* feat[2];
+    const int* nf[2];
+    cudaStream_t exs;
+    int ecap, scap;
+    pf_extract_device_outputs(ex, &feat[0], &nf[0], &feat[1], &nf[1], &exs, &ecap, &scap);
+    PF_REQUIRE(scap <= h->fcap, "extractor capacity %d exceeds max_features %d", scap, h->fcap);
+    PF_CUDA(cudaEventRecord(h->ev, exs));
+    PF_CUDA(cudaStreamWaitEvent(h->stream, h->ev, 0));
+    if (!h->inited) {
+        PF_CHECK(enqueue_init(h, feat, nf));
+    } else {
+        PF_CHECK(enqueue_update(h, feat, nf, scap));
+    }
+    return finish_frame(h, pose_out);
+}
+
+extern "C" int pf_frame_process(pf_extract* ex, pf_odom* od, const float* xyzi, int n, double pose_out[7]) {
+    PF_REQUIRE(ex && od, "null handle");
+    PF_CHECK(pf_extract_enqueue_single(ex, xyzi, n));
+    return pf_odom_process_extracted(od, ex, pose_out);
+}
+
+extern "C" int pf_odom_get_pose(pf_odom* h, double pose[7]) {
+    PF_REQUIRE(h && pose, "null argument");
+    PF_CUDA(cudaSetDevice(h->device));
+    return finish_frame(h, pose);
+}
+
+extern "C" int pf_odom_map_size(pf_odom* h, int which, int* n) {
+    PF_REQUIRE(h && n && (which == 0 || which == 1), "bad argument");
+    PF_CUDA(cudaSetDevice(h->device));
+    PF_CUDA(cudaMemcpyAsync(h->h_counts, h->d_nmap[h->cur], sizeof(int) * 2, cudaMemcpyDeviceToHost, h->stream));
+    PF_CUDA(cudaStreamSynchronize(h->stream));
+    *n = h->h_counts[which];
+    return PF_OK;
+}
+
+extern "C" int pf_odom_get_map_part(pf_odom* h, int which, pf_point* out, int cap, int* n) {
+    PF_REQUIRE(h && out && n && (which == 0 || which == 1), "bad argument");
+    int m = 0;
+    PF_CHECK(pf_odom_map_size(h, which, &m));
+    PF_REQUIRE(m <= cap, "map has %d points, buffer holds %d", m, cap);
+    if (m) PF_CUDA(cudaMemcpy(out, h->d_map[h->cur][which], sizeof(Pt) * m, cudaMemcpyDeviceToHost));
+    *n = m;
+    return PF_OK;
+}
+
+// getMap (:210-215): surf map, then corner map
+extern "C" int pf_odom_get_map(pf_odom* h, pf_point* out, int cap, int* n) {
+    PF_REQUIRE(h && out && n, "bad argument");
+    int ns = 0, ne = 0;
+    PF_CHECK(pf_odom_map_size(h, 1, &ns));
+    PF_CHECK(pf_odom_map_size(h, 0, &ne));
+    PF_REQUIRE(ns + ne <= cap, "map has %d points, buffer holds %d", ns + ne, cap);
+    if (ns) PF_CUDA(cudaMemcpy(out, h->d_map[h->cur][1], sizeof(Pt) * ns, cudaMemcpyDeviceToHost));
+    if (ne) PF_CUDA(cudaMemcpy(out + ns, h->d_map[h->cur][0], sizeof(Pt) * ne, cudaMemcpyDeviceToHost));
+    *n = ns + ne;
+    return PF_OK;
+}
+
+extern "C" int pf_odom_get_iter_poses(pf_odom* h, double* poses, int cap, int* n) {
+    PF_REQUIRE(h && poses && n, "bad argument");
+    PF_CUDA(cudaSetDevice(h->device));
+    PF_CUDA(cudaMemcpyAsync(h->h_iter, h->d_iter_poses, sizeof(double) * 16 * 7, cudaMemcpyDeviceToHost, h->stream));
+    PF_CUDA(cudaStreamSynchronize(h->stream));
+    int k = h->last_passes < 16 ? h->last_passes : 16;
+    if (k > cap) k = cap;
+    memcpy(poses, h->h_iter, sizeof(double) * 7 * k);
+    *n = k;
+    return PF_OK;
+}
+
+extern "C" int pf_odom_get_stats(pf_odom* h, pf_odom_stats* s) {
+    PF_REQUIRE(h && s, "bad argument");
+    PF_CUDA(cudaSetDevice(h->device));
+    PF_CUDA(cudaMemcpyAsync(h->h_counts, h->d_nds, sizeof(int) * 2, cudaMemcpyDeviceToHost, h->stream));
+    PF_CUDA(cudaMemcpyAsync(h->h_counts + 2, h->d_nmap[h->cur], sizeof(int) * 2, cudaMemcpyDeviceToHost, h->stream));
+    PF_CUDA(cudaMemcpyAsync(h->h_state, h->d_state, sizeof(LmState), cudaMemcpyDeviceToHost, h->stream));
+    PF_CUDA(cudaStreamSynchronize(h->stream));
+    s->n_edge_ds = h->h_counts[0]; s->n_surf_ds = h->h_counts[1];
+    s->map_edge = h->h_counts[2]; s->map_surf = h->h_counts[3];
+    s->n_edge_res = h->h_state->n_edge_res; s->n_surf_res = h->h_state->n_surf_res;
+    s->passes = h->last_passes;
+    s->lm_iterations = h->h_state->iter;
+    return PF_OK;
+}
+
+extern "C" void* pf_odom_stream(pf_odom* h) { return h ? (void*)h->stream : nullptr; }
+
+extern "C" int pf_odom_kernel_launches(pf_odom* h, uint64_t* launches) {
+    PF_REQUIRE(h && launches, "null argument");
+    *launches = h->ws.launches;
+    return PF_OK;
+}

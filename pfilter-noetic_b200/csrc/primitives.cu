@@ -147,10 +147,11 @@ int workspace_begin_step(Workspace& ws) {
     return PF_OK;
 }
 
-int radix_sort(Workspace& ws, const int* n_dev, int n_cap, int passes, bool vals_iota) {
+int radix_sort(Workspace& ws, const int* n_dev, int n_cap, int passes, bool vals_iota, int* result_buf) {
     PF_REQUIRE(n_cap <= ws.cap, "radix_sort: %d items exceed workspace capacity %d", n_cap, ws.cap);
-    PF_REQUIRE(passes % 2 == 0 && passes >= 2 && passes <= 4, "radix_sort: passes must be 2 or 4");
+    PF_REQUIRE(passes >= 1 && passes <= 4, "radix_sort: passes must be 1..4");
     const int nb = div_up(n_cap, kSortTile);
+    *result_buf = passes & 1;
     if (nb == 0) return PF_OK;
     for (int p = 0; p < passes; ++p) {
         const int src = p & 1, dst = src ^ 1, shift = p * kRadixBits;

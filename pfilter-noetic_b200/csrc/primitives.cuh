@@ -36,9 +36,9 @@ int workspace_create(Workspace& ws, int cap, cudaStream_t stream);
 void workspace_destroy(Workspace& ws);
 // zero the tickets and bump the epoch: first kernel of every pipeline step that uses chained scans
 int workspace_begin_step(Workspace& ws);
-// Sorts keys[0]/vals[0][0 .. *n_dev) by key, stable, `passes` 8-bit digits starting at bit 0 (passes must be even:
-// the result is back in keys[0]/vals[0]).  vals_iota: treat the input values as 0,1,2,... (vals[0] need not be filled).
-int radix_sort(Workspace& ws, const int* n_dev, int n_cap, int passes, bool vals_iota);
+// Sorts keys[0]/vals[0][0 .. *n_dev) by key, stable, `passes` 8-bit digits starting at bit 0; the result lands in
+// keys[*result_buf]/vals[*result_buf] (= passes & 1).  vals_iota: treat the input values as 0,1,2,... (vals[0] need not be filled).
+int radix_sort(Workspace& ws, const int* n_dev, int n_cap, int passes, bool vals_iota, int* result_buf);
 
 #ifdef __CUDACC__
 // ------------------------------------------------------------------------------------------------------------

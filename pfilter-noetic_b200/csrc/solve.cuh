@@ -1,0 +1,53 @@
+// K7 / K8: fused residual + Jacobian + Huber + 6x6 normal-equation reduction and the on-device Levenberg-Marquardt
+// state machine that replaces ceres::Solve (/root/reference/src/odomEstimationClass.cpp:254-271,
+// src/lidarOptimization.cpp:12-104; Ceres behaviour restated in SURVEY.md appendix A.3).
+#pragma once
+#include "common.cuh"
+
+namespace pf {
+
+struct ResidualSrc {          // one feature kind
+    const Pt* queries;        // sensor-frame points (float), used when p_override == null
+    const double* p_override; // [3 n] points in double (stage taps)
+    const uint8_t* flag;      // 2 = residual block present
+    const double* geom;       // [8 n] edge: a[3] b[3]; surf: n[3] d
+    const int* n;             // device count
+};
+
+struct LmState {
+    double x[7];              // accepted pose [qx qy qz qw tx ty tz]
+    double xc[7];             // candidate pose under evaluation
+    double cost;              // 1/2 sum rho at x
+    double H[21], g[6];       // sum J^T J (upper, row-major) and sum J^T r at x (robustified)
+    double scale[6];          // Jacobi scaling fixed at iteration 0
+    double diag[6];           // LM diagonal (scaled space)
+    double step[6];           // last step (scaled space)
+    double radius, decrease, x_norm, model_cost_change;
+    double last_H[21], last_g[6], last_cost;   // sums of the most recent evaluation (stage taps read these)
+    int phase;                // 0 initial evaluation pending, 1 candidate evaluation pending, 2 finished
+    int iter;                 // LM step attempts so far (<= 4)
+    int reuse_diag;
+    int n_res;                // residual blocks in the last evaluation
+    int pass;                 // outer iteration index within the frame
+    int n_edge_res, n_surf_res;
+    int pad;
+};
+
+struct LmParams {
+    ResidualSrc src[2];       // 0 edge, 1 surf
+    LmState* state;
+    double* partials;         // [blocks][32]
+    unsigned* ticket;         // last-block detection
+    double* iter_poses;       // [16][7] pose after every outer iteration (may be null)
+    int eval_only;            // stage tap: evaluate at state->x and stop
+};
+
+constexpr int kLmBlocks = 148;
+constexpr int kLmEvalsPerSolve = 5;   // 1 initial evaluation + max_num_iterations (4) candidates
+
+// pose_src: device pose to start from (null: keep state->x); resets the per-solve fields.
+int lm_begin(cudaStream_t stream, const LmParams& P, const double* pose_src, int first_pass, uint64_t* launches);
+// one launch = one evaluation + one transition of the LM state machine (no-op once finished)
+int lm_eval(cudaStream_t stream, const LmParams& P, uint64_t* launches);
+
+}  // namespace pf

@@ -225,9 +225,10 @@ int voxelize(Workspace& ws, const VoxParams& P_in, int slot, int cap0, int cap1)
     k_vox_keys<<<dim3(nblk, 2), 256, 0, ws.stream>>>(P, ws.keys[0]);
     ws.launches += 2;
     const int* n_total = reinterpret_cast<const int*>(P.state) + 14;
-    PF_CHECK(radix_sort(ws, n_total, cap, 4, true));
+    int rb = 0;
+    PF_CHECK(radix_sort(ws, n_total, cap, 4, true, &rb));
     const int tiles = div_up(capmax, 256);
-    k_vox_reduce<<<dim3(tiles < 1 ? 1 : tiles, 2), 256, 0, ws.stream>>>(P, ws.keys[0], ws.vals[0], ws.scan_status, ws.status_stride, ws.ctrl,
+    k_vox_reduce<<<dim3(tiles < 1 ? 1 : tiles, 2), 256, 0, ws.stream>>>(P, ws.keys[rb], ws.vals[rb], ws.scan_status, ws.status_stride, ws.ctrl,
                                                                        1 + 2 * slot, slot);
     ws.launches += 1;
     PF_CUDA(cudaGetLastError());

@@ -1,0 +1,82 @@
+"""End-to-end: extraction + odometry + persistence filter on a synthetic sequence, GPU vs the CPU oracle."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(pfb, oracle, capi, cfg, nframes, params, fused):
+    p = pfb.synth.config(cfg)
+    k_new, theta_p, theta_max = params
+    ex = capi.Extractor(num_lines=p.sensor_lines, max_points=131072)
+    od = capi.Odometry(0.4, k_new, theta_p, theta_max, max_map_points=262144)
+    ref = oracle.Odom(0.4, k_new, theta_p, theta_max)
+    gp, rp = [], []
+    for f in range(nframes):
+        s = pfb.synth.scan(p, f)
+        r = oracle.extract(s, num_lines=p.sensor_lines, order=1)
+        e, u = s[r["edge_idx"]], s[r["surf_idx"]]
+        if fused:
+            pose = capi.frame_process(ex, od, s)
+        else:
+            ge, gu, _ = ex.run(s, want_label=False)
+            if f == 0:
+                od.init_map(ge, gu)
+                pose = od.pose()
+            else:
+                pose = od.update(ge, gu)
+        if f == 0:
+            ref.init_map(e, u)
+            rpose = np.array([0, 0, 0, 1, 0, 0, 0.0])
+        else:
+            rpose = ref.update(e, u)
+        gp.append(pose)
+        rp.append(rpose)
+    return p, od, ref, np.array(gp), np.array(rp)
+
+
+@pytest.mark.parametrize("fused", [False, True])
+def test_sequence_matches_oracle(pfb, oracle, capi, fused):
+    n = 14
+    p, od, ref, gp, rp = _run(pfb, oracle, capi, "cfg2", n, (0, 0.4, 75), fused)
+    # per-frame poses within the stated tolerance (1e-4 relative on translation magnitudes of O(1..10) m)
+    assert np.abs(gp[:, 4:] - rp[:, 4:]).max() < 2e-3
+    assert np.abs(gp[:, :4] - rp[:, :4]).max() < 1e-4
+    gt = np.array([pfb.synth.pose(p, f) for f in range(n)])
+    assert np.abs((gp[:, 4:] - (gt[:, 4:] - gt[0, 4:]))).max() < 0.08      # and both track the ground truth
+    st, rst = od.stats(), ref.stats()
+    for k in ("n_edge_ds", "n_surf_ds", "passes"):
+        assert st[k] == rst[k]
+    assert abs(st["map_edge"] - rst["map_edge"]) <= 0.01 * rst["map_edge"]
+    assert abs(st["map_surf"] - rst["map_surf"]) <= 0.01 * rst["map_surf"]
+    assert od.launches > 50
+
+
+def test_first_update_is_bit_identical_in_integer_outputs(pfb, oracle, capi):
+    """Frame 1 starts from identical state on both sides: per-iteration poses agree to 1e-4 and the map keeps the
+    same voxels (the only differences allowed are last-bit effects of sin/cos in the pose)."""
+    p, od, ref, gp, rp = _run(pfb, oracle, capi, "cfg2", 2, (0, 0.4, 75), False)
+    gi, ri = od.iter_poses(), ref.iter_poses()
+    assert gi.shape == ri.shape == (11, 7)
+    np.testing.assert_allclose(gi, ri, rtol=1e-4, atol=1e-6)
+    for which in (0, 1):
+        gm, rm = od.map_part(which), ref.get_map(which)
+        assert abs(len(gm) - len(rm)) <= 2
+        if len(gm) == len(rm):
+            assert (np.abs(gm["x"] - rm["x"]) < 1e-3).mean() > 0.999
+            assert (gm["r"] == rm["r"]).mean() > 0.999 and (gm["g"] == rm["g"]).mean() > 0.99
+
+
+def test_getmap_order_and_pfilter_disabled(pfb, oracle, capi):
+    p, od, ref, gp, rp = _run(pfb, oracle, capi, "cfg2", 4, (0, 0.0, 0), False)
+    full = od.get_map()
+    e, s = od.map_part(0), od.map_part(1)
+    assert full.tobytes() == np.concatenate([s, e]).tobytes()      # getMap: surf first, then corner (:213-214)
+    assert np.abs(gp[:, 4:] - rp[:, 4:]).max() < 2e-3
+
+
+def test_update_before_init_is_an_error(capi):
+    od = capi.Odometry(max_map_points=65536, max_features=65536)
+    with pytest.raises(capi.PfError) as e:
+        od.update(np.zeros((10, 4), np.float32), np.zeros((10, 4), np.float32))
+    assert e.value.status == -4
