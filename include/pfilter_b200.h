@@ -145,6 +145,12 @@ int pf_odom_kernel_launches(pf_odom* h, uint64_t* launches);
 int pf_odom_process_extracted(pf_odom* h, pf_extract* ex, double pose_out[7]);
 /* Whole frame: H2D scan -> extract -> (init | update) -> pose D2H.  One call per frame. */
 int pf_frame_process(pf_extract* ex, pf_odom* od, const float* xyzi, int n, double pose_out[7]);
+/* Same with the scan already resident on the handle's device.  pose_out == NULL: enqueue only, no host
+ * synchronisation (frames can be queued back to back; errors surface at pf_odom_sync). */
+int pf_frame_process_device(pf_extract* ex, pf_odom* od, const void* d_xyzi, int n, double* pose_out);
+int pf_odom_sync(pf_odom* h);
+/* poses of updates first_frame .. first_frame+count-1 (frame 0 is the init frame; history depth 4096 frames) */
+int pf_odom_get_pose_history(pf_odom* h, long long first_frame, int count, double* poses);
 
 /* ------------------------------------------------------------------------------------------------
  * Stage taps (parity tests and micro-benchmarks); host buffers, synchronous.

@@ -91,6 +91,10 @@ __global__ void __launch_bounds__(kTile) k_ring_classify(ExtractParams P) {
     }
 }
 
+__global__ void k_set_int(int* p, int v) {
+    if (threadIdx.x == 0) *p = v;
+}
+
 // exclusive scan of a[0..n) in shared memory by the whole CTA (kExtractThreads threads); returns the total
 __device__ int block_excl_scan(int* a, int n, int* warp_tmp /*[9]*/) {
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
@@ -529,15 +533,22 @@ extern "C" int pf_extract_kernel_launches(pf_extract* h, uint64_t* launches) {
 }
 
 // Enqueue H2D + kernels for one scan; results stay on the device (used by pf_extract_run and the frame pipeline).
-int pf_extract_enqueue_single(pf_extract* h, const float* xyzi, int n) {
+// device_input: xyzi is a device pointer (no copy).  The count travels as a kernel argument, so consecutive frames
+// can be enqueued without a host synchronisation in between.
+int pf_extract_enqueue_single(pf_extract* h, const float* xyzi, int n, int device_input) {
     PF_REQUIRE(h && (xyzi || n == 0), "null argument");
     PF_REQUIRE(n >= 0 && n <= h->stride, "scan of %d points exceeds max_points %d", n, h->stride);
     PF_CUDA(cudaSetDevice(h->device));
-    h->h_counts[0] = n;
-    PF_CUDA(cudaMemcpyAsync(h->d_n, h->h_counts, sizeof(int), cudaMemcpyHostToDevice, h->stream));
-    if (n > 0) PF_CUDA(cudaMemcpyAsync(h->d_pts, xyzi, (size_t)n * 16, cudaMemcpyHostToDevice, h->stream));
-    PF_CHECK(extract_launch(h, h->d_pts, h->d_n, 1, h->stride, h->d_edge, h->d_n_edge, h->edge_stride, h->d_surf, h->d_n_surf,
-                            h->d_label));
+    k_set_int<<<1, 32, 0, h->stream>>>(h->d_n, n);
+    h->launches += 1;
+    const float4* src = h->d_pts;
+    if (device_input) {
+        src = reinterpret_cast<const float4*>(xyzi);
+    } else if (n > 0) {
+        PF_CUDA(cudaMemcpyAsync(h->d_pts, xyzi, (size_t)n * 16, cudaMemcpyHostToDevice, h->stream));
+    }
+    PF_CHECK(extract_launch(h, src ? src : h->d_pts, h->d_n, 1, h->stride, h->d_edge, h->d_n_edge, h->edge_stride, h->d_surf,
+                            h->d_n_surf, h->d_label));
     h->last_valid = 1;
     return PF_OK;
 }
@@ -590,7 +601,7 @@ extern "C" int pf_extract_run_batch(pf_extract* h, const float* xyzi, const int*
 extern "C" int pf_extract_run(pf_extract* h, const float* xyzi, int n, float* edge, int* n_edge, float* surf, int* n_surf,
                               uint8_t* label) {
     PF_REQUIRE(h && edge && n_edge && surf && n_surf, "null argument");
-    PF_CHECK(pf_extract_enqueue_single(h, xyzi, n));
+    PF_CHECK(pf_extract_enqueue_single(h, xyzi, n, 0));
     int* hc = h->h_counts + h->max_batch;
     PF_CUDA(cudaMemcpyAsync(hc, h->d_n_edge, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     PF_CUDA(cudaMemcpyAsync(hc + 1, h->d_n_surf, sizeof(int), cudaMemcpyDeviceToHost, h->stream));

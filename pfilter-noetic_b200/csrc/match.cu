@@ -18,10 +18,10 @@ namespace pf {
 __global__ void __launch_bounds__(256) k_assoc_match(AssocParams P) {
     const int kind = blockIdx.y;
     const AssocCloud& c = P.c[kind];
-    const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const unsigned lane = lane_id();
     const int nq = *c.n_q;
-    if (q >= nq) return;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; q < nq; q += nwarps) {
     const bool guard = P.min_edge_map == 0 || (*P.c[0].n_map > P.min_edge_map && *P.c[1].n_map > P.min_surf_map);   // :247
     unsigned flag = 0;
     if (guard) {
@@ -83,14 +83,15 @@ __global__ void __launch_bounds__(256) k_assoc_match(AssocParams P) {
         }
     }
     if (lane == 0) c.flag[q] = (uint8_t)flag;
+    }
 }
 
 __global__ void __launch_bounds__(128) k_assoc_persist(AssocParams P) {
     const int kind = blockIdx.y;
     const AssocCloud& c = P.c[kind];
-    const int q = blockIdx.x * blockDim.x + threadIdx.x;
     const int nq = *c.n_q;
-    if (q >= nq || c.flag[q] != 1) return;
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += gridDim.x * blockDim.x) {
+    if (c.flag[q] != 1) continue;
     int m[5], g0[5], len[5];
     int sg = 0, sr = 0;
 #pragma unroll
@@ -123,13 +124,17 @@ __global__ void __launch_bounds__(128) k_assoc_persist(AssocParams P) {
             c.head[m[j]] = -1;
         }
     }
+    }
 }
 
 int associate_pass(cudaStream_t stream, const AssocParams& P, int qcap0, int qcap1, uint64_t* launches) {
     const int qcap = qcap0 > qcap1 ? qcap0 : qcap1;
     if (qcap <= 0) return PF_OK;
-    k_assoc_match<<<dim3(div_up(qcap, 8), 2), 256, 0, stream>>>(P);
-    k_assoc_persist<<<dim3(div_up(qcap, 128), 2), 128, 0, stream>>>(P);
+    int gm = div_up(qcap, 8), gp = div_up(qcap, 128);
+    if (gm > 8 * kSMs) gm = 8 * kSMs;
+    if (gp > 4 * kSMs) gp = 4 * kSMs;
+    k_assoc_match<<<dim3(gm, 2), 256, 0, stream>>>(P);
+    k_assoc_persist<<<dim3(gp, 2), 128, 0, stream>>>(P);
     if (launches) *launches += 2;
     PF_CUDA(cudaGetLastError());
     return PF_OK;

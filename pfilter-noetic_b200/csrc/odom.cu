@@ -63,11 +63,14 @@ __global__ void k_predict(OdomShared* sh, LmState* S) {
     for (int i = 0; i < 3; ++i) S->x[4 + i] = p.t[i];
 }
 
+constexpr int kPoseHist = 4096;
+
 struct AppendParams {
     const Pt* ds[2]; const int* n_ds[2];
     Pt* map[2]; const int* n_map[2];
     OdomShared* sh; const LmState* S;
     int map_cap;      // capacity of the map buffers (points)
+    double* pose_hist; int hist_slot;
 };
 
 // odom <- (q_w_curr, t_w_curr) (:278-280) and addPointsToMap's append loop (:592-604)
@@ -84,7 +87,7 @@ __global__ void __launch_bounds__(256) k_append(AppendParams A) {
         if (kind == 0) {
             quat_to_mat(s_pose, A.sh->odom.R);
             for (int i = 0; i < 3; ++i) A.sh->odom.t[i] = s_pose[4 + i];
-            for (int i = 0; i < 7; ++i) A.sh->pose[i] = s_pose[i];
+            for (int i = 0; i < 7; ++i) { A.sh->pose[i] = s_pose[i]; A.pose_hist[7 * A.hist_slot + i] = s_pose[i]; }
         }
     }
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -125,12 +128,12 @@ using namespace pf;
 // accessors implemented in extract.cu
 void pf_extract_device_outputs(pf_extract* h, const float4** edge, const int** n_edge, const float4** surf, const int** n_surf,
                                cudaStream_t* stream, int* edge_cap, int* surf_cap);
-int pf_extract_enqueue_single(pf_extract* h, const float* xyzi, int n);
+int pf_extract_enqueue_single(pf_extract* h, const float* xyzi, int n, int device_input);
 
 struct pf_odom {
     int device = 0;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev = nullptr;
+    cudaEvent_t ev = nullptr, ev_done = nullptr;
     pf_odom_params prm{};
     int fcap = 0, mcap = 0, bufcap = 0;
     Workspace ws;
@@ -150,6 +153,8 @@ struct pf_odom {
     double *d_partials = nullptr, *d_iter_poses = nullptr;
     unsigned* d_ticket = nullptr;
     OdomShared* d_sh = nullptr;
+    double* d_pose_hist = nullptr;       // [kPoseHist][7] pose of every update (ring buffer)
+    long long frame = 0;                 // frames processed (frame 0 = init)
     // pinned host mirrors
     OdomShared* h_sh = nullptr;
     LmState* h_state = nullptr;
@@ -195,6 +200,8 @@ int odom_alloc(pf_odom* h) {
     PF_CUDA(cudaMalloc(&h->d_ticket, sizeof(unsigned)));
     PF_CUDA(cudaMemset(h->d_ticket, 0, sizeof(unsigned)));
     PF_CUDA(cudaMalloc(&h->d_sh, sizeof(OdomShared)));
+    PF_CUDA(cudaMalloc(&h->d_pose_hist, sizeof(double) * 7 * kPoseHist));
+    PF_CUDA(cudaMemset(h->d_pose_hist, 0, sizeof(double) * 7 * kPoseHist));
     PF_CUDA(cudaMallocHost(&h->h_sh, sizeof(OdomShared)));
     PF_CUDA(cudaMallocHost(&h->h_state, sizeof(LmState)));
     PF_CUDA(cudaMallocHost(&h->h_counts, sizeof(int) * 8));
@@ -224,6 +231,7 @@ int enqueue_init(pf_odom* h, const float4* const feat[2], const int* const n_fea
     PF_CUDA(cudaGetLastError());
     h->optimization_count = 12;   // :221
     h->inited = true;
+    h->frame = 1;
     return PF_OK;
 }
 
@@ -272,6 +280,7 @@ int enqueue_update(pf_odom* h, const float4* const feat[2], const int* const n_f
     AppendParams P{};
     for (int k = 0; k < 2; ++k) { P.ds[k] = h->d_ds[k]; P.n_ds[k] = h->d_nds + k; P.map[k] = h->d_map[cur][k]; P.n_map[k] = h->d_nmap[cur] + k; }
     P.sh = h->d_sh; P.S = h->d_state; P.map_cap = h->bufcap;
+    P.pose_hist = h->d_pose_hist; P.hist_slot = (int)(h->frame % kPoseHist);
     k_append<<<dim3(kSMs, 2), 256, 0, h->stream>>>(P);
     ws.launches += 1;
     VoxParams M{};
@@ -288,6 +297,7 @@ int enqueue_update(pf_odom* h, const float4* const feat[2], const int* const n_f
     ws.launches += 1;
     PF_CUDA(cudaGetLastError());
     h->cur = nxt;
+    h->frame += 1;
     return PF_OK;
 }
 
@@ -324,6 +334,7 @@ extern "C" int pf_odom_create(const pf_odom_params* p, int device, pf_odom** out
     h->bufcap = h->mcap + h->fcap;
     PF_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     PF_CUDA(cudaEventCreateWithFlags(&h->ev, cudaEventDisableTiming));
+    PF_CUDA(cudaEventCreateWithFlags(&h->ev_done, cudaEventDisableTiming));
     int rc = odom_alloc(h);
     if (rc != PF_OK) { pf_odom_destroy(h); return rc; }
     *out = h;
@@ -341,9 +352,10 @@ extern "C" int pf_odom_destroy(pf_odom* h) {
         cudaFree(h->d_gpts[k]); cudaFree(h->d_cs[k]); cudaFree(h->d_ce[k]); cudaFree(h->d_head[k]); cudaFree(h->d_hits[k]);
         cudaFree(h->d_next[k]); cudaFree(h->d_nn[k]); cudaFree(h->d_flag[k]); cudaFree(h->d_g8[k]);
     }
-    cudaFree(h->d_state); cudaFree(h->d_partials); cudaFree(h->d_iter_poses); cudaFree(h->d_ticket); cudaFree(h->d_sh);
+    cudaFree(h->d_state); cudaFree(h->d_partials); cudaFree(h->d_iter_poses); cudaFree(h->d_ticket); cudaFree(h->d_sh); cudaFree(h->d_pose_hist);
     cudaFreeHost(h->h_sh); cudaFreeHost(h->h_state); cudaFreeHost(h->h_counts); cudaFreeHost(h->h_iter);
     if (h->ev) cudaEventDestroy(h->ev);
+    if (h->ev_done) cudaEventDestroy(h->ev_done);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return PF_OK;
@@ -370,7 +382,7 @@ extern "C" int pf_odom_update(pf_odom* h, const float* edge, int n_edge, const f
     return finish_frame(h, pose_out);
 }
 
-extern "C" int pf_odom_process_extracted(pf_odom* h, pf_extract* ex, double pose_out[7]) {
+static int process_extracted(pf_odom* h, pf_extract* ex, double pose_out[7], bool sync) {
     PF_REQUIRE(h && ex, "null handle");
     PF_CUDA(cudaSetDevice(h->device));
     const float4* feat[2];
@@ -386,13 +398,43 @@ extern "C" int pf_odom_process_extracted(pf_odom* h, pf_extract* ex, double pose
     } else {
         PF_CHECK(enqueue_update(h, feat, nf, scap));
     }
-    return finish_frame(h, pose_out);
+    // the extractor's output buffers are reused by the next frame: it must not start before this frame consumed them
+    PF_CUDA(cudaEventRecord(h->ev_done, h->stream));
+    PF_CUDA(cudaStreamWaitEvent(exs, h->ev_done, 0));
+    return sync ? finish_frame(h, pose_out) : PF_OK;
+}
+
+extern "C" int pf_odom_process_extracted(pf_odom* h, pf_extract* ex, double pose_out[7]) {
+    return process_extracted(h, ex, pose_out, true);
 }
 
 extern "C" int pf_frame_process(pf_extract* ex, pf_odom* od, const float* xyzi, int n, double pose_out[7]) {
     PF_REQUIRE(ex && od, "null handle");
-    PF_CHECK(pf_extract_enqueue_single(ex, xyzi, n));
-    return pf_odom_process_extracted(od, ex, pose_out);
+    PF_CHECK(pf_extract_enqueue_single(ex, xyzi, n, 0));
+    return process_extracted(od, ex, pose_out, true);
+}
+
+extern "C" int pf_frame_process_device(pf_extract* ex, pf_odom* od, const void* d_xyzi, int n, double* pose_out) {
+    PF_REQUIRE(ex && od, "null handle");
+    PF_CHECK(pf_extract_enqueue_single(ex, (const float*)d_xyzi, n, 1));
+    return process_extracted(od, ex, pose_out, pose_out != nullptr);
+}
+
+extern "C" int pf_odom_sync(pf_odom* h) {
+    PF_REQUIRE(h, "null handle");
+    PF_CUDA(cudaSetDevice(h->device));
+    return finish_frame(h, nullptr);
+}
+
+extern "C" int pf_odom_get_pose_history(pf_odom* h, long long first_frame, int count, double* poses) {
+    PF_REQUIRE(h && poses && count >= 0 && first_frame >= 1, "bad argument");
+    PF_REQUIRE(first_frame + count <= h->frame && h->frame - first_frame <= kPoseHist, "frames [%lld, %lld) are not in the history (have < %lld, depth %d)",
+               first_frame, first_frame + count, h->frame, kPoseHist);
+    PF_CUDA(cudaSetDevice(h->device));
+    PF_CUDA(cudaStreamSynchronize(h->stream));
+    for (int i = 0; i < count; ++i)
+        PF_CUDA(cudaMemcpy(poses + 7 * i, h->d_pose_hist + 7 * ((first_frame + i) % kPoseHist), sizeof(double) * 7, cudaMemcpyDeviceToHost));
+    return PF_OK;
 }
 
 extern "C" int pf_odom_get_pose(pf_odom* h, double pose[7]) {

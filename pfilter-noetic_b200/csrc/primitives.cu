@@ -8,25 +8,27 @@ namespace pf {
 __global__ void __launch_bounds__(kSortThreads) k_sort_hist(const uint32_t* __restrict__ keys, const int* __restrict__ n_dev, int shift,
                                                             uint32_t* __restrict__ hist, int nb_cap) {
     const int n = *n_dev;
-    const int b = blockIdx.x, start = b * kSortTile;
-    if (start >= n) return;
+    const int ntiles = (n + kSortTile - 1) / kSortTile;
     __shared__ unsigned h[kRadix];
-    h[threadIdx.x] = 0;
-    __syncthreads();
+    for (int b = blockIdx.x; b < ntiles; b += gridDim.x) {   // persistent: the grid is bounded, tiles are not
+        const int start = b * kSortTile;
+        h[threadIdx.x] = 0;
+        __syncthreads();
 #pragma unroll
-    for (int k = 0; k < kSortItems; ++k) {
-        int i = start + k * kSortThreads + threadIdx.x;
-        const bool ok = i < n;
-        const unsigned act = __ballot_sync(0xffffffffu, ok);
-        if (ok) {
-            unsigned d = (keys[i] >> shift) & (kRadix - 1);
-            // warp-aggregated shared atomic: one add per distinct digit in the warp
-            unsigned m = __match_any_sync(act, d);
-            if ((int)lane_id() == __ffs(m) - 1) atomicAdd(&h[d], (unsigned)__popc(m));
+        for (int k = 0; k < kSortItems; ++k) {
+            int i = start + k * kSortThreads + threadIdx.x;
+            const bool ok = i < n;
+            const unsigned act = __ballot_sync(0xffffffffu, ok);
+            if (ok) {
+                unsigned d = (keys[i] >> shift) & (kRadix - 1);
+                // warp-aggregated shared atomic: one add per distinct digit in the warp
+                unsigned m = __match_any_sync(act, d);
+                if ((int)lane_id() == __ffs(m) - 1) atomicAdd(&h[d], (unsigned)__popc(m));
+            }
         }
+        __syncthreads();
+        hist[(size_t)threadIdx.x * nb_cap + b] = h[threadIdx.x];
     }
-    __syncthreads();
-    hist[(size_t)threadIdx.x * nb_cap + b] = h[threadIdx.x];
 }
 
 // one warp per digit: exclusive scan of hist[d][0..nb) in place, totals[d] = sum
@@ -56,11 +58,13 @@ __global__ void __launch_bounds__(kSortThreads) k_sort_scatter(const uint32_t* _
                                                                const int* __restrict__ n_dev, int shift, const uint32_t* __restrict__ hist,
                                                                const uint32_t* __restrict__ totals, int nb_cap) {
     const int n = *n_dev;
-    const int b = blockIdx.x, start = b * kSortTile;
-    if (start >= n) return;
+    const int ntiles = (n + kSortTile - 1) / kSortTile;
     __shared__ unsigned wc[kSortThreads / 32][kRadix];   // warp-private digit counters -> exclusive bases
     __shared__ int tmp[9];
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    for (int b = blockIdx.x; b < ntiles; b += gridDim.x) {
+    const int start = b * kSortTile;
+    __syncthreads();
     for (int k = 0; k < kSortThreads / 32; ++k) wc[k][tid] = 0;
     __syncthreads();
     // warp w owns the contiguous sub-chunk [start + w*256, +256), processed in 8 ordered rounds of 32 keys
@@ -109,6 +113,7 @@ __global__ void __launch_bounds__(kSortThreads) k_sort_scatter(const uint32_t* _
             vals_out[pos] = val[k];
         }
     }
+    }
 }
 
 __global__ void k_begin_step(unsigned int* ctrl) {
@@ -150,9 +155,10 @@ int workspace_begin_step(Workspace& ws) {
 int radix_sort(Workspace& ws, const int* n_dev, int n_cap, int passes, bool vals_iota, int* result_buf) {
     PF_REQUIRE(n_cap <= ws.cap, "radix_sort: %d items exceed workspace capacity %d", n_cap, ws.cap);
     PF_REQUIRE(passes >= 1 && passes <= 4, "radix_sort: passes must be 1..4");
-    const int nb = div_up(n_cap, kSortTile);
+    int nb = div_up(n_cap, kSortTile);
     *result_buf = passes & 1;
     if (nb == 0) return PF_OK;
+    if (nb > 4 * kSMs) nb = 4 * kSMs;
     for (int p = 0; p < passes; ++p) {
         const int src = p & 1, dst = src ^ 1, shift = p * kRadixBits;
         k_sort_hist<<<nb, kSortThreads, 0, ws.stream>>>(ws.keys[src], n_dev, shift, ws.hist, ws.nb_cap);

@@ -148,12 +148,14 @@ __global__ void __launch_bounds__(256) k_vox_reduce(VoxParams P, const uint32_t*
     __shared__ int s_tile;
     __shared__ int s_tmp[9];
     __shared__ unsigned s_bcast;
-    if (threadIdx.x == 0) s_tile = (int)atomicAdd(&ctrl[ticket_word + cloud], 1u);
-    __syncthreads();
-    const int tile = s_tile;
     const int* st = reinterpret_cast<const int*>(P.state);
     const int start = cloud == 0 ? 0 : st[12];
     const int len = st[12 + cloud];
+    while (true) {   // persistent CTAs pull tiles by ticket until the cloud is exhausted
+    __syncthreads();
+    if (threadIdx.x == 0) s_tile = (int)atomicAdd(&ctrl[ticket_word + cloud], 1u);
+    __syncthreads();
+    const int tile = s_tile;
     if (len == 0) {
         if (tile == 0 && threadIdx.x == 0) *c.n_out = 0;
         return;
@@ -210,6 +212,7 @@ __global__ void __launch_bounds__(256) k_vox_reduce(VoxParams P, const uint32_t*
     const unsigned excl = chained_scan_exclusive(status + (size_t)cloud * status_stride, tag, tile, (unsigned)total, &s_bcast);
     if (keep) c.out[excl + local] = o;
     if (tile == (len - 1) / 256 && threadIdx.x == 0) *c.n_out = (int)excl + total;
+    }
 }
 
 int voxelize(Workspace& ws, const VoxParams& P_in, int slot, int cap0, int cap1) {
@@ -227,7 +230,8 @@ int voxelize(Workspace& ws, const VoxParams& P_in, int slot, int cap0, int cap1)
     const int* n_total = reinterpret_cast<const int*>(P.state) + 14;
     int rb = 0;
     PF_CHECK(radix_sort(ws, n_total, cap, 4, true, &rb));
-    const int tiles = div_up(capmax, 256);
+    int tiles = div_up(capmax, 256);
+    if (tiles > 6 * kSMs) tiles = 6 * kSMs;
     k_vox_reduce<<<dim3(tiles < 1 ? 1 : tiles, 2), 256, 0, ws.stream>>>(P, ws.keys[rb], ws.vals[rb], ws.scan_status, ws.status_stride, ws.ctrl,
                                                                        1 + 2 * slot, slot);
     ws.launches += 1;
