@@ -181,16 +181,8 @@ int pf_eval_normal_eq(int device, const double pose[7], const double* edge9, int
 int pf_lm_solve(int device, double pose_io[7], const double* edge9, int n_edge, const double* surf7, int n_surf,
                 int* iterations, double* final_cost);
 
-/* ------------------------------------------------------------------------------------------------
- * Global mapping  --  replaces LaserMappingClass (include/laserMappingClass.h:32-58, src/laserMappingClass.cpp)
- * ---------------------------------------------------------------------------------------------- */
-typedef struct pf_mapping pf_mapping;
-int pf_mapping_create(double map_resolution, int max_points, int device, pf_mapping** out);   /* init :7-32 */
-int pf_mapping_destroy(pf_mapping* h);
-/* updateCurrentPointsToMap :152-191; pose = [qx qy qz qw tx ty tz] */
-int pf_mapping_update(pf_mapping* h, const float* xyzi, int n, const double pose[7]);
-int pf_mapping_size(pf_mapping* h, int* n);
-int pf_mapping_get_map(pf_mapping* h, float* xyzi_out, int cap, int* n);                      /* getMap :196-208 */
+/* LaserMappingClass (include/laserMappingClass.h:32-58) is the next component on the path;
+ * it is not part of this ABI yet. */
 
 #ifdef __cplusplus
 }
