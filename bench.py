@@ -225,7 +225,8 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device(f"cuda:{local}")
     K, W = args.steps, max(args.warmup, 3)
-    cfg = "cfg2" if world == 1 else f"cfg5.{rank}"
+    from pfilter_noetic_b200 import shard
+    cfg = shard.sequence_for_rank(rank, world)
     p, scans, gt = _sequence(pfb, cfg, K)
 
     def handles():

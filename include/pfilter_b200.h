@@ -138,6 +138,9 @@ typedef struct pf_odom_stats {
 } pf_odom_stats;
 int pf_odom_get_stats(pf_odom* h, pf_odom_stats* s);
 void* pf_odom_stream(pf_odom* h);
+/* CUDA-event phase timing of the last update (PF_ODOM_TIMING=1 at create time): ms[0] predict + down-sample, ms[1] search-grid
+ * build, ms[2] optimisation passes up to the last association, ms[3] the last pass's 5 LM evaluations, ms[4] append + map update */
+int pf_odom_get_phase_ms(pf_odom* h, float ms[5]);
 int pf_odom_kernel_launches(pf_odom* h, uint64_t* launches);
 
 /* Device-resident hand-off: consume the outputs of the last single-scan extraction of `ex` (same device)

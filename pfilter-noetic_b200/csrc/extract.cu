@@ -385,6 +385,7 @@ struct pf_extract {
     uint64_t launches = 0;
     // result of the last single-scan run (device resident hand-off to the odometry)
     int last_valid = 0;
+    int last_n = 0;
 };
 
 namespace pf {
@@ -550,6 +551,7 @@ int pf_extract_enqueue_single(pf_extract* h, const float* xyzi, int n, int devic
     PF_CHECK(extract_launch(h, src ? src : h->d_pts, h->d_n, 1, h->stride, h->d_edge, h->d_n_edge, h->edge_stride, h->d_surf,
                             h->d_n_surf, h->d_label));
     h->last_valid = 1;
+    h->last_n = n;
     return PF_OK;
 }
 
@@ -557,7 +559,7 @@ int pf_extract_enqueue_single(pf_extract* h, const float* xyzi, int n, int devic
 void pf_extract_device_outputs(pf_extract* h, const float4** edge, const int** n_edge, const float4** surf, const int** n_surf,
                                cudaStream_t* stream, int* edge_cap, int* surf_cap) {
     *edge = h->d_edge; *n_edge = h->d_n_edge; *surf = h->d_surf; *n_surf = h->d_n_surf; *stream = h->stream;
-    *edge_cap = h->edge_stride; *surf_cap = h->stride;
+    *edge_cap = h->edge_stride < h->last_n ? h->edge_stride : h->last_n; *surf_cap = h->last_n;   // upper bounds of the device counts
 }
 
 extern "C" int pf_extract_run_batch(pf_extract* h, const float* xyzi, const int* n, int batch, int stride, float* edge,

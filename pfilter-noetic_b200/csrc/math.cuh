@@ -229,13 +229,15 @@ __device__ __forceinline__ void mat_to_quat(const double* R, double* q) {   // E
 __device__ __forceinline__ void se3_exp(const double* d, double* dq, D3& dt) {
     const D3 om = d3(d[0], d[1], d[2]), up = d3(d[3], d[4], d[5]);
     const double theta = norm3(om), half = 0.5 * theta;
-    const double real = cos(half);
+    double sh, ch;
+    sincos(half, &sh, &ch);
+    const double real = ch;
     double imag;
     if (theta < 1e-10) {
         const double t2 = theta * theta, t4 = t2 * t2;
         imag = 0.5 - 0.0208333 * t2 + 0.000260417 * t4;
     } else {
-        imag = sin(half) / theta;
+        imag = sh / theta;
     }
     dq[0] = imag * om.x; dq[1] = imag * om.y; dq[2] = imag * om.z; dq[3] = real;
     double J[9];
@@ -243,7 +245,9 @@ __device__ __forceinline__ void se3_exp(const double* d, double* dq, D3& dt) {
         quat_to_mat(dq, J);
     } else {
         const double O[9] = {0, -om.z, om.y, om.z, 0, -om.x, -om.y, om.x, 0};
-        const double c1 = (1 - cos(theta)) / (theta * theta), c2 = (theta - sin(theta)) / (theta * theta * theta);
+        double st, ct;
+        sincos(theta, &st, &ct);
+        const double c1 = (1 - ct) / (theta * theta), c2 = (theta - st) / (theta * theta * theta);
 #pragma unroll
         for (int i = 0; i < 3; ++i)
 #pragma unroll
@@ -265,36 +269,57 @@ __device__ __forceinline__ void se3_plus(const double* x, const double* d, doubl
 }
 
 // Solve (A) y = b for a symmetric positive definite 6x6 (upper triangle U21, row-major) by Cholesky. false if not SPD.
+// Fully unrolled so that the factor lives in registers.
 __device__ __forceinline__ bool chol6_solve(const double* U21, const double* b, double* y) {
     double L[6][6];
-    int k = 0;
-    for (int i = 0; i < 6; ++i)
-        for (int j = i; j < 6; ++j) { L[j][i] = U21[k]; L[i][j] = U21[k]; ++k; }
+    {
+        int k = 0;
+#pragma unroll
+        for (int i = 0; i < 6; ++i)
+#pragma unroll
+            for (int j = i; j < 6; ++j) { L[j][i] = U21[k]; ++k; }
+    }
+    bool ok = true;
+    double inv[6];
+#pragma unroll
     for (int j = 0; j < 6; ++j) {
         double s = L[j][j];
-        for (int p = 0; p < j; ++p) s -= L[j][p] * L[j][p];
-        if (!(s > 0.0)) return false;
+#pragma unroll
+        for (int p = 0; p < 6; ++p) if (p < j) s -= L[j][p] * L[j][p];
+        if (!(s > 0.0)) ok = false;
         const double d = sqrt(s);
         L[j][j] = d;
-        for (int i = j + 1; i < 6; ++i) {
-            double t = L[i][j];
-            for (int p = 0; p < j; ++p) t -= L[i][p] * L[j][p];
-            L[i][j] = t / d;
+        inv[j] = 1.0 / d;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            if (i > j) {
+                double t = L[i][j];
+#pragma unroll
+                for (int p = 0; p < 6; ++p) if (p < j) t -= L[i][p] * L[j][p];
+                L[i][j] = t * inv[j];
+            }
         }
     }
+    if (!ok) return false;
     double z[6];
+#pragma unroll
     for (int i = 0; i < 6; ++i) {
         double s = b[i];
-        for (int p = 0; p < i; ++p) s -= L[i][p] * z[p];
-        z[i] = s / L[i][i];
+#pragma unroll
+        for (int p = 0; p < 6; ++p) if (p < i) s -= L[i][p] * z[p];
+        z[i] = s * inv[i];
     }
+#pragma unroll
     for (int i = 5; i >= 0; --i) {
         double s = z[i];
-        for (int p = i + 1; p < 6; ++p) s -= L[p][i] * y[p];
-        y[i] = s / L[i][i];
+#pragma unroll
+        for (int p = 0; p < 6; ++p) if (p > i) s -= L[p][i] * y[p];
+        y[i] = s * inv[i];
     }
-    for (int i = 0; i < 6; ++i) if (!isfinite(y[i])) return false;
-    return true;
+    bool fin = true;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) fin = fin && isfinite(y[i]);
+    return fin;
 }
 
 }  // namespace pf

@@ -26,6 +26,8 @@ struct OdomShared {   // small device-resident block
     int n_app[2];          // map sizes after appending the new points
     int err;               // bit 0: map capacity exceeded
     int pad;
+    int n_map[2];          // map sizes after the last update (read back with the pose: tight launch bounds for the next frame)
+    long long frame;       // frame index this block describes
 };
 
 __global__ void k_odom_reset(OdomShared* sh, LmState* S) {
@@ -108,7 +110,7 @@ __global__ void __launch_bounds__(256) k_init_map(InitParams I) {
     const int kind = blockIdx.y;
     int n = *I.n_feat[kind];
     if (n > I.map_cap) { n = I.map_cap; if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(&I.sh->err, 1); }
-    if (blockIdx.x == 0 && threadIdx.x == 0) *I.n_map[kind] = n;
+    if (blockIdx.x == 0 && threadIdx.x == 0) { *I.n_map[kind] = n; I.sh->n_map[kind] = n; I.sh->frame = 0; }
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const float4 f = I.feat[kind][i];
         Pt o;
@@ -117,8 +119,12 @@ __global__ void __launch_bounds__(256) k_init_map(InitParams I) {
     }
 }
 
-__global__ void k_check_map_cap(const int* n_map0, const int* n_map1, int cap, OdomShared* sh) {
-    if (threadIdx.x == 0 && (*n_map0 > cap || *n_map1 > cap)) atomicOr(&sh->err, 1);
+__global__ void k_check_map_cap(const int* n_map0, const int* n_map1, int cap, OdomShared* sh, long long frame) {
+    if (threadIdx.x != 0) return;
+    if (*n_map0 > cap || *n_map1 > cap) atomicOr(&sh->err, 1);
+    sh->n_map[0] = *n_map0;
+    sh->n_map[1] = *n_map1;
+    sh->frame = frame;
 }
 
 }  // namespace pf
@@ -163,6 +169,19 @@ struct pf_odom {
     bool inited = false;
     int optimization_count = 2;          // :198
     int last_passes = 0;
+    // host-side upper bounds of the device-resident counts (launch geometry only; the kernels read the exact counts)
+    int map_ub[2] = {0, 0};
+    static constexpr int kRing = 32;
+    OdomShared* h_ring = nullptr;        // pinned [kRing]: asynchronous read-back of the shared block after every frame
+    cudaEvent_t ring_ev[kRing] = {};
+    long long ring_frame[kRing] = {};
+    int ring_add[kRing][2] = {};
+    long long ring_head = 0;             // frames recorded in the ring
+    long long known_frame = -1;          // newest frame whose exact map sizes have been folded into map_ub
+    // optional phase timing (PF_ODOM_TIMING=1): CUDA events at the phase boundaries of the last update
+    bool timing = false;
+    cudaEvent_t tev[8] = {};
+    float phase_ms[8] = {};
 };
 
 namespace {
@@ -206,6 +225,10 @@ int odom_alloc(pf_odom* h) {
     PF_CUDA(cudaMallocHost(&h->h_state, sizeof(LmState)));
     PF_CUDA(cudaMallocHost(&h->h_counts, sizeof(int) * 8));
     PF_CUDA(cudaMallocHost(&h->h_iter, sizeof(double) * 16 * 7));
+    PF_CUDA(cudaMallocHost(&h->h_ring, sizeof(OdomShared) * pf_odom::kRing));
+    h->timing = getenv("PF_ODOM_TIMING") != nullptr;
+    if (h->timing) for (int i = 0; i < 8; ++i) PF_CUDA(cudaEventCreate(&h->tev[i]));
+    for (int i = 0; i < pf_odom::kRing; ++i) PF_CUDA(cudaEventCreateWithFlags(&h->ring_ev[i], cudaEventDisableTiming));
     k_odom_reset<<<1, 32, 0, h->stream>>>(h->d_sh, h->d_state);
     PF_CUDA(cudaStreamSynchronize(h->stream));
     return PF_OK;
@@ -221,7 +244,37 @@ int upload_features(pf_odom* h, const float* edge, int ne, const float* surf, in
     return PF_OK;
 }
 
-int enqueue_init(pf_odom* h, const float4* const feat[2], const int* const n_feat[2]) {
+// asynchronous read-back of the shared block: lets later frames size their launches from exact map counts
+int ring_record(pf_odom* h, int add_e, int add_s) {
+    const int slot = (int)(h->ring_head % pf_odom::kRing);
+    PF_CUDA(cudaMemcpyAsync(h->h_ring + slot, h->d_sh, sizeof(OdomShared), cudaMemcpyDeviceToHost, h->stream));
+    PF_CUDA(cudaEventRecord(h->ring_ev[slot], h->stream));
+    h->ring_frame[slot] = h->frame;
+    h->ring_add[slot][0] = add_e; h->ring_add[slot][1] = add_s;
+    h->ring_head += 1;
+    return PF_OK;
+}
+
+void ring_refresh(pf_odom* h) {
+    // newest completed read-back wins; frames enqueued after it contribute their (upper-bound) additions
+    const long long lo = h->ring_head > pf_odom::kRing ? h->ring_head - pf_odom::kRing : 0;
+    for (long long i = h->ring_head - 1; i >= lo; --i) {
+        const int slot = (int)(i % pf_odom::kRing);
+        if (h->ring_frame[slot] <= h->known_frame) break;
+        if (cudaEventQuery(h->ring_ev[slot]) != cudaSuccess) continue;
+        int ub[2] = {h->h_ring[slot].n_map[0], h->h_ring[slot].n_map[1]};
+        for (long long j = i + 1; j < h->ring_head; ++j) {
+            const int sj = (int)(j % pf_odom::kRing);
+            ub[0] += h->ring_add[sj][0]; ub[1] += h->ring_add[sj][1];
+        }
+        for (int k = 0; k < 2; ++k) h->map_ub[k] = ub[k] < h->bufcap ? ub[k] : h->bufcap;
+        h->known_frame = h->ring_frame[slot];
+        break;
+    }
+    cudaGetLastError();   // cudaErrorNotReady from the queries is not an error
+}
+
+int enqueue_init(pf_odom* h, const float4* const feat[2], const int* const n_feat[2], int ub_e, int ub_s) {
     InitParams I{};
     for (int k = 0; k < 2; ++k) { I.feat[k] = feat[k]; I.n_feat[k] = n_feat[k]; I.map[k] = h->d_map[h->cur][k]; I.n_map[k] = h->d_nmap[h->cur] + k; }
     I.map_cap = h->mcap;
@@ -231,16 +284,28 @@ int enqueue_init(pf_odom* h, const float4* const feat[2], const int* const n_fea
     PF_CUDA(cudaGetLastError());
     h->optimization_count = 12;   // :221
     h->inited = true;
+    h->map_ub[0] = ub_e < h->mcap ? ub_e : h->mcap;
+    h->map_ub[1] = ub_s < h->mcap ? ub_s : h->mcap;
+    h->frame = 0;
+    PF_CHECK(ring_record(h, 0, 0));
     h->frame = 1;
     return PF_OK;
 }
 
-int enqueue_update(pf_odom* h, const float4* const feat[2], const int* const n_feat[2], int fcap_in) {
+int enqueue_update(pf_odom* h, const float4* const feat[2], const int* const n_feat[2], int ub_e, int ub_s) {
     if (h->optimization_count > 2) h->optimization_count--;   // :232-233
+    ring_refresh(h);
+    if (ub_e > h->fcap) ub_e = h->fcap;
+    if (ub_s > h->fcap) ub_s = h->fcap;
+    if (ub_e < 1) ub_e = 1;
+    if (ub_s < 1) ub_s = 1;
+    const int mub_e = h->map_ub[0] > 1 ? h->map_ub[0] : 1, mub_s = h->map_ub[1] > 1 ? h->map_ub[1] : 1;
     const int passes = h->optimization_count;
     h->last_passes = passes;
     Workspace& ws = h->ws;
     const int cur = h->cur, nxt = cur ^ 1;
+    auto mark = [&](int i) { if (h->timing) cudaEventRecord(h->tev[i], h->stream); };
+    mark(0);
     PF_CHECK(workspace_begin_step(ws));
     k_predict<<<1, 32, 0, h->stream>>>(h->d_sh, h->d_state);
     ws.launches += 1;
@@ -250,14 +315,16 @@ int enqueue_update(pf_odom* h, const float4* const feat[2], const int* const n_f
     const float leaf[2] = {(float)h->prm.map_resolution, (float)(h->prm.map_resolution * 2)};
     for (int k = 0; k < 2; ++k)
         V.c[k] = VoxCloud{reinterpret_cast<const Pt*>(feat[k]), n_feat[k], h->d_ds[k], h->d_nds + k, leaf[k], 1};
-    PF_CHECK(voxelize(ws, V, 0, fcap_in, fcap_in));
+    PF_CHECK(voxelize(ws, V, 0, ub_e, ub_s));
+    mark(1);
     // search grids over the current maps
     GridBuild G{};
     for (int k = 0; k < 2; ++k) {
         G.map[k] = h->d_map[cur][k]; G.n_map[k] = h->d_nmap[cur] + k; G.pts[k] = h->d_gpts[k];
         G.cell_start[k] = h->d_cs[k]; G.cell_end[k] = h->d_ce[k]; G.geom[k] = h->d_geom + 6 * k;
     }
-    PF_CHECK(build_grids(ws, G, 2, h->mcap, h->mcap));
+    PF_CHECK(build_grids(ws, G, 2, mub_e, mub_s));
+    mark(2);
     // optimisation passes
     AssocParams A{};
     LmParams L{};
@@ -273,9 +340,11 @@ int enqueue_update(pf_odom* h, const float4* const feat[2], const int* const n_f
     L.state = h->d_state; L.partials = h->d_partials; L.ticket = h->d_ticket; L.iter_poses = h->d_iter_poses; L.eval_only = 0;
     for (int it = 0; it < passes; ++it) {
         PF_CHECK(lm_begin(h->stream, L, nullptr, it == 0, &ws.launches));
-        PF_CHECK(associate_pass(h->stream, A, fcap_in, fcap_in, &ws.launches));
+        PF_CHECK(associate_pass(h->stream, A, ub_e, ub_s, &ws.launches));
+        if (it == passes - 1) mark(3);
         for (int e = 0; e < kLmEvalsPerSolve; ++e) PF_CHECK(lm_eval(h->stream, L, &ws.launches));
     }
+    mark(4);
     // append + map maintenance
     AppendParams P{};
     for (int k = 0; k < 2; ++k) { P.ds[k] = h->d_ds[k]; P.n_ds[k] = h->d_nds + k; P.map[k] = h->d_map[cur][k]; P.n_map[k] = h->d_nmap[cur] + k; }
@@ -292,11 +361,15 @@ int enqueue_update(pf_odom* h, const float4* const feat[2], const int* const n_f
         M.c[k] = VoxCloud{h->d_map[cur][k], h->d_sh->n_app + k, h->d_map[nxt][k], h->d_nmap[nxt] + k, mleaf[k], 0};
     M.center = h->d_sh->odom.t;
     M.k_new = h->prm.k_new; M.theta_p = h->prm.theta_p; M.theta_max = h->prm.theta_max;
-    PF_CHECK(voxelize(ws, M, 1, h->bufcap, h->bufcap));
-    k_check_map_cap<<<1, 32, 0, h->stream>>>(h->d_nmap[nxt], h->d_nmap[nxt] + 1, h->mcap, h->d_sh);
+    const int app_e = mub_e + ub_e < h->bufcap ? mub_e + ub_e : h->bufcap, app_s = mub_s + ub_s < h->bufcap ? mub_s + ub_s : h->bufcap;
+    PF_CHECK(voxelize(ws, M, 1, app_e, app_s));
+    k_check_map_cap<<<1, 32, 0, h->stream>>>(h->d_nmap[nxt], h->d_nmap[nxt] + 1, h->mcap, h->d_sh, h->frame);
     ws.launches += 1;
     PF_CUDA(cudaGetLastError());
     h->cur = nxt;
+    mark(5);
+    h->map_ub[0] = app_e; h->map_ub[1] = app_s;     // the update never grows a map beyond old + appended
+    PF_CHECK(ring_record(h, ub_e, ub_s));
     h->frame += 1;
     return PF_OK;
 }
@@ -309,6 +382,10 @@ int finish_frame(pf_odom* h, double pose_out[7]) {
         return PF_ERR_CAPACITY;
     }
     if (pose_out) memcpy(pose_out, h->h_sh->pose, sizeof(double) * 7);
+    if (h->inited) {
+        h->map_ub[0] = h->h_sh->n_map[0]; h->map_ub[1] = h->h_sh->n_map[1];
+        h->known_frame = h->frame - 1;
+    }
     return PF_OK;
 }
 
@@ -353,7 +430,8 @@ extern "C" int pf_odom_destroy(pf_odom* h) {
         cudaFree(h->d_next[k]); cudaFree(h->d_nn[k]); cudaFree(h->d_flag[k]); cudaFree(h->d_g8[k]);
     }
     cudaFree(h->d_state); cudaFree(h->d_partials); cudaFree(h->d_iter_poses); cudaFree(h->d_ticket); cudaFree(h->d_sh); cudaFree(h->d_pose_hist);
-    cudaFreeHost(h->h_sh); cudaFreeHost(h->h_state); cudaFreeHost(h->h_counts); cudaFreeHost(h->h_iter);
+    cudaFreeHost(h->h_sh); cudaFreeHost(h->h_state); cudaFreeHost(h->h_counts); cudaFreeHost(h->h_iter); cudaFreeHost(h->h_ring);
+    for (int i = 0; i < pf_odom::kRing; ++i) if (h->ring_ev[i]) cudaEventDestroy(h->ring_ev[i]);
     if (h->ev) cudaEventDestroy(h->ev);
     if (h->ev_done) cudaEventDestroy(h->ev_done);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -367,7 +445,7 @@ extern "C" int pf_odom_init_map(pf_odom* h, const float* edge, int n_edge, const
     PF_CHECK(upload_features(h, edge, n_edge, surf, n_surf));
     const float4* feat[2] = {h->d_feat[0], h->d_feat[1]};
     const int* nf[2] = {h->d_nfeat, h->d_nfeat + 1};
-    PF_CHECK(enqueue_init(h, feat, nf));
+    PF_CHECK(enqueue_init(h, feat, nf, n_edge, n_surf));
     return finish_frame(h, nullptr);
 }
 
@@ -378,7 +456,7 @@ extern "C" int pf_odom_update(pf_odom* h, const float* edge, int n_edge, const f
     PF_CHECK(upload_features(h, edge, n_edge, surf, n_surf));
     const float4* feat[2] = {h->d_feat[0], h->d_feat[1]};
     const int* nf[2] = {h->d_nfeat, h->d_nfeat + 1};
-    PF_CHECK(enqueue_update(h, feat, nf, h->fcap));
+    PF_CHECK(enqueue_update(h, feat, nf, n_edge, n_surf));
     return finish_frame(h, pose_out);
 }
 
@@ -390,13 +468,13 @@ static int process_extracted(pf_odom* h, pf_extract* ex, double pose_out[7], boo
     cudaStream_t exs;
     int ecap, scap;
     pf_extract_device_outputs(ex, &feat[0], &nf[0], &feat[1], &nf[1], &exs, &ecap, &scap);
-    PF_REQUIRE(scap <= h->fcap, "extractor capacity %d exceeds max_features %d", scap, h->fcap);
+    PF_REQUIRE(scap <= h->fcap, "scan of %d points exceeds max_features %d", scap, h->fcap);
     PF_CUDA(cudaEventRecord(h->ev, exs));
     PF_CUDA(cudaStreamWaitEvent(h->stream, h->ev, 0));
     if (!h->inited) {
-        PF_CHECK(enqueue_init(h, feat, nf));
+        PF_CHECK(enqueue_init(h, feat, nf, ecap, scap));
     } else {
-        PF_CHECK(enqueue_update(h, feat, nf, scap));
+        PF_CHECK(enqueue_update(h, feat, nf, ecap, scap));
     }
     // the extractor's output buffers are reused by the next frame: it must not start before this frame consumed them
     PF_CUDA(cudaEventRecord(h->ev_done, h->stream));
@@ -499,6 +577,16 @@ extern "C" int pf_odom_get_stats(pf_odom* h, pf_odom_stats* s) {
     s->n_edge_res = h->h_state->n_edge_res; s->n_surf_res = h->h_state->n_surf_res;
     s->passes = h->last_passes;
     s->lm_iterations = h->h_state->iter;
+    return PF_OK;
+}
+
+// Phase timing of the last update (needs PF_ODOM_TIMING=1 at create time): ms[0] predict + down-sample, ms[1] grid build,
+// ms[2] passes up to the last association, ms[3] last pass's 5 LM evaluations, ms[4] append + map maintenance.
+extern "C" int pf_odom_get_phase_ms(pf_odom* h, float ms[5]) {
+    PF_REQUIRE(h && ms, "null argument");
+    PF_REQUIRE(h->timing, "phase timing is off (set PF_ODOM_TIMING=1 before pf_odom_create)");
+    PF_CUDA(cudaStreamSynchronize(h->stream));
+    for (int i = 0; i < 5; ++i) PF_CUDA(cudaEventElapsedTime(&ms[i], h->tev[i], h->tev[i + 1]));
     return PF_OK;
 }
 

@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(256) k_sort_scan(uint32_t* __restrict__ hist, 
 __global__ void __launch_bounds__(kSortThreads) k_sort_scatter(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                                                                uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
                                                                const int* __restrict__ n_dev, int shift, const uint32_t* __restrict__ hist,
-                                                               const uint32_t* __restrict__ totals, int nb_cap) {
+                                                               const uint32_t* __restrict__ totals, int nb_cap, int fused_scan) {
     const int n = *n_dev;
     const int ntiles = (n + kSortTile - 1) / kSortTile;
     __shared__ unsigned wc[kSortThreads / 32][kRadix];   // warp-private digit counters -> exclusive bases
@@ -92,9 +92,21 @@ __global__ void __launch_bounds__(kSortThreads) k_sort_scatter(const uint32_t* _
     // digit tid: exclusive prefix over the 8 warps, plus the global base of the digit for this tile
     {
         int tot;
-        unsigned t = totals[tid];
+        unsigned t, before;
+        if (fused_scan) {   // few tiles: every CTA scans the raw per-tile histogram itself (saves the k_sort_scan launch)
+            t = 0; before = 0;
+            const uint32_t* row = hist + (size_t)tid * nb_cap;
+            for (int bb = 0; bb < ntiles; ++bb) {
+                const unsigned v = row[bb];
+                t += v;
+                if (bb < b) before += v;
+            }
+        } else {
+            t = totals[tid];
+            before = hist[(size_t)tid * nb_cap + b];
+        }
         int dbase = block_scan_excl_256((int)t, tmp, &tot);
-        unsigned run = (unsigned)dbase + hist[(size_t)tid * nb_cap + b];
+        unsigned run = (unsigned)dbase + before;
 #pragma unroll
         for (int k = 0; k < kSortThreads / 32; ++k) {
             unsigned c = wc[k][tid];
@@ -158,14 +170,15 @@ int radix_sort(Workspace& ws, const int* n_dev, int n_cap, int passes, bool vals
     int nb = div_up(n_cap, kSortTile);
     *result_buf = passes & 1;
     if (nb == 0) return PF_OK;
+    const int fused = nb <= 96 ? 1 : 0;
     if (nb > 4 * kSMs) nb = 4 * kSMs;
     for (int p = 0; p < passes; ++p) {
         const int src = p & 1, dst = src ^ 1, shift = p * kRadixBits;
         k_sort_hist<<<nb, kSortThreads, 0, ws.stream>>>(ws.keys[src], n_dev, shift, ws.hist, ws.nb_cap);
-        k_sort_scan<<<kRadix / 8, 256, 0, ws.stream>>>(ws.hist, n_dev, ws.nb_cap, ws.totals);
+        if (!fused) k_sort_scan<<<kRadix / 8, 256, 0, ws.stream>>>(ws.hist, n_dev, ws.nb_cap, ws.totals);
         k_sort_scatter<<<nb, kSortThreads, 0, ws.stream>>>(ws.keys[src], (p == 0 && vals_iota) ? nullptr : ws.vals[src], ws.keys[dst],
-                                                           ws.vals[dst], n_dev, shift, ws.hist, ws.totals, ws.nb_cap);
-        ws.launches += 3;
+                                                           ws.vals[dst], n_dev, shift, ws.hist, ws.totals, ws.nb_cap, fused);
+        ws.launches += fused ? 2 : 3;
     }
     PF_CUDA(cudaGetLastError());
     return PF_OK;

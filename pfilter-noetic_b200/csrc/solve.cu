@@ -69,8 +69,13 @@ __device__ double vec_norm7(const double* x) {
     return sqrt(s);
 }
 
-// gradient_max_norm of Ceres: | x - Plus(x, -g) |_inf
+// gradient_max_norm of Ceres: | x - Plus(x, -g) |_inf.  The tolerance is 1e-10: the exponential map is only evaluated
+// when the plain max-norm of g is anywhere near it (|x - Plus(x,-g)| <= |g| (1 + |x|) for such tiny g).
 __device__ double gradient_max_norm(const double* x, const double* g) {
+    double gm = 0;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) gm = fmax(gm, fabs(g[k]));
+    if (gm > 1e-6) return gm;
     double ng[6], xp[7];
     for (int k = 0; k < 6; ++k) ng[k] = -g[k];
     se3_plus(x, ng, xp);
@@ -90,20 +95,30 @@ __device__ void lm_propose(const LmParams& P, LmState* S) {
     while (true) {
         if (S->iter >= 4) { lm_finish(P, S); return; }               // max_num_iterations = 4 (:265)
         S->iter += 1;
-        double Hs[21], gs[6];
-        int t = 0;
-        for (int a = 0; a < 6; ++a)
-            for (int b = a; b < 6; ++b) { Hs[t] = S->H[t] * S->scale[a] * S->scale[b]; ++t; }
-        for (int a = 0; a < 6; ++a) gs[a] = S->g[a] * S->scale[a];
+        double Hs[21], gs[6], sc[6];
+#pragma unroll
+        for (int a = 0; a < 6; ++a) sc[a] = S->scale[a];
+        {
+            int t = 0;
+#pragma unroll
+            for (int a = 0; a < 6; ++a)
+#pragma unroll
+                for (int b = a; b < 6; ++b) { Hs[t] = S->H[t] * sc[a] * sc[b]; ++t; }
+        }
+#pragma unroll
+        for (int a = 0; a < 6; ++a) gs[a] = S->g[a] * sc[a];
+        constexpr int dpos[6] = {0, 6, 11, 15, 18, 20};
         if (!S->reuse_diag) {
-            const int dpos[6] = {0, 6, 11, 15, 18, 20};
+#pragma unroll
             for (int a = 0; a < 6; ++a) S->diag[a] = fmin(fmax(Hs[dpos[a]], 1e-6), 1e32);   // min/max_lm_diagonal
         }
         double A[21];
         {
-            const int dpos[6] = {0, 6, 11, 15, 18, 20};
+            const double inv_radius = 1.0 / S->radius;
+#pragma unroll
             for (int k = 0; k < 21; ++k) A[k] = Hs[k];
-            for (int a = 0; a < 6; ++a) A[dpos[a]] += S->diag[a] / S->radius;
+#pragma unroll
+            for (int a = 0; a < 6; ++a) A[dpos[a]] += S->diag[a] * inv_radius;
         }
         double y[6];
         bool ok = chol6_solve(A, gs, y);                              // (J^T J + D^T D) y = J^T r ; step = -y
@@ -111,15 +126,19 @@ __device__ void lm_propose(const LmParams& P, LmState* S) {
         double mcc = 0;
         if (ok) {
             double st[6];
+#pragma unroll
             for (int a = 0; a < 6; ++a) st[a] = -y[a];
             // model_cost_change = -(step . g_s + 1/2 step^T H_s step)
             double sg = 0, sHs = 0;
             int k = 0;
+#pragma unroll
             for (int a = 0; a < 6; ++a) {
                 sg += st[a] * gs[a];
+#pragma unroll
                 for (int b = a; b < 6; ++b) { sHs += (a == b ? 1.0 : 2.0) * st[a] * Hs[k] * st[b]; ++k; }
             }
             mcc = -(sg + 0.5 * sHs);
+#pragma unroll
             for (int a = 0; a < 6; ++a) S->step[a] = st[a];
         }
         if (!ok || !(mcc > 0)) {                                      // invalid step == rejected with zero quality
@@ -210,11 +229,13 @@ __global__ void __launch_bounds__(256) k_lm_eval(LmParams P) {
             if (kind == 0) ++cnt_edge;
         }
     }
-    // warp reduction, fixed tree
+    // warp reduction, fixed tree (skipped by warps that evaluated nothing: their partial is exactly zero)
+    if (__any_sync(0xffffffffu, acc[28] != 0.0)) {
 #pragma unroll
-    for (int k = 0; k < kAcc; ++k) {
+        for (int k = 0; k < kAcc; ++k) {
 #pragma unroll
-        for (int o = 16; o >= 1; o >>= 1) acc[k] += __shfl_down_sync(0xffffffffu, acc[k], o);
+            for (int o = 16; o >= 1; o >>= 1) acc[k] += __shfl_down_sync(0xffffffffu, acc[k], o);
+        }
     }
     cnt_edge = __reduce_add_sync(0xffffffffu, cnt_edge);
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -247,17 +268,34 @@ __global__ void __launch_bounds__(256) k_lm_eval(LmParams P) {
     __shared__ double s_sum[32];
     if (threadIdx.x < 32) {
         double s = 0;
-        if (threadIdx.x < kAcc || threadIdx.x == 31)
-            for (unsigned b = 0; b < gridDim.x; ++b) s += __ldcg(P.partials + b * 32 + threadIdx.x);
+        if (threadIdx.x < kAcc || threadIdx.x == 31) {
+            double v[kLmBlocks];
+#pragma unroll
+            for (int b = 0; b < kLmBlocks; ++b) v[b] = __ldcg(P.partials + b * 32 + threadIdx.x);   // independent loads in flight
+#pragma unroll
+            for (int b = 0; b < kLmBlocks; ++b) s += v[b];                                         // fixed order: deterministic
+        }
         s_sum[threadIdx.x] = s;
+    }
+    // the state machine runs on a shared-memory copy of the state (one coalesced read, one coalesced write-back)
+    __shared__ LmState s_state;
+    {
+        const unsigned* src = reinterpret_cast<const unsigned*>(S);
+        unsigned* dst = reinterpret_cast<unsigned*>(&s_state);
+        for (unsigned i = threadIdx.x; i < sizeof(LmState) / 4; i += blockDim.x) dst[i] = __ldcg(src + i);
     }
     __syncthreads();
     if (threadIdx.x == 0) {
         *P.ticket = 0;
-        S->n_edge_res = (int)s_sum[31];
-        S->n_surf_res = (int)s_sum[28] - (int)s_sum[31];
-        lm_advance(P, S, s_sum);
-        __threadfence();
+        s_state.n_edge_res = (int)s_sum[31];
+        s_state.n_surf_res = (int)s_sum[28] - (int)s_sum[31];
+        lm_advance(P, &s_state, s_sum);
+    }
+    __syncthreads();
+    {
+        unsigned* dst = reinterpret_cast<unsigned*>(S);
+        const unsigned* src = reinterpret_cast<const unsigned*>(&s_state);
+        for (unsigned i = threadIdx.x; i < sizeof(LmState) / 4; i += blockDim.x) dst[i] = src[i];
     }
 }
 

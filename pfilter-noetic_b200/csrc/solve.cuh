@@ -42,7 +42,7 @@ struct LmParams {
     int eval_only;            // stage tap: evaluate at state->x and stop
 };
 
-constexpr int kLmBlocks = 148;
+constexpr int kLmBlocks = 32;    // 8192 threads cover a frame's residual blocks in one grid-stride step
 constexpr int kLmEvalsPerSolve = 5;   // 1 initial evaluation + max_num_iterations (4) candidates
 
 // pose_src: device pose to start from (null: keep state->x); resets the per-solve fields.

@@ -171,33 +171,39 @@ __global__ void __launch_bounds__(256) k_vox_reduce(VoxParams P, const uint32_t*
         const unsigned key = keys[p];
         const bool head = (p == start) || (keys[p - 1] != key);
         if (head) {
+            // segment end first (contiguous key reads), then the ordered sum with 8 independent gathers in flight
+            int e = p + 1;
+            while (e < end && keys[e] == key) ++e;
             float sx = 0.f, sy = 0.f, sz = 0.f;
-            int cnt = 0;
-            if (P.mode == VOX_PCL) {
-                float sr = 0.f, sg = 0.f, sb = 0.f, sa = 0.f;
-                for (int q = p; q < end && keys[q] == key; ++q) {
-                    Pt v = load_pt(c, (int)vals[q] - ibase);
-                    sx = __fadd_rn(sx, v.x); sy = __fadd_rn(sy, v.y); sz = __fadd_rn(sz, v.z);
-                    sr += (float)(v.rgba & 0xff); sg += (float)((v.rgba >> 8) & 0xff);
-                    sb += (float)((v.rgba >> 16) & 0xff); sa += (float)(v.rgba >> 24);
-                    ++cnt;
+            float sr = 0.f, sg = 0.f, sb = 0.f, sa = 0.f;
+            int rmax = -1, gmax = -1;
+            const bool pcl = P.mode == VOX_PCL;
+            for (int q = p; q < e; q += 8) {
+                Pt v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+                    if (q + u < e) v[u] = load_pt(c, (int)vals[q + u] - ibase);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    if (q + u < e) {
+                        sx = __fadd_rn(sx, v[u].x); sy = __fadd_rn(sy, v[u].y); sz = __fadd_rn(sz, v[u].z);
+                        if (pcl) {
+                            sr += (float)(v[u].rgba & 0xff); sg += (float)((v[u].rgba >> 8) & 0xff);
+                            sb += (float)((v[u].rgba >> 16) & 0xff); sa += (float)(v[u].rgba >> 24);
+                        } else {
+                            rmax = max(rmax, (int)pt_r(v[u].rgba));
+                            gmax = max(gmax, (int)pt_g(v[u].rgba));
+                        }
+                    }
                 }
-                const float fn = (float)cnt;
-                o.x = __fdiv_rn(sx, fn); o.y = __fdiv_rn(sy, fn); o.z = __fdiv_rn(sz, fn);
+            }
+            const float fn = (float)(e - p);
+            o.x = __fdiv_rn(sx, fn); o.y = __fdiv_rn(sy, fn); o.z = __fdiv_rn(sz, fn);
+            if (pcl) {
                 o.rgba = pack_rgba((unsigned)__fdiv_rn(sr, fn) & 0xff, (unsigned)__fdiv_rn(sg, fn) & 0xff,
                                    (unsigned)__fdiv_rn(sb, fn) & 0xff, (unsigned)__fdiv_rn(sa, fn) & 0xff);
                 keep = true;
             } else {
-                int rmax = -1, gmax = -1;
-                for (int q = p; q < end && keys[q] == key; ++q) {
-                    Pt v = load_pt(c, (int)vals[q] - ibase);
-                    sx = __fadd_rn(sx, v.x); sy = __fadd_rn(sy, v.y); sz = __fadd_rn(sz, v.z);
-                    rmax = max(rmax, (int)pt_r(v.rgba));
-                    gmax = max(gmax, (int)pt_g(v.rgba));
-                    ++cnt;
-                }
-                const float fn = (float)cnt;
-                o.x = __fdiv_rn(sx, fn); o.y = __fdiv_rn(sy, fn); o.z = __fdiv_rn(sz, fn);
                 // extractstablepoint (:12-14): drop if g < r*theta_p && r > k_new && g < theta_max + 1
                 const bool drop = ((float)gmax < __fmul_rn((float)rmax, P.theta_p)) && (rmax > P.k_new) && (gmax < P.theta_max + 1);
                 keep = !drop;
