@@ -134,7 +134,7 @@ using namespace pf;
 // accessors implemented in extract.cu
 void pf_extract_device_outputs(pf_extract* h, const float4** edge, const int** n_edge, const float4** surf, const int** n_surf,
                                cudaStream_t* stream, int* edge_cap, int* surf_cap);
-int pf_extract_enqueue_single(pf_extract* h, const float* xyzi, int n, int device_input);
+int pf_extract_enqueue_single(pf_extract* h, const float* xyzi, int n, int device_input, int want_label);
 
 struct pf_odom {
     int device = 0;
@@ -488,13 +488,13 @@ extern "C" int pf_odom_process_extracted(pf_odom* h, pf_extract* ex, double pose
 
 extern "C" int pf_frame_process(pf_extract* ex, pf_odom* od, const float* xyzi, int n, double pose_out[7]) {
     PF_REQUIRE(ex && od, "null handle");
-    PF_CHECK(pf_extract_enqueue_single(ex, xyzi, n, 0));
+    PF_CHECK(pf_extract_enqueue_single(ex, xyzi, n, 0, 0));
     return process_extracted(od, ex, pose_out, true);
 }
 
 extern "C" int pf_frame_process_device(pf_extract* ex, pf_odom* od, const void* d_xyzi, int n, double* pose_out) {
     PF_REQUIRE(ex && od, "null handle");
-    PF_CHECK(pf_extract_enqueue_single(ex, (const float*)d_xyzi, n, 1));
+    PF_CHECK(pf_extract_enqueue_single(ex, (const float*)d_xyzi, n, 1, 0));
     return process_extracted(od, ex, pose_out, pose_out != nullptr);
 }
 

@@ -77,3 +77,58 @@ def test_extract_ring_capacity_error(capi, cfg2_scans):
     with pytest.raises(capi.PfError) as e:
         ex.run(scans[0])
     assert e.value.status == -3
+
+
+def test_extract_quantised_coordinates_exact_ties(capi, oracle, cfg2_scans):
+    """Coordinates snapped to a 1/32 m lattice: curvature values collide exactly (and share key buckets), so the
+    selection has to fall back on the exact double value and on the index order (ties: lower ring position first in
+    the ascending sort = higher first in the descending walk)."""
+    _, scans = cfg2_scans
+    ex = capi.Extractor(num_lines=64, max_points=131072)
+    for q in (32.0, 8.0):
+        s = scans[2].copy()
+        s[:, :3] = np.round(s[:, :3] * q) / q
+        ref = oracle.extract(s, order=1)
+        # the lattice must actually produce tied candidates, otherwise this test checks nothing
+        _check(s, ex.run(s), ref)
+    assert len(ref["edge_idx"]) > 100
+
+
+def test_extract_near_equal_curvatures(capi, oracle, pfb):
+    """Curvatures that differ only below fp32 resolution (same 23-bit key bucket, different doubles)."""
+    rng = np.random.default_rng(5)
+    n_ring, rings = 1800, 64
+    az = np.linspace(-np.pi, np.pi, n_ring, endpoint=False)
+    pts = []
+    for r in range(rings):
+        el = np.deg2rad(1.95 - r / 3.0) if r < 32 else np.deg2rad(-8.68 - (r - 32) / 2.0)
+        rho = np.full(n_ring, 20.0)
+        # isolated identical spikes: every spike has (nearly) the same curvature; a 1e-7 relative perturbation
+        # keeps them in one fp32 bucket while making the exact doubles differ
+        spikes = np.arange(40, n_ring - 40, 23)
+        rho[spikes] += 0.5 * (1.0 + 1e-7 * rng.integers(-3, 4, len(spikes)))
+        x = rho * np.cos(el) * np.cos(az); y = rho * np.cos(el) * np.sin(az); z = rho * np.sin(el)
+        pts.append(np.stack([x, y, z, np.full(n_ring, r / 64.0)], 1))
+    s = np.ascontiguousarray(np.concatenate(pts).astype(np.float32))
+    ex = capi.Extractor(num_lines=64, max_points=131072)
+    ref = oracle.extract(s, order=1)
+    assert len(ref["edge_idx"]) > 64 * 6 * 5
+    _check(s, ex.run(s), ref)
+
+
+def test_extract_random_elevations_and_nonfinite(capi, oracle):
+    """Ring ids away from the bin centres: uniformly random elevations (many points close to bin boundaries and to the
+    validity gates), ranges straddling the 3 m / 90 m gate, plus NaN / inf coordinates (dropped by the reference)."""
+    rng = np.random.default_rng(11)
+    for lines, lo, hi, n in ((64, -27.0, 4.0, 100000), (32, -34.0, 14.0, 50000), (16, -18.0, 18.0, 25000)):
+        el = np.deg2rad(rng.uniform(lo, hi, n))
+        az = np.sort(rng.uniform(-np.pi, np.pi, n))
+        rho = rng.uniform(2.5, 95.0, n)
+        rho[:2000] = np.float32(3.0) / np.cos(el[:2000])        # horizontal range on the gate
+        s = np.stack([rho * np.cos(el) * np.cos(az), rho * np.cos(el) * np.sin(az), rho * np.sin(el), rng.uniform(0, 1, n)], 1)
+        s = np.ascontiguousarray(s.astype(np.float32))
+        s[5000, 0] = np.nan; s[5001, 2] = np.nan; s[5002, 1] = np.inf; s[5003, 2] = -np.inf
+        ex = capi.Extractor(num_lines=lines, max_points=131072, max_ring_points=3040)
+        ref = oracle.extract(s, num_lines=lines, order=1)
+        assert (ref["label"] > 0).sum() > n // 10
+        _check(s, ex.run(s), ref)
