@@ -156,8 +156,7 @@ struct pf_odom {
     uint8_t* d_flag[2] = {nullptr, nullptr};
     double* d_g8[2] = {nullptr, nullptr};
     LmState* d_state = nullptr;
-    double *d_partials = nullptr, *d_iter_poses = nullptr;
-    unsigned* d_ticket = nullptr;
+    double* d_iter_poses = nullptr;
     OdomShared* d_sh = nullptr;
     double* d_pose_hist = nullptr;       // [kPoseHist][7] pose of every update (ring buffer)
     long long frame = 0;                 // frames processed (frame 0 = init)
@@ -213,11 +212,8 @@ int odom_alloc(pf_odom* h) {
     }
     PF_CUDA(cudaMalloc(&h->d_state, sizeof(LmState)));
     PF_CUDA(cudaMemset(h->d_state, 0, sizeof(LmState)));
-    PF_CUDA(cudaMalloc(&h->d_partials, sizeof(double) * 32 * kLmBlocks));
     PF_CUDA(cudaMalloc(&h->d_iter_poses, sizeof(double) * 16 * 7));
     PF_CUDA(cudaMemset(h->d_iter_poses, 0, sizeof(double) * 16 * 7));
-    PF_CUDA(cudaMalloc(&h->d_ticket, sizeof(unsigned)));
-    PF_CUDA(cudaMemset(h->d_ticket, 0, sizeof(unsigned)));
     PF_CUDA(cudaMalloc(&h->d_sh, sizeof(OdomShared)));
     PF_CUDA(cudaMalloc(&h->d_pose_hist, sizeof(double) * 7 * kPoseHist));
     PF_CUDA(cudaMemset(h->d_pose_hist, 0, sizeof(double) * 7 * kPoseHist));
@@ -337,12 +333,11 @@ int enqueue_update(pf_odom* h, const float4* const feat[2], const int* const n_f
     A.pose = h->d_state->x;
     A.k_new = h->prm.k_new; A.theta_p = h->prm.theta_p; A.theta_max = h->prm.theta_max;
     A.min_edge_map = 10; A.min_surf_map = 50;   // :247
-    L.state = h->d_state; L.partials = h->d_partials; L.ticket = h->d_ticket; L.iter_poses = h->d_iter_poses; L.eval_only = 0;
+    L.state = h->d_state; L.iter_poses = h->d_iter_poses; L.eval_only = 0;
     for (int it = 0; it < passes; ++it) {
-        PF_CHECK(lm_begin(h->stream, L, nullptr, it == 0, &ws.launches));
         PF_CHECK(associate_pass(h->stream, A, ub_e, ub_s, &ws.launches));
         if (it == passes - 1) mark(3);
-        for (int e = 0; e < kLmEvalsPerSolve; ++e) PF_CHECK(lm_eval(h->stream, L, &ws.launches));
+        PF_CHECK(lm_solve(h->stream, L, nullptr, it == 0, &ws.launches));
     }
     mark(4);
     // append + map maintenance
@@ -429,7 +424,7 @@ extern "C" int pf_odom_destroy(pf_odom* h) {
         cudaFree(h->d_gpts[k]); cudaFree(h->d_cs[k]); cudaFree(h->d_ce[k]); cudaFree(h->d_head[k]); cudaFree(h->d_hits[k]);
         cudaFree(h->d_next[k]); cudaFree(h->d_nn[k]); cudaFree(h->d_flag[k]); cudaFree(h->d_g8[k]);
     }
-    cudaFree(h->d_state); cudaFree(h->d_partials); cudaFree(h->d_iter_poses); cudaFree(h->d_ticket); cudaFree(h->d_sh); cudaFree(h->d_pose_hist);
+    cudaFree(h->d_state); cudaFree(h->d_iter_poses); cudaFree(h->d_sh); cudaFree(h->d_pose_hist);
     cudaFreeHost(h->h_sh); cudaFreeHost(h->h_state); cudaFreeHost(h->h_counts); cudaFreeHost(h->h_iter); cudaFreeHost(h->h_ring);
     for (int i = 0; i < pf_odom::kRing; ++i) if (h->ring_ev[i]) cudaEventDestroy(h->ring_ev[i]);
     if (h->ev) cudaEventDestroy(h->ev);

@@ -1,13 +1,13 @@
 // Stable LSD radix sort (8-bit digits) of (u32 key, u32 value) pairs with a device-resident element count,
 // plus workspace management.  Three kernels per digit: per-tile digit histogram, per-digit scan across tiles,
 // stable scatter (warp-private digit counters keep the input order inside a tile).
+#include <cooperative_groups.h>
+
 #include "primitives.cuh"
 
 namespace pf {
 
-__global__ void __launch_bounds__(kSortThreads) k_sort_hist(const uint32_t* __restrict__ keys, const int* __restrict__ n_dev, int shift,
-                                                            uint32_t* __restrict__ hist, int nb_cap) {
-    const int n = *n_dev;
+__device__ __forceinline__ void d_sort_hist(const uint32_t* __restrict__ keys, int n, int shift, uint32_t* __restrict__ hist, int nb_cap) {
     const int ntiles = (n + kSortTile - 1) / kSortTile;
     __shared__ unsigned h[kRadix];
     for (int b = blockIdx.x; b < ntiles; b += gridDim.x) {   // persistent: the grid is bounded, tiles are not
@@ -28,15 +28,15 @@ __global__ void __launch_bounds__(kSortThreads) k_sort_hist(const uint32_t* __re
         }
         __syncthreads();
         hist[(size_t)threadIdx.x * nb_cap + b] = h[threadIdx.x];
+        __syncthreads();
     }
 }
 
 // one warp per digit: exclusive scan of hist[d][0..nb) in place, totals[d] = sum
-__global__ void __launch_bounds__(256) k_sort_scan(uint32_t* __restrict__ hist, const int* __restrict__ n_dev, int nb_cap,
-                                                   uint32_t* __restrict__ totals) {
-    const int n = *n_dev;
+__device__ __forceinline__ void d_sort_scan(uint32_t* __restrict__ hist, int n, int nb_cap, uint32_t* __restrict__ totals) {
     const int nb = (n + kSortTile - 1) / kSortTile;
-    const int d = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31;
+    for (int d = blockIdx.x * 8 + (threadIdx.x >> 5); d < kRadix; d += gridDim.x * 8) {
     uint32_t* row = hist + (size_t)d * nb_cap;
     unsigned carry = 0;
     for (int base = 0; base < nb; base += 32) {
@@ -51,13 +51,12 @@ __global__ void __launch_bounds__(256) k_sort_scan(uint32_t* __restrict__ hist, 
         carry += __shfl_sync(0xffffffffu, x, 31);
     }
     if (lane == 0) totals[d] = carry;
+    }
 }
 
-__global__ void __launch_bounds__(kSortThreads) k_sort_scatter(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
-                                                               uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
-                                                               const int* __restrict__ n_dev, int shift, const uint32_t* __restrict__ hist,
-                                                               const uint32_t* __restrict__ totals, int nb_cap, int fused_scan) {
-    const int n = *n_dev;
+__device__ __forceinline__ void d_sort_scatter(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
+                                               uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, int n, int shift,
+                                               const uint32_t* __restrict__ hist, const uint32_t* __restrict__ totals, int nb_cap, int fused_scan) {
     const int ntiles = (n + kSortTile - 1) / kSortTile;
     __shared__ unsigned wc[kSortThreads / 32][kRadix];   // warp-private digit counters -> exclusive bases
     __shared__ int tmp[9];
@@ -128,6 +127,33 @@ __global__ void __launch_bounds__(kSortThreads) k_sort_scatter(const uint32_t* _
     }
 }
 
+// One cooperative launch = the whole sort: per 8-bit digit { per-tile histogram | grid barrier | [digit scan | grid barrier] |
+// stable scatter | grid barrier }.  All CTAs are co-resident (grid <= SMs x occupancy, cudaLaunchCooperativeKernel), so the
+// barriers are cooperative-groups grid syncs and nothing returns to the host between digits.
+__global__ void __launch_bounds__(kSortThreads) k_sort_coop(uint32_t* keys0, uint32_t* vals0, uint32_t* keys1, uint32_t* vals1,
+                                                            const int* __restrict__ n_dev, int passes, int vals_iota, uint32_t* hist,
+                                                            uint32_t* totals, int nb_cap) {
+    cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+    const int n = *n_dev;
+    const int ntiles = (n + kSortTile - 1) / kSortTile;
+    const int fused = ntiles <= 96 ? 1 : 0;
+    for (int p = 0; p < passes; ++p) {
+        uint32_t* kin = (p & 1) ? keys1 : keys0;
+        uint32_t* vin = (p & 1) ? vals1 : vals0;
+        uint32_t* kout = (p & 1) ? keys0 : keys1;
+        uint32_t* vout = (p & 1) ? vals0 : vals1;
+        const int shift = p * kRadixBits;
+        d_sort_hist(kin, n, shift, hist, nb_cap);
+        grid.sync();
+        if (!fused) {
+            d_sort_scan(hist, n, nb_cap, totals);
+            grid.sync();
+        }
+        d_sort_scatter(kin, (p == 0 && vals_iota) ? nullptr : vin, kout, vout, n, shift, hist, totals, nb_cap, fused);
+        if (p + 1 < passes) grid.sync();
+    }
+}
+
 __global__ void k_begin_step(unsigned int* ctrl) {
     if (threadIdx.x == 0) ctrl[0] += 1;
     else if (threadIdx.x < kCtrlWords) ctrl[threadIdx.x] = 0;
@@ -170,17 +196,18 @@ int radix_sort(Workspace& ws, const int* n_dev, int n_cap, int passes, bool vals
     int nb = div_up(n_cap, kSortTile);
     *result_buf = passes & 1;
     if (nb == 0) return PF_OK;
-    const int fused = nb <= 96 ? 1 : 0;
-    if (nb > 4 * kSMs) nb = 4 * kSMs;
-    for (int p = 0; p < passes; ++p) {
-        const int src = p & 1, dst = src ^ 1, shift = p * kRadixBits;
-        k_sort_hist<<<nb, kSortThreads, 0, ws.stream>>>(ws.keys[src], n_dev, shift, ws.hist, ws.nb_cap);
-        if (!fused) k_sort_scan<<<kRadix / 8, 256, 0, ws.stream>>>(ws.hist, n_dev, ws.nb_cap, ws.totals);
-        k_sort_scatter<<<nb, kSortThreads, 0, ws.stream>>>(ws.keys[src], (p == 0 && vals_iota) ? nullptr : ws.vals[src], ws.keys[dst],
-                                                           ws.vals[dst], n_dev, shift, ws.hist, ws.totals, ws.nb_cap, fused);
-        ws.launches += fused ? 2 : 3;
+    if (ws.coop_blocks == 0) {
+        int per_sm = 0;
+        PF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sort_coop, kSortThreads, 0));
+        PF_REQUIRE(per_sm >= 1, "radix_sort: the cooperative sort kernel does not fit an SM");
+        if (per_sm > 2) per_sm = 2;
+        ws.coop_blocks = per_sm * kSMs;
     }
-    PF_CUDA(cudaGetLastError());
+    if (nb > ws.coop_blocks) nb = ws.coop_blocks;
+    int iota = vals_iota ? 1 : 0, nb_cap = ws.nb_cap;
+    void* args[] = {&ws.keys[0], &ws.vals[0], &ws.keys[1], &ws.vals[1], (void*)&n_dev, &passes, &iota, &ws.hist, &ws.totals, &nb_cap};
+    PF_CUDA(cudaLaunchCooperativeKernel((const void*)k_sort_coop, dim3(nb), dim3(kSortThreads), args, 0, ws.stream));
+    ws.launches += 1;
     return PF_OK;
 }
 

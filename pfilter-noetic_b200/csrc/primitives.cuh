@@ -30,6 +30,7 @@ struct Workspace {
     int status_stride = 0;
     unsigned int* ctrl = nullptr;             // [kCtrlWords]
     uint64_t launches = 0;
+    int coop_blocks = 0;                      // grid of the cooperative sort (SMs x resident CTAs), set on first use
 };
 
 int workspace_create(Workspace& ws, int cap, cudaStream_t stream);

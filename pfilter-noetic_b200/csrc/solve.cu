@@ -1,13 +1,16 @@
 // K7 / K8.  See solve.cuh.
 //
-// k_lm_eval: every thread walks a grid-stride slice of the residual blocks of both kinds, evaluates
+// k_lm_solve: every thread walks a grid-stride slice of the residual blocks of both kinds, evaluates
 //   edge (EdgeAnalyticCostFunction, src/lidarOptimization.cpp:12-46):  lp = q p + t, nu = (lp-a) x (lp-b), r = |nu| / |a-b|,
 //        J = -nu^T/|nu| [a-b]x [ -[lp]x  I ] / |a-b|
 //   surf (SurfNormAnalyticCostFunction, :56-78):                        r = n . lp + d,  J = n^T [ -[lp]x  I ]
 //   applies ceres::HuberLoss(0.1) with Ceres' corrector (rho'' <= 0 -> scale r and J by sqrt(rho')), accumulates the 21
 //   upper entries of J^T J, the 6 of J^T r and the cost in fp64 registers, reduces by warp shuffles + shared memory to one
-//   partial per CTA; the last CTA (atomic ticket) sums the partials in a fixed order (deterministic) and runs one transition
-//   of the Levenberg-Marquardt state machine, so one solver iteration is one launch and nothing returns to the host.
+//   partial per CTA; rank 0 of the 8-CTA cluster sums the partials in a fixed order through distributed shared memory
+//   (deterministic) and runs the Levenberg-Marquardt state machine, so a whole solve (<= 5 evaluations) is one launch
+//   and nothing returns to the host.
+#include <cooperative_groups.h>
+
 #include <vector>
 
 #include "solve.cuh"
@@ -156,7 +159,7 @@ __device__ void lm_propose(const LmParams& P, LmState* S) {
     }
 }
 
-__device__ void lm_advance(const LmParams& P, LmState* S, const double* sum) {
+__device__ __noinline__ void lm_advance(const LmParams& P, LmState* S, const double* sum) {
     for (int k = 0; k < 21; ++k) S->last_H[k] = sum[k];
     for (int k = 0; k < 6; ++k) S->last_g[k] = sum[21 + k];
     S->last_cost = sum[27];
@@ -202,123 +205,126 @@ __device__ void lm_advance(const LmParams& P, LmState* S, const double* sum) {
     lm_propose(P, S);
 }
 
-__global__ void __launch_bounds__(256) k_lm_eval(LmParams P) {
-    LmState* S = P.state;
-    const int phase = *reinterpret_cast<volatile int*>(&S->phase);
-    if (phase == 2) return;
-    __shared__ double s_pose[7];
-    __shared__ double s_red[8][kAcc];
-    __shared__ bool s_last;
-    if (threadIdx.x < 7) s_pose[threadIdx.x] = (phase == 0) ? S->x[threadIdx.x] : S->xc[threadIdx.x];
-    __syncthreads();
-    double acc[kAcc];
-#pragma unroll
-    for (int k = 0; k < kAcc; ++k) acc[k] = 0.0;
-    const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gstride = gridDim.x * blockDim.x;
-    int cnt_edge = 0;
-#pragma unroll
-    for (int kind = 0; kind < 2; ++kind) {
-        const ResidualSrc& R = P.src[kind];
-        const int n = R.n ? *R.n : 0;
-        for (int i = gtid; i < n; i += gstride) {
-            if (R.flag[i] != 2) continue;
-            D3 p;
-            if (R.p_override) p = d3(R.p_override[3 * i], R.p_override[3 * i + 1], R.p_override[3 * i + 2]);
-            else { const Pt q = R.queries[i]; p = d3((double)q.x, (double)q.y, (double)q.z); }
-            eval_one(kind, p, R.geom + 8 * (size_t)i, s_pose, acc);
-            if (kind == 0) ++cnt_edge;
-        }
-    }
-    // warp reduction, fixed tree (skipped by warps that evaluated nothing: their partial is exactly zero)
-    if (__any_sync(0xffffffffu, acc[28] != 0.0)) {
-#pragma unroll
-        for (int k = 0; k < kAcc; ++k) {
-#pragma unroll
-            for (int o = 16; o >= 1; o >>= 1) acc[k] += __shfl_down_sync(0xffffffffu, acc[k], o);
-        }
-    }
-    cnt_edge = __reduce_add_sync(0xffffffffu, cnt_edge);
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    __shared__ int s_cnt[8];
-    if (lane == 0) {
-#pragma unroll
-        for (int k = 0; k < kAcc; ++k) s_red[w][k] = acc[k];
-        s_cnt[w] = cnt_edge;
-    }
-    __syncthreads();
-    if (threadIdx.x < kAcc) {
-        double s = 0;
-        for (int k = 0; k < 8; ++k) s += s_red[k][threadIdx.x];
-        P.partials[blockIdx.x * 32 + threadIdx.x] = s;
-    }
-    if (threadIdx.x == 31) {
-        int c = 0;
-        for (int k = 0; k < 8; ++k) c += s_cnt[k];
-        P.partials[blockIdx.x * 32 + 31] = (double)c;
-    }
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const unsigned t = atomicAdd(P.ticket, 1u);
-        s_last = (t == gridDim.x - 1);
-    }
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
-    __shared__ double s_sum[32];
-    if (threadIdx.x < 32) {
-        double s = 0;
-        if (threadIdx.x < kAcc || threadIdx.x == 31) {
-            double v[kLmBlocks];
-#pragma unroll
-            for (int b = 0; b < kLmBlocks; ++b) v[b] = __ldcg(P.partials + b * 32 + threadIdx.x);   // independent loads in flight
-#pragma unroll
-            for (int b = 0; b < kLmBlocks; ++b) s += v[b];                                         // fixed order: deterministic
-        }
-        s_sum[threadIdx.x] = s;
-    }
-    // the state machine runs on a shared-memory copy of the state (one coalesced read, one coalesced write-back)
-    __shared__ LmState s_state;
-    {
-        const unsigned* src = reinterpret_cast<const unsigned*>(S);
+// One launch = one complete solve (ceres::Solve with max_num_iterations = 4): a cluster of kLmCluster CTAs evaluates the
+// residual blocks (one grid-stride sweep per evaluation), reduces the 29 sums deterministically (warp shuffles -> shared
+// memory -> rank 0 reads the CTA partials of its peers through distributed shared memory, fixed order) and thread 0 of
+// rank 0 runs the trust-region state machine on a shared-memory copy of the state; the next candidate pose travels back to
+// the peers through the same distributed shared memory.  Two cluster barriers per evaluation, nothing returns to the host.
+__global__ void __cluster_dims__(kLmCluster, 1, 1) __launch_bounds__(kLmThreads) k_lm_solve(LmParams P, const double* pose_src, int first_pass) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    const unsigned rank = cluster.block_rank();
+    constexpr int NW = kLmThreads / 32;
+    __shared__ double s_red[NW][kAcc];
+    __shared__ int s_cnt[NW];
+    __shared__ double s_part[32];          // this CTA's partial sums ([31] = edge count)
+    __shared__ double s_sum[32];           // rank 0: cluster totals
+    __shared__ LmState s_state;            // rank 0: the solver state
+    __shared__ double s_pose[8];           // pose to evaluate at; [7] = phase (as double) -- peers read rank 0's copy
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+
+    if (rank == 0) {
+        const unsigned* src = reinterpret_cast<const unsigned*>(P.state);
         unsigned* dst = reinterpret_cast<unsigned*>(&s_state);
-        for (unsigned i = threadIdx.x; i < sizeof(LmState) / 4; i += blockDim.x) dst[i] = __ldcg(src + i);
+        for (unsigned i = tid; i < sizeof(LmState) / 4; i += blockDim.x) dst[i] = src[i];
+        __syncthreads();
+        if (tid == 0) {   // lm_begin
+            if (pose_src) for (int k = 0; k < 7; ++k) s_state.x[k] = pose_src[k];
+            s_state.phase = 0;
+            s_state.iter = 0;
+            s_state.reuse_diag = 0;
+            s_state.pass = first_pass ? 0 : s_state.pass + 1;
+            for (int k = 0; k < 7; ++k) s_pose[k] = s_state.x[k];
+            s_pose[7] = 0.0;
+        }
     }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        *P.ticket = 0;
-        s_state.n_edge_res = (int)s_sum[31];
-        s_state.n_surf_res = (int)s_sum[28] - (int)s_sum[31];
-        lm_advance(P, &s_state, s_sum);
+    cluster.sync();
+    const double* pose0 = cluster.map_shared_rank(s_pose, 0);
+    const double* part_of[kLmCluster];
+#pragma unroll
+    for (int r = 0; r < kLmCluster; ++r) part_of[r] = cluster.map_shared_rank(s_part, r);
+
+    const int gtid = rank * blockDim.x + tid, gstride = kLmCluster * blockDim.x;
+    for (int round = 0; round < 8; ++round) {
+        double pose[7];
+#pragma unroll
+        for (int k = 0; k < 7; ++k) pose[k] = pose0[k];
+        if (pose0[7] != 0.0) break;           // finished (uniform across the cluster: read after a cluster barrier)
+        double acc[kAcc];
+#pragma unroll
+        for (int k = 0; k < kAcc; ++k) acc[k] = 0.0;
+        int cnt_edge = 0;
+#pragma unroll
+        for (int kind = 0; kind < 2; ++kind) {
+            const ResidualSrc& R = P.src[kind];
+            const int n = R.n ? *R.n : 0;
+            for (int i = gtid; i < n; i += gstride) {
+                if (R.flag[i] != 2) continue;
+                D3 p;
+                if (R.p_override) p = d3(R.p_override[3 * i], R.p_override[3 * i + 1], R.p_override[3 * i + 2]);
+                else { const Pt q = R.queries[i]; p = d3((double)q.x, (double)q.y, (double)q.z); }
+                eval_one(kind, p, R.geom + 8 * (size_t)i, pose, acc);
+                if (kind == 0) ++cnt_edge;
+            }
+        }
+        // warp reduction, fixed tree (skipped by warps that evaluated nothing: their partial is exactly zero)
+        if (__any_sync(0xffffffffu, acc[28] != 0.0)) {
+#pragma unroll
+            for (int k = 0; k < kAcc; ++k) {
+#pragma unroll
+                for (int o = 16; o >= 1; o >>= 1) acc[k] += __shfl_down_sync(0xffffffffu, acc[k], o);
+            }
+        }
+        cnt_edge = __reduce_add_sync(0xffffffffu, cnt_edge);
+        if (lane == 0) {
+#pragma unroll
+            for (int k = 0; k < kAcc; ++k) s_red[w][k] = acc[k];
+            s_cnt[w] = cnt_edge;
+        }
+        __syncthreads();
+        if (tid < kAcc) {
+            double s = 0;
+#pragma unroll
+            for (int k = 0; k < NW; ++k) s += s_red[k][tid];
+            s_part[tid] = s;
+        }
+        if (tid == 31) {
+            int c = 0;
+#pragma unroll
+            for (int k = 0; k < NW; ++k) c += s_cnt[k];
+            s_part[31] = (double)c;
+        }
+        cluster.sync();                        // all partials visible
+        if (rank == 0) {
+            if (tid < 32 && (tid < kAcc || tid == 31)) {
+                double s = 0;
+#pragma unroll
+                for (int r = 0; r < kLmCluster; ++r) s += part_of[r][tid];   // fixed order: deterministic
+                s_sum[tid] = s;
+            }
+            __syncthreads();
+            if (tid == 0) {
+                s_state.n_edge_res = (int)s_sum[31];
+                s_state.n_surf_res = (int)s_sum[28] - (int)s_sum[31];
+                lm_advance(P, &s_state, s_sum);
+                const double* nx = s_state.phase == 1 ? s_state.xc : s_state.x;
+                for (int k = 0; k < 7; ++k) s_pose[k] = nx[k];
+                s_pose[7] = s_state.phase == 2 ? 1.0 : 0.0;
+            }
+        }
+        cluster.sync();                        // next pose / phase visible; partials may be overwritten
     }
-    __syncthreads();
-    {
-        unsigned* dst = reinterpret_cast<unsigned*>(S);
+    if (rank == 0) {
+        __syncthreads();
+        unsigned* dst = reinterpret_cast<unsigned*>(P.state);
         const unsigned* src = reinterpret_cast<const unsigned*>(&s_state);
-        for (unsigned i = threadIdx.x; i < sizeof(LmState) / 4; i += blockDim.x) dst[i] = src[i];
+        for (unsigned i = tid; i < sizeof(LmState) / 4; i += blockDim.x) dst[i] = src[i];
     }
+    cluster.sync();                            // peers must not exit while rank 0 may still read their shared memory
 }
 
-__global__ void k_lm_begin(LmParams P, const double* pose_src, int first_pass) {
-    if (threadIdx.x != 0) return;
-    LmState* S = P.state;
-    if (pose_src) for (int k = 0; k < 7; ++k) S->x[k] = pose_src[k];
-    S->phase = 0;
-    S->iter = 0;
-    S->reuse_diag = 0;
-    S->pass = first_pass ? 0 : S->pass + 1;
-    *P.ticket = 0;
-}
-
-int lm_begin(cudaStream_t stream, const LmParams& P, const double* pose_src, int first_pass, uint64_t* launches) {
-    k_lm_begin<<<1, 32, 0, stream>>>(P, pose_src, first_pass);
-    if (launches) *launches += 1;
-    PF_CUDA(cudaGetLastError());
-    return PF_OK;
-}
-
-int lm_eval(cudaStream_t stream, const LmParams& P, uint64_t* launches) {
-    k_lm_eval<<<kLmBlocks, 256, 0, stream>>>(P);
+int lm_solve(cudaStream_t stream, const LmParams& P, const double* pose_src, int first_pass, uint64_t* launches) {
+    k_lm_solve<<<kLmCluster, kLmThreads, 0, stream>>>(P, pose_src, first_pass);
     if (launches) *launches += 1;
     PF_CUDA(cudaGetLastError());
     return PF_OK;
@@ -334,14 +340,13 @@ using namespace pf;
 namespace {
 struct SolveTap {
     cudaStream_t stream = nullptr;
-    double *d_p[2] = {nullptr, nullptr}, *d_geom[2] = {nullptr, nullptr}, *d_partials = nullptr;
+    double *d_p[2] = {nullptr, nullptr}, *d_geom[2] = {nullptr, nullptr};
     uint8_t* d_flag[2] = {nullptr, nullptr};
     int* d_n = nullptr;
-    unsigned* d_ticket = nullptr;
     LmState* d_state = nullptr;
     ~SolveTap() {
         for (int k = 0; k < 2; ++k) { cudaFree(d_p[k]); cudaFree(d_geom[k]); cudaFree(d_flag[k]); }
-        cudaFree(d_partials); cudaFree(d_n); cudaFree(d_ticket); cudaFree(d_state);
+        cudaFree(d_n); cudaFree(d_state);
         if (stream) cudaStreamDestroy(stream);
     }
 };
@@ -378,14 +383,10 @@ int solve_tap_setup(SolveTap& t, int device, const double pose[7], const double*
         }
         P.src[k] = ResidualSrc{nullptr, t.d_p[k], t.d_flag[k], t.d_geom[k], t.d_n + k};
     }
-    PF_CUDA(cudaMalloc(&t.d_partials, sizeof(double) * 32 * kLmBlocks));
-    PF_CUDA(cudaMalloc(&t.d_ticket, sizeof(unsigned)));
     PF_CUDA(cudaMalloc(&t.d_state, sizeof(LmState)));
     PF_CUDA(cudaMemsetAsync(t.d_state, 0, sizeof(LmState), t.stream));
     PF_CUDA(cudaMemcpyAsync(t.d_state->x, pose, sizeof(double) * 7, cudaMemcpyHostToDevice, t.stream));
     P.state = t.d_state;
-    P.partials = t.d_partials;
-    P.ticket = t.d_ticket;
     P.iter_poses = nullptr;
     PF_CUDA(cudaStreamSynchronize(t.stream));   // the staging vectors go out of scope
     return PF_OK;
@@ -399,8 +400,7 @@ extern "C" int pf_eval_normal_eq(int device, const double pose[7], const double*
     LmParams P{};
     PF_CHECK(solve_tap_setup(t, device, pose, edge9, n_edge, surf7, n_surf, P));
     P.eval_only = 1;
-    PF_CHECK(lm_begin(t.stream, P, nullptr, 1, nullptr));
-    PF_CHECK(lm_eval(t.stream, P, nullptr));
+    PF_CHECK(lm_solve(t.stream, P, nullptr, 1, nullptr));
     LmState S;
     PF_CUDA(cudaMemcpyAsync(&S, t.d_state, sizeof(S), cudaMemcpyDeviceToHost, t.stream));
     PF_CUDA(cudaStreamSynchronize(t.stream));
@@ -417,8 +417,7 @@ extern "C" int pf_lm_solve(int device, double pose_io[7], const double* edge9, i
     LmParams P{};
     PF_CHECK(solve_tap_setup(t, device, pose_io, edge9, n_edge, surf7, n_surf, P));
     P.eval_only = 0;
-    PF_CHECK(lm_begin(t.stream, P, nullptr, 1, nullptr));
-    for (int k = 0; k < kLmEvalsPerSolve; ++k) PF_CHECK(lm_eval(t.stream, P, nullptr));
+    PF_CHECK(lm_solve(t.stream, P, nullptr, 1, nullptr));
     LmState S;
     PF_CUDA(cudaMemcpyAsync(&S, t.d_state, sizeof(S), cudaMemcpyDeviceToHost, t.stream));
     PF_CUDA(cudaStreamSynchronize(t.stream));

@@ -36,18 +36,15 @@ struct LmState {
 struct LmParams {
     ResidualSrc src[2];       // 0 edge, 1 surf
     LmState* state;
-    double* partials;         // [blocks][32]
-    unsigned* ticket;         // last-block detection
     double* iter_poses;       // [16][7] pose after every outer iteration (may be null)
     int eval_only;            // stage tap: evaluate at state->x and stop
 };
 
-constexpr int kLmBlocks = 32;    // 8192 threads cover a frame's residual blocks in one grid-stride step
-constexpr int kLmEvalsPerSolve = 5;   // 1 initial evaluation + max_num_iterations (4) candidates
+constexpr int kLmCluster = 8;    // CTAs of the solver cluster (8 SMs, distributed shared memory reduction)
+constexpr int kLmThreads = 256;  // 2048 threads; 255 registers per thread keep the serial state machine out of local memory
 
-// pose_src: device pose to start from (null: keep state->x); resets the per-solve fields.
-int lm_begin(cudaStream_t stream, const LmParams& P, const double* pose_src, int first_pass, uint64_t* launches);
-// one launch = one evaluation + one transition of the LM state machine (no-op once finished)
-int lm_eval(cudaStream_t stream, const LmParams& P, uint64_t* launches);
+// One launch = one complete solve: at most 1 + 4 evaluations (max_num_iterations = 4) and the trust-region state machine.
+// pose_src: device pose to start from (null: keep state->x); first_pass resets the outer-iteration counter.
+int lm_solve(cudaStream_t stream, const LmParams& P, const double* pose_src, int first_pass, uint64_t* launches);
 
 }  // namespace pf
