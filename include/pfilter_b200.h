@@ -165,6 +165,12 @@ int pf_voxel_downsample(int device, const pf_point* in, int n, float leaf, pf_po
  * rgbds(leaf) (:34-134), extractstablepoint (:7-25), r += 2 saturating (:634-646). */
 int pf_map_update(int device, const pf_point* in, int n, const double center[3], float leaf, int k_new, float theta_p,
                   int theta_max, pf_point* out, int* n_out);
+/* The same map maintenance in its streaming form (what pf_odom_update runs from the second update on): `sorted_map` is the
+ * sorted part of a map as a previous update left it (ascending voxel key, one point per voxel), `extra` the unsorted
+ * points (exceptions + the points appended by the frame).  Result = pf_map_update(sorted_map ++ extra), except that
+ * centroids which left their voxel by float rounding are placed behind the sorted part: out[0, *n_sorted_out) is sorted. */
+int pf_map_merge(int device, const pf_point* sorted_map, int m_sorted, const pf_point* extra, int n_extra, const double center[3],
+                 float leaf, int k_new, float theta_p, int theta_max, pf_point* out, int cap_out, int* n_out, int* n_sorted_out);
 /* KdTreeFLANN::nearestKSearch(k = 5) (src/odomEstimationClass.cpp:299, 447): exact, float L2_Simple distances,
  * ascending, ties by lower index.  Contract: results are exact whenever d2[5q+4] < 1.0 (the only case the
  * reference uses, :300/:451); otherwise idx[5q..] = -1 and d2 = +inf. */

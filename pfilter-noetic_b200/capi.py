@@ -201,6 +201,17 @@ def map_update(pts, center, leaf, k_new, theta_p, theta_max, device=0):
     return out[:n.value].copy()
 
 
+def map_merge(sorted_map, extra, center, leaf, k_new, theta_p, theta_max, device=0):
+    """pf_map_merge: returns (map, n_sorted)."""
+    a, b = _pts(sorted_map), _pts(extra)
+    out = np.empty(max(len(a) + len(b), 1), POINT_DTYPE)
+    n, ns = C.c_int(), C.c_int()
+    c = np.asarray(center, np.float64)
+    check(lib().pf_map_merge(device, _vp(a), len(a), _vp(b), len(b), _vp(c), C.c_float(leaf), k_new, C.c_float(theta_p), theta_max,
+                             _vp(out), len(out), C.byref(n), C.byref(ns)))
+    return out[:n.value].copy(), ns.value
+
+
 def knn5(map_pts, queries_xyz4, device=0):
     m = _pts(map_pts)
     q = np.ascontiguousarray(queries_xyz4, np.float32)

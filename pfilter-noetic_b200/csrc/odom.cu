@@ -7,12 +7,13 @@
 //   build_grids      1 m search grids over both local maps (stands in for the two kd-tree builds)  (:249-250)
 //   optimization_count x { associate_pass (kNN + line/plane fit + persistence counters), 5 x k_lm_eval }   (:252-272)
 //   k_append         transform all down-sampled points with the final pose and append them to the maps      (:592-604)
-//   voxelize(MAP)    CropBox + rgbds + extractstablepoint + r += 2                                 (:606-647)
+//   map_merge        CropBox + rgbds + extractstablepoint + r += 2 as a streaming merge (merge.cuh) (:606-647)
 // and finally copies the 7-double pose to the host.  Maps, counters and the pose stay in HBM between frames.
 #include <vector>
 
 #include "match.cuh"
 #include "math.cuh"
+#include "merge.cuh"
 #include "solve.cuh"
 #include "voxel.cuh"
 
@@ -24,7 +25,7 @@ struct OdomShared {   // small device-resident block
     IsoDev odom, last_odom;
     double pose[7];        // pose of the last finished update (what the caller reads)
     int n_app[2];          // map sizes after appending the new points
-    int err;               // bit 0: map capacity exceeded
+    int err;               // bit 0: map capacity exceeded; bits 1..2: map merge (voxel coordinate range, exception capacity)
     int pad;
     int n_map[2];          // map sizes after the last update (read back with the pose: tight launch bounds for the next frame)
     long long frame;       // frame index this block describes
@@ -66,6 +67,7 @@ __global__ void k_predict(OdomShared* sh, LmState* S) {
 }
 
 constexpr int kPoseHist = 4096;
+constexpr int kMergeExcCap = 4096;   // centroids per update that may leave their voxel by rounding (a handful in practice)
 
 struct AppendParams {
     const Pt* ds[2]; const int* n_ds[2];
@@ -103,14 +105,14 @@ __global__ void __launch_bounds__(256) k_append(AppendParams A) {
     }
 }
 
-struct InitParams { const float4* feat[2]; const int* n_feat[2]; Pt* map[2]; int* n_map[2]; int map_cap; OdomShared* sh; };
+struct InitParams { const float4* feat[2]; const int* n_feat[2]; Pt* map[2]; int* n_map[2]; int* n_sorted[2]; int map_cap; OdomShared* sh; };
 
 // initMapWithPoints (:217-222): the raw first-frame clouds become the maps
 __global__ void __launch_bounds__(256) k_init_map(InitParams I) {
     const int kind = blockIdx.y;
     int n = *I.n_feat[kind];
     if (n > I.map_cap) { n = I.map_cap; if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(&I.sh->err, 1); }
-    if (blockIdx.x == 0 && threadIdx.x == 0) { *I.n_map[kind] = n; I.sh->n_map[kind] = n; I.sh->frame = 0; }
+    if (blockIdx.x == 0 && threadIdx.x == 0) { *I.n_map[kind] = n; *I.n_sorted[kind] = 0; I.sh->n_map[kind] = n; I.sh->frame = 0; }
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const float4 f = I.feat[kind][i];
         Pt o;
@@ -119,9 +121,10 @@ __global__ void __launch_bounds__(256) k_init_map(InitParams I) {
     }
 }
 
-__global__ void k_check_map_cap(const int* n_map0, const int* n_map1, int cap, OdomShared* sh, long long frame) {
+__global__ void k_check_map_cap(const int* n_map0, const int* n_map1, int cap, OdomShared* sh, long long frame, const unsigned* merge_err) {
     if (threadIdx.x != 0) return;
     if (*n_map0 > cap || *n_map1 > cap) atomicOr(&sh->err, 1);
+    if (*merge_err) atomicOr(&sh->err, (int)(*merge_err & 6u));
     sh->n_map[0] = *n_map0;
     sh->n_map[1] = *n_map1;
     sh->frame = frame;
@@ -148,7 +151,9 @@ struct pf_odom {
     Pt* d_ds[2] = {nullptr, nullptr};
     int* d_nds = nullptr;                // [2]
     Pt* d_map[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // [buffer][kind]
-    int* d_nmap[2] = {nullptr, nullptr}; // [buffer] -> 2 ints
+    int* d_nmap[2] = {nullptr, nullptr}; // [buffer] -> 4 ints: n_map[kind], n_sorted[kind] (merge.cuh: sorted prefix of the map)
+    MapMergeScratch msc{};
+    bool sorted_known = false;           // false until the first update after init: the raw first-frame maps are unsorted
     int cur = 0;
     float4* d_gpts[2] = {nullptr, nullptr};
     int *d_cs[2] = {nullptr, nullptr}, *d_ce[2] = {nullptr, nullptr}, *d_geom = nullptr;
@@ -195,8 +200,8 @@ int odom_alloc(pf_odom* h) {
         PF_CUDA(cudaMalloc(&h->d_feat[k], sizeof(float4) * fcap));
         PF_CUDA(cudaMalloc(&h->d_ds[k], sizeof(Pt) * fcap));
         for (int b = 0; b < 2; ++b) PF_CUDA(cudaMalloc(&h->d_map[b][k], sizeof(Pt) * bufcap));
-        PF_CUDA(cudaMalloc(&h->d_nmap[k], sizeof(int) * 2));
-        PF_CUDA(cudaMemset(h->d_nmap[k], 0, sizeof(int) * 2));
+        PF_CUDA(cudaMalloc(&h->d_nmap[k], sizeof(int) * 4));
+        PF_CUDA(cudaMemset(h->d_nmap[k], 0, sizeof(int) * 4));
         PF_CUDA(cudaMalloc(&h->d_gpts[k], sizeof(float4) * bufcap));
         PF_CUDA(cudaMalloc(&h->d_cs[k], sizeof(int) * (size_t)kGridCellCap));
         PF_CUDA(cudaMalloc(&h->d_ce[k], sizeof(int) * (size_t)kGridCellCap));
@@ -210,6 +215,7 @@ int odom_alloc(pf_odom* h) {
         PF_CUDA(cudaMemset(h->d_flag[k], 0, fcap));
         PF_CUDA(cudaMalloc(&h->d_g8[k], sizeof(double) * 8 * fcap));
     }
+    PF_CHECK(map_merge_scratch_create(h->msc, 2 * fcap + kMergeExcCap, kMergeExcCap));
     PF_CUDA(cudaMalloc(&h->d_state, sizeof(LmState)));
     PF_CUDA(cudaMemset(h->d_state, 0, sizeof(LmState)));
     PF_CUDA(cudaMalloc(&h->d_iter_poses, sizeof(double) * 16 * 7));
@@ -272,7 +278,10 @@ void ring_refresh(pf_odom* h) {
 
 int enqueue_init(pf_odom* h, const float4* const feat[2], const int* const n_feat[2], int ub_e, int ub_s) {
     InitParams I{};
-    for (int k = 0; k < 2; ++k) { I.feat[k] = feat[k]; I.n_feat[k] = n_feat[k]; I.map[k] = h->d_map[h->cur][k]; I.n_map[k] = h->d_nmap[h->cur] + k; }
+    for (int k = 0; k < 2; ++k) {
+        I.feat[k] = feat[k]; I.n_feat[k] = n_feat[k]; I.map[k] = h->d_map[h->cur][k];
+        I.n_map[k] = h->d_nmap[h->cur] + k; I.n_sorted[k] = h->d_nmap[h->cur] + 2 + k;
+    }
     I.map_cap = h->mcap;
     I.sh = h->d_sh;
     k_init_map<<<dim3(2 * kSMs, 2), 256, 0, h->stream>>>(I);
@@ -280,6 +289,7 @@ int enqueue_init(pf_odom* h, const float4* const feat[2], const int* const n_fea
     PF_CUDA(cudaGetLastError());
     h->optimization_count = 12;   // :221
     h->inited = true;
+    h->sorted_known = false;
     h->map_ub[0] = ub_e < h->mcap ? ub_e : h->mcap;
     h->map_ub[1] = ub_s < h->mcap ? ub_s : h->mcap;
     h->frame = 0;
@@ -347,18 +357,23 @@ int enqueue_update(pf_odom* h, const float4* const feat[2], const int* const n_f
     P.pose_hist = h->d_pose_hist; P.hist_slot = (int)(h->frame % kPoseHist);
     k_append<<<dim3(kSMs, 2), 256, 0, h->stream>>>(P);
     ws.launches += 1;
-    VoxParams M{};
-    M.mode = VOX_MAP;
     // rgbds(tmpSurf, map_resolution * 2) / rgbds(tmpCorner, map_resolution) with the float member map_resolution (:625-626)
     const float mres = (float)h->prm.map_resolution;
     const float mleaf[2] = {mres, mres * 2};
+    MapMergeParams M{};
     for (int k = 0; k < 2; ++k)
-        M.c[k] = VoxCloud{h->d_map[cur][k], h->d_sh->n_app + k, h->d_map[nxt][k], h->d_nmap[nxt] + k, mleaf[k], 0};
+        M.c[k] = MapMergeCloud{h->d_map[cur][k], h->d_nmap[cur] + 2 + k, h->d_sh->n_app + k, h->d_map[nxt][k], h->d_nmap[nxt] + k,
+                               h->d_nmap[nxt] + 2 + k, mleaf[k]};
     M.center = h->d_sh->odom.t;
     M.k_new = h->prm.k_new; M.theta_p = h->prm.theta_p; M.theta_max = h->prm.theta_max;
+    M.s = h->msc;
     const int app_e = mub_e + ub_e < h->bufcap ? mub_e + ub_e : h->bufcap, app_s = mub_s + ub_s < h->bufcap ? mub_s + ub_s : h->bufcap;
-    PF_CHECK(voxelize(ws, M, 1, app_e, app_s));
-    k_check_map_cap<<<1, 32, 0, h->stream>>>(h->d_nmap[nxt], h->d_nmap[nxt] + 1, h->mcap, h->d_sh, h->frame);
+    // unsorted part: everything on the first update (raw first-frame maps), later last update's exceptions + this frame's points
+    const int capb_e = h->sorted_known ? (kMergeExcCap + ub_e < app_e ? kMergeExcCap + ub_e : app_e) : app_e;
+    const int capb_s = h->sorted_known ? (kMergeExcCap + ub_s < app_s ? kMergeExcCap + ub_s : app_s) : app_s;
+    PF_CHECK(map_merge(ws, M, capb_e, capb_s, mub_e, mub_s));
+    h->sorted_known = true;
+    k_check_map_cap<<<1, 32, 0, h->stream>>>(h->d_nmap[nxt], h->d_nmap[nxt] + 1, h->mcap, h->d_sh, h->frame, map_merge_error_word(ws));
     ws.launches += 1;
     PF_CUDA(cudaGetLastError());
     h->cur = nxt;
@@ -376,6 +391,10 @@ int finish_frame(pf_odom* h, double pose_out[7]) {
         set_error("local map exceeded max_map_points = %d", h->mcap);
         return PF_ERR_CAPACITY;
     }
+    if (h->h_sh->err & 6) {
+        set_error("map update failed (bits %d: 2 = map_resolution below 0.2 m, 4 = more than %d centroids left their voxel)", h->h_sh->err & 6, kMergeExcCap);
+        return PF_ERR_CAPACITY;
+    }
     if (pose_out) memcpy(pose_out, h->h_sh->pose, sizeof(double) * 7);
     if (h->inited) {
         h->map_ub[0] = h->h_sh->n_map[0]; h->map_ub[1] = h->h_sh->n_map[1];
@@ -388,7 +407,8 @@ int finish_frame(pf_odom* h, double pose_out[7]) {
 
 extern "C" int pf_odom_create(const pf_odom_params* p, int device, pf_odom** out) {
     PF_REQUIRE(p && out, "null argument");
-    PF_REQUIRE(p->map_resolution > 0, "map_resolution must be positive");
+    PF_REQUIRE(p->map_resolution >= 0.2, "map_resolution %g: the streaming map update keeps 10-bit voxel coordinates inside the 200 m crop box (needs >= 0.2 m)",
+               p->map_resolution);
     PF_REQUIRE(p->weight_type == 0.0, "weight_type %g: only 0 (the class default) is implemented in this round", p->weight_type);
     int ndev = 0;
     PF_CUDA(cudaGetDeviceCount(&ndev));
@@ -418,6 +438,7 @@ extern "C" int pf_odom_destroy(pf_odom* h) {
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     workspace_destroy(h->ws);
+    map_merge_scratch_destroy(h->msc);
     cudaFree(h->d_nfeat); cudaFree(h->d_nds); cudaFree(h->d_geom);
     for (int k = 0; k < 2; ++k) {
         cudaFree(h->d_feat[k]); cudaFree(h->d_ds[k]); cudaFree(h->d_map[0][k]); cudaFree(h->d_map[1][k]); cudaFree(h->d_nmap[k]);
