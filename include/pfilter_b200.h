@@ -190,8 +190,28 @@ int pf_eval_normal_eq(int device, const double pose[7], const double* edge9, int
 int pf_lm_solve(int device, double pose_io[7], const double* edge9, int n_edge, const double* surf7, int n_surf,
                 int* iterations, double* final_cost);
 
-/* LaserMappingClass (include/laserMappingClass.h:32-58) is the next component on the path;
- * it is not part of this ABI yet. */
+/* ------------------------------------------------------------------------------------------------
+ * Global map  --  replaces LaserMappingClass (include/laserMappingClass.h:32-58, src/laserMappingClass.cpp)
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct pf_mapping pf_mapping;
+
+/* LaserMappingClass::init(map_resolution), src/laserMappingClass.cpp:7-32.  max_map_points: capacity of the global map
+ * (0 = 16 Mi points); max_points: capacity of one input cloud (0 = 262144). */
+int pf_mapping_create(double map_resolution, int max_map_points, int max_points, int device, pf_mapping** out);
+int pf_mapping_destroy(pf_mapping* h);
+/* updateCurrentPointsToMap(pc_in, pose_current), src/laserMappingClass.cpp:152-191.  xyzi: n host points (float4, sensor
+ * frame); rt: the Eigen::Isometry3d pose as row-major 3x4 [R | t] doubles.  Points that fall outside the 5x5x5 block of
+ * 50 m cells around the pose (the reference indexes a NULL / out-of-range cell there) are dropped and counted.
+ * The call returns when the work is enqueued; the next call on the handle waits for it. */
+int pf_mapping_update(pf_mapping* h, const float* xyzi, int n, const double rt[12]);
+int pf_mapping_update_device(pf_mapping* h, const void* d_xyzi, int n, const double rt[12]);
+int pf_mapping_map_size(pf_mapping* h, int* n);
+/* getMap, src/laserMappingClass.cpp:196-208: every cell in (x, y, z) cell order, each cell in VoxelGrid order; the few
+ * centroids that rounding pushed out of their voxel in the last update trail the array until the next update. */
+int pf_mapping_get_map(pf_mapping* h, float* xyzi_out, int cap, int* n);
+/* n_sorted: length of the sorted part; dropped: points dropped so far (see pf_mapping_update); launches: kernels so far */
+int pf_mapping_stats(pf_mapping* h, int* n_sorted, long long* dropped, uint64_t* launches);
+void* pf_mapping_stream(pf_mapping* h);
 
 #ifdef __cplusplus
 }

@@ -209,3 +209,33 @@ class Odom:
         lib().pforacle_odom_stats(self.h, _vp(out))
         return dict(zip(("n_edge_ds", "n_surf_ds", "n_edge_res", "n_surf_res", "map_edge", "map_surf", "passes", "lm_iterations"),
                         out.tolist()))
+
+
+class Mapping:
+    """Restated LaserMappingClass (CPU), oracle_mapping.cpp."""
+
+    def __init__(self, map_resolution=0.4):
+        L = lib()
+        L.pforacle_mapping_create.restype = C.c_void_p
+        L.pforacle_mapping_size.restype = C.c_long
+        L.pforacle_mapping_dropped.restype = C.c_long
+        self.h = C.c_void_p(L.pforacle_mapping_create(C.c_double(map_resolution)))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().pforacle_mapping_destroy(self.h)
+            self.h = None
+
+    def update(self, xyzi, rt12):
+        a = _f32(xyzi)
+        rt = np.ascontiguousarray(rt12, np.float64).reshape(12)
+        lib().pforacle_mapping_update(self.h, _vp(a), len(a), _vp(rt))
+
+    def dropped(self):
+        return int(lib().pforacle_mapping_dropped(self.h))
+
+    def get_map(self):
+        n = int(lib().pforacle_mapping_size(self.h))
+        out = np.empty((max(n, 1), 4), np.float32)
+        lib().pforacle_mapping_get_map(self.h, _vp(out))
+        return out[:n].copy()

@@ -5,6 +5,7 @@ a ROS-free harness of the reference:
 
   LaserProcessingClass   /root/reference/include/laserProcessingClass.h:30-42
   Odom_ES_EstimationClass (alias OdomEstimationClass)   /root/reference/include/odomEstimationClass.h:140-167
+  LaserMappingClass      /root/reference/include/laserMappingClass.h:32-58
   Lidar                  /root/reference/include/lidar.h:9-32
 
 Clouds are numpy arrays: XYZI clouds are float32 [n, 4]; map / feature clouds with counters are ``capi.POINT_DTYPE``
@@ -137,6 +138,35 @@ class Odom_ES_EstimationClass:
 
 
 OdomEstimationClass = Odom_ES_EstimationClass
+
+
+class LaserMappingClass:
+    """init(map_resolution) / updateCurrentPointsToMap(pc_in, pose_current) / getMap()
+    (/root/reference/include/laserMappingClass.h:32-58).  pose_current is a 4x4 (or 3x4) isometry like the reference's
+    Eigen::Isometry3d; the global map stays in HBM and getMap() copies it out on demand."""
+
+    def __init__(self, device=0, max_map_points=0, max_points=0):
+        self._device, self._mm, self._mp = device, max_map_points, max_points
+        self._mp_handle = None
+        self.status = 0
+
+    def init(self, map_resolution):
+        self._mp_handle = capi.Mapping(map_resolution, self._mm, self._mp, self._device)
+
+    def updateCurrentPointsToMap(self, pc_in, pose_current):
+        try:
+            self._mp_handle.update(pc_in, np.asarray(pose_current, np.float64)[:3, :4])
+            self.status = 0
+        except capi.PfError as e:
+            _report("updateCurrentPointsToMap", e)
+            self.status = e.status
+
+    def getMap(self):
+        return self._mp_handle.get_map()
+
+    @property
+    def mapping(self):
+        return self._mp_handle
 
 
 def smoke_odometry(p, O):

@@ -52,7 +52,7 @@ def lib():
             raise RuntimeError(f"{LIB_PATH} missing: build it with `python -c 'import __graft_entry__ as g; g.build()'`")
         _lib = C.CDLL(LIB_PATH)
         _lib.pf_last_error.restype = C.c_char_p
-        for name in ("pf_extract_stream", "pf_odom_stream"):
+        for name in ("pf_extract_stream", "pf_odom_stream", "pf_mapping_stream"):
             if hasattr(_lib, name):
                 getattr(_lib, name).restype = C.c_void_p
     return _lib
@@ -328,6 +328,57 @@ class Odometry:
         v = C.c_uint64()
         check(lib().pf_odom_kernel_launches(self.h, C.byref(v)))
         return v.value
+
+
+def pose_to_rt(pose7):
+    """[qx qy qz qw tx ty tz] -> row-major 3x4 [R | t] (Eigen::Quaterniond::toRotationMatrix, double)."""
+    x, y, z, w = (float(v) for v in pose7[:4])
+    tx, ty, tz = 2 * x, 2 * y, 2 * z
+    twx, twy, twz, txx, txy, txz, tyy, tyz, tzz = tx * w, ty * w, tz * w, tx * x, ty * x, tz * x, ty * y, tz * y, tz * z
+    return np.array([1 - (tyy + tzz), txy - twz, txz + twy, pose7[4],
+                     txy + twz, 1 - (txx + tzz), tyz - twx, pose7[5],
+                     txz - twy, tyz + twx, 1 - (txx + tyy), pose7[6]], np.float64)
+
+
+class Mapping:
+    """Handle of pf_mapping_* (replaces LaserMappingClass)."""
+
+    def __init__(self, map_resolution=0.4, max_map_points=0, max_points=0, device=0):
+        self.h = C.c_void_p()
+        check(lib().pf_mapping_create(C.c_double(map_resolution), max_map_points, max_points, device, C.byref(self.h)))
+
+    def close(self):
+        if self.h:
+            lib().pf_mapping_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def update(self, xyzi, rt12):
+        a = as_points(xyzi)
+        rt = np.ascontiguousarray(rt12, np.float64).reshape(12)
+        check(lib().pf_mapping_update(self.h, _vp(a), len(a), _vp(rt)))
+
+    def size(self):
+        n = C.c_int()
+        check(lib().pf_mapping_map_size(self.h, C.byref(n)))
+        return n.value
+
+    def get_map(self):
+        n = self.size()
+        out = np.empty((max(n, 1), 4), np.float32)
+        m = C.c_int()
+        check(lib().pf_mapping_get_map(self.h, _vp(out), len(out), C.byref(m)))
+        return out[:m.value].copy()
+
+    def stats(self):
+        ns, dr, la = C.c_int(), C.c_longlong(), C.c_uint64()
+        check(lib().pf_mapping_stats(self.h, C.byref(ns), C.byref(dr), C.byref(la)))
+        return {"n_sorted": ns.value, "dropped": dr.value, "launches": la.value}
 
 
 def frame_process(extractor, odometry, xyzi):

@@ -1,0 +1,546 @@
+// K10: global map -- device-resident replacement of LaserMappingClass
+// (/root/reference/src/laserMappingClass.cpp:7-32, :110-149, :152-191, :196-208; include/laserMappingClass.h:23-30).
+//
+// The reference tiles space into 50 m cells (cell = floor(x / 50 + 0.5)), pushes every transformed point of the frame into
+// its cell's cloud and then re-runs pcl::VoxelGrid on all 5 x 5 x 5 cells around the pose, every frame; getMap concatenates
+// every cell.  VoxelGrid emits a cell's voxels in ascending (vz, vy, vx) order and getMap walks the cells in (cx, cy, cz)
+// order, so the whole map is one array sorted by (cell, voxel) -- and it stays sorted from one update to the next.  One
+// update is therefore the same streaming merge as the local-map update (merge.cu):
+//   k_mp_append  transform (pcl::transformPointCloud, float) + intensity (:169) + cell id (:170-172) of the frame's points,
+//                written behind the map in input order
+//   k_mp_keys    31-bit key (cell inside the 5x5x5 block : 7 | voxel inside the cell : 3 x 8) of every unsorted point
+//   radix_sort   stable -> canonical summation order (ascending input index)
+//   k_mp_heads   one thread per voxel run of the sorted new points: binary search in the sorted map; runs that meet a map
+//                point are "matched", the others are reduced to finished voxels ("inserts")
+//   k_mp_merge   ONE streaming pass over the map: cells outside the block pass through, block cells merge their matched
+//                runs (VoxelGrid centroid of x, y, z, intensity) and take the inserts in key order
+//   k_mp_finish  appends "exceptions" (centroids that float rounding pushed out of their voxel) behind the sorted part
+// A point keeps the cell it was first binned into (the reference never re-bins: the cloud a centroid lives in is its cell),
+// hence the 4-byte cell id beside every point: 20 B read + 20 B written per map point per update, O(map) streaming instead
+// of the reference's 125 sorts + O(map) concatenation.
+#include "primitives.cuh"
+
+namespace pf {
+
+namespace {
+
+constexpr int kMpTile = 1024;
+constexpr unsigned kBadKey = 0xffffffffu;
+constexpr unsigned kNoCell = 0xffffffffu;
+constexpr int kBlock = 5;            // 2 * LASER_CELL_RANGE + 1 cells per axis (include/laserMappingClass.h:29-30)
+constexpr int kExcCap = 4096;
+
+struct MapperParams {
+    float4* buf;  unsigned* cbuf;     // current map: points + cell ids, [0, n_sorted) sorted | exceptions | this frame's points
+    float4* out;  unsigned* cell_out; // next map
+    int* counts;                      // device: [0] n_sorted [1] n_map [2] n_app [3] n_sorted_out [4] err bits [5] buffer capacity [6] map capacity
+    unsigned long long* dropped;      // device: points that fell outside the 5x5x5 block (the reference's out-of-range access)
+    float inv_leaf;
+    int bx, by, bz;                   // lowest cell of the block around the pose
+    int *m_ra, *m_start, *m_len, *i_ra;
+    float4* i_pt;  unsigned* i_cell;
+    float4* exc;   unsigned* exc_cell;
+    unsigned* state;                  // [0] nB [2] nvalid [4] n matched [6] n inserts [10] n exceptions
+};
+
+__host__ __device__ __forceinline__ int cell_of(double v) { return (int)floor(v / 50.0 + 0.5); }   // :154-156, :170-172
+
+__device__ __forceinline__ unsigned pack_cell(int cx, int cy, int cz) {
+    return ((unsigned)(cx + 512) << 20) | ((unsigned)(cy + 512) << 10) | (unsigned)(cz + 512);
+}
+__device__ __forceinline__ void unpack_cell(unsigned c, int& cx, int& cy, int& cz) {
+    cx = (int)(c >> 20) - 512; cy = (int)((c >> 10) & 1023u) - 512; cz = (int)(c & 1023u) - 512;
+}
+__device__ __forceinline__ bool in_block(const MapperParams& P, unsigned cell) {
+    int cx, cy, cz;
+    unpack_cell(cell, cx, cy, cz);
+    return (unsigned)(cx - P.bx) < (unsigned)kBlock && (unsigned)(cy - P.by) < (unsigned)kBlock && (unsigned)(cz - P.bz) < (unsigned)kBlock;
+}
+// voxel of a point inside its cell: VoxelGrid's floor(x * inverse_leaf) relative to the first voxel that touches the cell (+1
+// of slack for a centroid rounded onto the cell face), 8 bits per axis, (vz, vy, vx) = VoxelGrid's output order
+__device__ __forceinline__ unsigned vox24(const float4& p, unsigned cell, float inv) {
+    int c[3];
+    unpack_cell(cell, c[0], c[1], c[2]);
+    const float v[3] = {p.x, p.y, p.z};
+    unsigned r[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const int base = (int)floor(((double)c[a] - 0.5) * 50.0 * (double)inv);
+        const int q = (int)floorf(__fmul_rn(v[a], inv)) - base + 1;
+        r[a] = (unsigned)min(max(q, 0), 255);
+    }
+    return (r[2] << 16) | (r[1] << 8) | r[0];
+}
+__device__ __forceinline__ unsigned long long key64(unsigned cell, unsigned v24) { return ((unsigned long long)cell << 24) | v24; }
+__device__ __forceinline__ unsigned key31(const MapperParams& P, unsigned cell, unsigned v24) {
+    int cx, cy, cz;
+    unpack_cell(cell, cx, cy, cz);
+    return ((unsigned)(((cx - P.bx) * kBlock + (cy - P.by)) * kBlock + (cz - P.bz)) << 24) | v24;
+}
+__device__ __forceinline__ unsigned cell_of_key31(const MapperParams& P, unsigned k) {
+    const int b = (int)(k >> 24);
+    return pack_cell(P.bx + b / (kBlock * kBlock), P.by + (b / kBlock) % kBlock, P.bz + b % kBlock);
+}
+
+struct Acc4 { float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f; int n = 0; };
+__device__ __forceinline__ void acc_add(Acc4& a, const float4& v) {   // CentroidPoint accumulators, in order
+    a.sx = __fadd_rn(a.sx, v.x); a.sy = __fadd_rn(a.sy, v.y); a.sz = __fadd_rn(a.sz, v.z); a.si = __fadd_rn(a.si, v.w);
+    a.n += 1;
+}
+__device__ __forceinline__ float4 acc_mean(const Acc4& a) {
+    const float fn = (float)a.n;
+    return make_float4(__fdiv_rn(a.sx, fn), __fdiv_rn(a.sy, fn), __fdiv_rn(a.sz, fn), __fdiv_rn(a.si, fn));
+}
+__device__ __forceinline__ void put_exception(const MapperParams& P, const float4& o, unsigned cell) {
+    const unsigned slot = atomicAdd(&P.state[10], 1u);
+    if ((int)slot < kExcCap) { P.exc[slot] = o; P.exc_cell[slot] = cell; }
+}
+
+// transform + intensity + cell of the frame's points (:162-176); m = row-major 3x4 float pose (pose_current.cast<float>())
+struct Mat34 { float m[12]; };
+__global__ void __launch_bounds__(256) k_mp_append(MapperParams P, const float4* __restrict__ in, int n_in, Mat34 T) {
+    const int n_map = P.counts[1], cap = P.counts[5];
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        int tot = n_map + n_in;
+        if (tot > cap) { atomicOr(&P.counts[4], 1); tot = cap; }
+        P.counts[2] = tot;
+    }
+    int drop = 0;
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < n_in; q += gridDim.x * blockDim.x) {
+        if (n_map + q >= cap) break;
+        const float4 s = ld_stream_f4(in + q);
+        float4 o;
+        // detail::Transformer<float>::se3 (SSE): col0 * x + (col1 * y + (col2 * z + col3))
+        o.x = __fadd_rn(__fmul_rn(T.m[0], s.x), __fadd_rn(__fmul_rn(T.m[1], s.y), __fadd_rn(__fmul_rn(T.m[2], s.z), T.m[3])));
+        o.y = __fadd_rn(__fmul_rn(T.m[4], s.x), __fadd_rn(__fmul_rn(T.m[5], s.y), __fadd_rn(__fmul_rn(T.m[6], s.z), T.m[7])));
+        o.z = __fadd_rn(__fmul_rn(T.m[8], s.x), __fadd_rn(__fmul_rn(T.m[9], s.y), __fadd_rn(__fmul_rn(T.m[10], s.z), T.m[11])));
+        o.w = (float)fmin(1.0, fmax((double)s.z + 2.0, 0.0) / 5);                                  // :169
+        const int cx = cell_of((double)o.x), cy = cell_of((double)o.y), cz = cell_of((double)o.z);
+        unsigned cell = kNoCell;
+        if ((unsigned)(cx - P.bx) < (unsigned)kBlock && (unsigned)(cy - P.by) < (unsigned)kBlock && (unsigned)(cz - P.bz) < (unsigned)kBlock &&
+            abs(cx) < 512 && abs(cy) < 512 && abs(cz) < 512 && isfinite(o.x) && isfinite(o.y) && isfinite(o.z))
+            cell = pack_cell(cx, cy, cz);
+        else
+            ++drop;
+        P.buf[n_map + q] = o;
+        P.cbuf[n_map + q] = cell;
+    }
+    drop = __reduce_add_sync(0xffffffffu, drop);
+    if ((threadIdx.x & 31) == 0 && drop) atomicAdd(P.dropped, (unsigned long long)drop);
+}
+
+__global__ void __launch_bounds__(256) k_mp_keys(MapperParams P, uint32_t* __restrict__ keys) {
+    const int mA = P.counts[0];
+    const int nB = max(0, P.counts[2] - mA);
+    if (blockIdx.x == 0 && threadIdx.x == 0) P.state[0] = (unsigned)nB;
+    int valid = 0;
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < nB; q += gridDim.x * blockDim.x) {
+        const unsigned cell = P.cbuf[mA + q];
+        unsigned key = kBadKey;
+        if (cell != kNoCell) {
+            const float4 p = P.buf[mA + q];
+            if (in_block(P, cell)) { key = key31(P, cell, vox24(p, cell, P.inv_leaf)); ++valid; }
+            else put_exception(P, p, cell);     // an exception of a cell that is not filtered this frame waits for its turn
+        }
+        keys[q] = key;
+    }
+    valid = __reduce_add_sync(0xffffffffu, valid);
+    if ((threadIdx.x & 31) == 0 && valid) atomicAdd(&P.state[2], (unsigned)valid);
+}
+
+__global__ void __launch_bounds__(256) k_mp_heads(MapperParams P, const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals,
+                                                  unsigned long long* status, int status_stride, unsigned* ctrl) {
+    __shared__ int s_tile;
+    __shared__ int s_tmp[9];
+    __shared__ unsigned s_bcast;
+    const int nv = (int)P.state[2];
+    const int mA = P.counts[0];
+    const float4* bpts = P.buf + mA;
+    while (true) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_tile = (int)atomicAdd(&ctrl[1], 1u);
+        __syncthreads();
+        const int tile = s_tile;
+        if (tile * 256 >= nv) return;
+        const int e = tile * 256 + threadIdx.x;
+        bool matched = false, ins = false;
+        int rA = 0, len = 0;
+        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+        unsigned cell = 0;
+        if (e < nv) {
+            const unsigned key = keys[e];
+            if (e == 0 || keys[e - 1] != key) {
+                int e2 = e + 1;
+                while (e2 < nv && keys[e2] == key) ++e2;
+                len = e2 - e;
+                cell = cell_of_key31(P, key);
+                const unsigned v24 = key & 0xffffffu;
+                const unsigned long long k64 = key64(cell, v24);
+                int lo = 0, hi = mA;
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    const unsigned cm = P.cbuf[mid];
+                    // cells order the map; the voxel only matters inside the run's own cell
+                    const bool less = cm != cell ? cm < cell : key64(cm, vox24(P.buf[mid], cm, P.inv_leaf)) < k64;
+                    if (less) lo = mid + 1; else hi = mid;
+                }
+                rA = lo;
+                if (rA < mA) {
+                    const unsigned ca = P.cbuf[rA];
+                    matched = ca == cell && vox24(P.buf[rA], ca, P.inv_leaf) == v24;
+                }
+                if (!matched) {
+                    Acc4 acc;
+                    for (int q = e; q < e2; ++q) acc_add(acc, bpts[vals[q]]);
+                    o = acc_mean(acc);
+                    if (acc.n > 1 && vox24(o, cell, P.inv_leaf) != v24) put_exception(P, o, cell);
+                    else ins = true;
+                }
+            }
+        }
+        const unsigned tag = (ctrl[0] << 3);
+        int total_m, total_i;
+        const int lm = block_scan_excl_256(matched ? 1 : 0, s_tmp, &total_m);
+        const unsigned excl_m = chained_scan_exclusive(status, tag | 2u, tile, (unsigned)total_m, &s_bcast);
+        if (matched) { const int idx = (int)excl_m + lm; P.m_ra[idx] = rA; P.m_start[idx] = e; P.m_len[idx] = len; }
+        const int li = block_scan_excl_256(ins ? 1 : 0, s_tmp, &total_i);
+        const unsigned excl_i = chained_scan_exclusive(status + status_stride, tag | 3u, tile, (unsigned)total_i, &s_bcast);
+        if (ins) { const int idx = (int)excl_i + li; P.i_ra[idx] = rA; P.i_pt[idx] = o; P.i_cell[idx] = cell; }
+        if (tile == (nv - 1) / 256 && threadIdx.x == 0) {
+            P.state[4] = excl_m + (unsigned)total_m;
+            P.state[6] = excl_i + (unsigned)total_i;
+        }
+    }
+}
+
+// first index i in [0, n) with a[i] >= key (whole warp, same arguments)
+__device__ __forceinline__ int warp_lower_bound_i(const int* a, int n, int key) {
+    const int lane = (int)lane_id();
+    int lo = 0, hi = n;
+    while (hi - lo > 32) {
+        const int step = (hi - lo + 31) / 32;
+        const int idx = lo + (lane + 1) * step - 1;
+        const bool less = idx < hi && a[idx] < key;
+        const int c = __popc(__ballot_sync(0xffffffffu, less));
+        const int first_ge = lo + (c + 1) * step - 1;
+        const int nlo = lo + c * step;
+        hi = (c < 32 && first_ge < hi) ? first_ge : hi;
+        lo = nlo < hi ? nlo : hi;
+    }
+    const int idx = lo + lane;
+    const bool less = idx < hi && a[idx] < key;
+    return lo + __popc(__ballot_sync(0xffffffffu, less));
+}
+
+__global__ void __launch_bounds__(256) k_mp_merge(MapperParams P, const uint32_t* __restrict__ vals, unsigned long long* status, unsigned* ctrl) {
+    __shared__ int s_link[kMpTile];
+    __shared__ int s_cnt[kMpTile + 1];
+    __shared__ int s_first[kMpTile + 1];
+    __shared__ int s_pre[kMpTile + 1];
+    __shared__ int s_rng[4];
+    __shared__ int s_tile;
+    __shared__ int s_tmp[9];
+    __shared__ unsigned s_bcast;
+    const int mA = P.counts[0];
+    const int ntiles = mA / kMpTile + 1;     // the last tile also takes the inserts behind the last map point
+    const int nm = (int)P.state[4], ni = (int)P.state[6];
+    const float4* bpts = P.buf + mA;
+    const int tid = threadIdx.x;
+    while (true) {
+        __syncthreads();
+        if (tid == 0) s_tile = (int)atomicAdd(&ctrl[2], 1u);
+        __syncthreads();
+        const int tile = s_tile;
+        if (tile >= ntiles) return;
+        const int base = tile * kMpTile;
+        const bool last = tile == ntiles - 1;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { s_link[tid + 256 * k] = 0; s_cnt[tid + 256 * k] = 0; s_first[tid + 256 * k] = 0x7fffffff; }
+        if (tid == 0) { s_cnt[kMpTile] = 0; s_first[kMpTile] = 0x7fffffff; }
+        if (tid < 32) {
+            const int a = warp_lower_bound_i(P.m_ra, nm, base);
+            const int b = last ? nm : warp_lower_bound_i(P.m_ra, nm, base + kMpTile);
+            if (tid == 0) { s_rng[0] = a; s_rng[1] = b; }
+        } else if (tid < 64) {
+            const int a = warp_lower_bound_i(P.i_ra, ni, base);
+            const int b = last ? ni : warp_lower_bound_i(P.i_ra, ni, base + kMpTile);
+            if (tid == 32) { s_rng[2] = a; s_rng[3] = b; }
+        }
+        __syncthreads();
+        const int mLo = s_rng[0], mHi = s_rng[1], iLo = s_rng[2], iHi = s_rng[3];
+        for (int h = mLo + tid; h < mHi; h += 256) s_link[P.m_ra[h] - base] = h + 1;
+        for (int e = iLo + tid; e < iHi; e += 256) {
+            const int s = P.i_ra[e] - base;
+            atomicAdd(&s_cnt[s], 1);
+            atomicMin(&s_first[s], e);
+        }
+        __syncthreads();
+        float4 o[4];
+        unsigned oc[4];
+        bool keep[4];
+        int v = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int slot = 4 * tid + k, i = base + slot;
+            keep[k] = false;
+            if (i < mA) {
+                const float4 p = P.buf[i];
+                const unsigned cell = P.cbuf[i];
+                o[k] = p; oc[k] = cell; keep[k] = true;
+                const int l = s_link[slot];
+                if (l) {     // this map point's voxel receives new points (its cell is inside the block by construction)
+                    Acc4 acc;
+                    acc_add(acc, p);
+                    const int st = P.m_start[l - 1], ln = P.m_len[l - 1];
+                    for (int q = 0; q < ln; ++q) acc_add(acc, bpts[vals[st + q]]);
+                    const float4 r = acc_mean(acc);
+                    if (vox24(r, cell, P.inv_leaf) != vox24(p, cell, P.inv_leaf)) { put_exception(P, r, cell); keep[k] = false; }
+                    o[k] = r;
+                }
+            }
+            v += (keep[k] ? 1 : 0) + s_cnt[slot];
+        }
+        if (tid == 255) v += s_cnt[kMpTile];
+        int total;
+        const int t_excl = block_scan_excl_256(v, s_tmp, &total);
+        {
+            int run = t_excl;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                s_pre[4 * tid + k] = run;
+                run += s_cnt[4 * tid + k] + (keep[k] ? 1 : 0);
+            }
+            if (tid == 255) s_pre[kMpTile] = run;
+        }
+        const unsigned tag = (ctrl[0] << 3) | 4u;
+        const unsigned gbase = chained_scan_exclusive(status, tag, tile, (unsigned)total, &s_bcast);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (keep[k]) {
+                const int d = (int)gbase + s_pre[4 * tid + k] + s_cnt[4 * tid + k];
+                P.out[d] = o[k]; P.cell_out[d] = oc[k];
+            }
+        }
+        for (int e = iLo + tid; e < iHi; e += 256) {
+            const int s = P.i_ra[e] - base;
+            const int d = (int)gbase + s_pre[s] + (e - s_first[s]);
+            P.out[d] = P.i_pt[e]; P.cell_out[d] = P.i_cell[e];
+        }
+        if (last && tid == 0) P.counts[3] = (int)gbase + total;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_mp_finish(MapperParams P) {
+    const int ns = P.counts[3];
+    int ne = (int)P.state[10];
+    if (ne > kExcCap) { if (threadIdx.x == 0) atomicOr(&P.counts[4], 2); ne = kExcCap; }
+    for (int j = threadIdx.x; j < ne; j += blockDim.x) { P.out[ns + j] = P.exc[j]; P.cell_out[ns + j] = P.exc_cell[j]; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (ns + ne > P.counts[6]) atomicOr(&P.counts[4], 1);
+        P.counts[0] = ns; P.counts[1] = ns + ne; P.counts[2] = ns + ne;
+    }
+}
+
+}  // namespace
+}  // namespace pf
+
+using namespace pf;
+
+struct pf_mapping {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev = nullptr;
+    float leaf = 0.4f;
+    int mcap = 0, pcap = 0, bufcap = 0;
+    Workspace ws;
+    float4* d_map[2] = {nullptr, nullptr};
+    unsigned* d_cell[2] = {nullptr, nullptr};
+    int cur = 0;
+    float4* d_in = nullptr;
+    int* d_counts = nullptr;
+    unsigned long long* d_dropped = nullptr;
+    int *d_mra = nullptr, *d_mstart = nullptr, *d_mlen = nullptr, *d_ira = nullptr;
+    float4 *d_ipt = nullptr, *d_exc = nullptr;
+    unsigned *d_icell = nullptr, *d_exccell = nullptr;
+    int* h_counts = nullptr;              // pinned read-back of the device counts after the last update
+    unsigned long long* h_dropped = nullptr;
+    bool pending = false;                 // a read-back is in flight
+    int map_ub = 0, sorted_ub = 0;        // upper bounds for launch geometry
+    uint64_t launches = 0;
+};
+
+namespace {
+
+int mapping_settle(pf_mapping* h) {   // wait for the last update's counts
+    if (h->pending) {
+        PF_CUDA(cudaEventSynchronize(h->ev));
+        h->pending = false;
+        if (h->h_counts[4] & 1) { set_error("global map exceeded max_map_points = %d", h->mcap); return PF_ERR_CAPACITY; }
+        if (h->h_counts[4] & 2) { set_error("more than %d centroids left their voxel in one update", kExcCap); return PF_ERR_CAPACITY; }
+        h->map_ub = h->h_counts[1];
+        h->sorted_ub = h->h_counts[0];
+    }
+    return PF_OK;
+}
+
+}  // namespace
+
+// LaserMappingClass::init, src/laserMappingClass.cpp:7-32 (the 5x5x5 block of empty cells needs no storage here)
+extern "C" int pf_mapping_create(double map_resolution, int max_map_points, int max_points, int device, pf_mapping** out) {
+    PF_REQUIRE(out, "null argument");
+    PF_REQUIRE(map_resolution >= 0.2, "map_resolution %g: voxel coordinates inside a 50 m cell are kept in 8 bits (needs >= 0.2 m)", map_resolution);
+    int ndev = 0;
+    PF_CUDA(cudaGetDeviceCount(&ndev));
+    PF_REQUIRE(device >= 0 && device < ndev, "device %d not available (%d devices)", device, ndev);
+    PF_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    PF_CUDA(cudaGetDeviceProperties(&prop, device));
+    PF_REQUIRE(prop.major == 10, "pfilter_b200 needs an sm_100a device, found sm_%d%d", prop.major, prop.minor);
+    pf_mapping* h = new pf_mapping();
+    h->device = device;
+    h->leaf = (float)map_resolution;       // setLeafSize takes floats (:31)
+    h->mcap = max_map_points > 0 ? max_map_points : (16 << 20);
+    h->pcap = max_points > 0 ? max_points : 262144;
+    h->bufcap = h->mcap + h->pcap;
+    auto body = [&]() -> int {
+        PF_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+        PF_CUDA(cudaEventCreateWithFlags(&h->ev, cudaEventDisableTiming));
+        const int capb = h->pcap + kExcCap;
+        PF_CHECK(workspace_create(h->ws, capb > h->mcap / 4 ? capb : h->mcap / 4, h->stream));   // status words cover mcap / 1024 merge tiles
+        for (int b = 0; b < 2; ++b) {
+            PF_CUDA(cudaMalloc(&h->d_map[b], sizeof(float4) * (size_t)h->bufcap));
+            PF_CUDA(cudaMalloc(&h->d_cell[b], sizeof(unsigned) * (size_t)h->bufcap));
+        }
+        PF_CUDA(cudaMalloc(&h->d_in, sizeof(float4) * (size_t)h->pcap));
+        PF_CUDA(cudaMalloc(&h->d_counts, sizeof(int) * 8));
+        PF_CUDA(cudaMalloc(&h->d_dropped, sizeof(unsigned long long)));
+        PF_CUDA(cudaMemset(h->d_dropped, 0, sizeof(unsigned long long)));
+        const int counts[8] = {0, 0, 0, 0, 0, h->bufcap, h->mcap, 0};
+        PF_CUDA(cudaMemcpy(h->d_counts, counts, sizeof(counts), cudaMemcpyHostToDevice));
+        PF_CUDA(cudaMalloc(&h->d_mra, sizeof(int) * capb));
+        PF_CUDA(cudaMalloc(&h->d_mstart, sizeof(int) * capb));
+        PF_CUDA(cudaMalloc(&h->d_mlen, sizeof(int) * capb));
+        PF_CUDA(cudaMalloc(&h->d_ira, sizeof(int) * capb));
+        PF_CUDA(cudaMalloc(&h->d_ipt, sizeof(float4) * capb));
+        PF_CUDA(cudaMalloc(&h->d_icell, sizeof(unsigned) * capb));
+        PF_CUDA(cudaMalloc(&h->d_exc, sizeof(float4) * kExcCap));
+        PF_CUDA(cudaMalloc(&h->d_exccell, sizeof(unsigned) * kExcCap));
+        PF_CUDA(cudaMallocHost(&h->h_counts, sizeof(int) * 8));
+        PF_CUDA(cudaMallocHost(&h->h_dropped, sizeof(unsigned long long)));
+        memset(h->h_counts, 0, sizeof(int) * 8);
+        *h->h_dropped = 0;
+        return PF_OK;
+    };
+    const int rc = body();
+    if (rc != PF_OK) { pf_mapping_destroy(h); return rc; }
+    *out = h;
+    return PF_OK;
+}
+
+extern "C" int pf_mapping_destroy(pf_mapping* h) {
+    if (!h) return PF_OK;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    workspace_destroy(h->ws);
+    for (int b = 0; b < 2; ++b) { cudaFree(h->d_map[b]); cudaFree(h->d_cell[b]); }
+    cudaFree(h->d_in); cudaFree(h->d_counts); cudaFree(h->d_dropped);
+    cudaFree(h->d_mra); cudaFree(h->d_mstart); cudaFree(h->d_mlen); cudaFree(h->d_ira); cudaFree(h->d_ipt); cudaFree(h->d_icell);
+    cudaFree(h->d_exc); cudaFree(h->d_exccell);
+    cudaFreeHost(h->h_counts); cudaFreeHost(h->h_dropped);
+    if (h->ev) cudaEventDestroy(h->ev);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return PF_OK;
+}
+
+// LaserMappingClass::updateCurrentPointsToMap, src/laserMappingClass.cpp:152-191.  rt = row-major 3x4 [R | t] (double) of
+// the Eigen::Isometry3d pose_current.  Asynchronous: returns once the work is enqueued; the next call (or get_map) waits.
+static int mapping_update(pf_mapping* h, const float* xyzi, int n, const double rt[12], int device_input) {
+    PF_REQUIRE(h && rt && (xyzi || n == 0), "null argument");
+    PF_REQUIRE(n >= 0 && n <= h->pcap, "cloud of %d points exceeds max_points %d", n, h->pcap);
+    PF_CUDA(cudaSetDevice(h->device));
+    PF_CHECK(mapping_settle(h));
+    const float4* src = reinterpret_cast<const float4*>(xyzi);
+    if (!device_input && n > 0) {
+        PF_CUDA(cudaMemcpyAsync(h->d_in, xyzi, sizeof(float4) * (size_t)n, cudaMemcpyHostToDevice, h->stream));
+        src = h->d_in;
+    }
+    Workspace& ws = h->ws;
+    MapperParams P{};
+    P.buf = h->d_map[h->cur]; P.cbuf = h->d_cell[h->cur];
+    P.out = h->d_map[h->cur ^ 1]; P.cell_out = h->d_cell[h->cur ^ 1];
+    P.counts = h->d_counts; P.dropped = h->d_dropped;
+    P.inv_leaf = 1.0f / h->leaf;       // inverse_leaf_size_ = 1 / leaf_size_ (float)
+    P.bx = cell_of(rt[3]) - 2; P.by = cell_of(rt[7]) - 2; P.bz = cell_of(rt[11]) - 2;   // :154-156, block of checkPoints :110-149
+    P.m_ra = h->d_mra; P.m_start = h->d_mstart; P.m_len = h->d_mlen; P.i_ra = h->d_ira; P.i_pt = h->d_ipt; P.i_cell = h->d_icell;
+    P.exc = h->d_exc; P.exc_cell = h->d_exccell;
+    P.state = ws.ctrl + kSlotBase;
+    Mat34 T;
+    for (int i = 0; i < 12; ++i) T.m[i] = (float)rt[i];     // pose_current.cast<float>() (:162)
+    PF_CHECK(workspace_begin_step(ws));
+    int nblk = div_up(n > 0 ? n : 1, 256 * 2);
+    if (nblk > 4 * kSMs) nblk = 4 * kSMs;
+    k_mp_append<<<nblk, 256, 0, h->stream>>>(P, src, n, T);
+    const int capB = (h->map_ub - h->sorted_ub) + n > 0 ? (h->map_ub - h->sorted_ub) + n : 1;
+    PF_REQUIRE(capB <= h->pcap + kExcCap, "internal: %d unsorted points exceed the scratch capacity", capB);
+    int kblk = div_up(capB, 256 * 4);
+    if (kblk > 4 * kSMs) kblk = 4 * kSMs;
+    k_mp_keys<<<kblk, 256, 0, h->stream>>>(P, ws.keys[0]);
+    ws.launches += 2;
+    int rb = 0;
+    PF_CHECK(radix_sort(ws, reinterpret_cast<const int*>(P.state), capB, 4, true, &rb));
+    int tiles = div_up(capB, 256);
+    if (tiles > 6 * kSMs) tiles = 6 * kSMs;
+    k_mp_heads<<<tiles, 256, 0, h->stream>>>(P, ws.keys[rb], ws.vals[rb], ws.scan_status, ws.status_stride, ws.ctrl);
+    int mtiles = h->map_ub / kMpTile + 1;
+    if (mtiles > 4 * kSMs) mtiles = 4 * kSMs;
+    k_mp_merge<<<mtiles, 256, 0, h->stream>>>(P, ws.vals[rb], ws.scan_status, ws.ctrl);
+    k_mp_finish<<<1, 256, 0, h->stream>>>(P);
+    ws.launches += 3;
+    PF_CUDA(cudaGetLastError());
+    h->cur ^= 1;
+    PF_CUDA(cudaMemcpyAsync(h->h_counts, h->d_counts, sizeof(int) * 8, cudaMemcpyDeviceToHost, h->stream));
+    PF_CUDA(cudaMemcpyAsync(h->h_dropped, h->d_dropped, sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+    PF_CUDA(cudaEventRecord(h->ev, h->stream));
+    h->pending = true;
+    h->launches = ws.launches;
+    return PF_OK;
+}
+
+extern "C" int pf_mapping_update(pf_mapping* h, const float* xyzi, int n, const double rt[12]) { return mapping_update(h, xyzi, n, rt, 0); }
+extern "C" int pf_mapping_update_device(pf_mapping* h, const void* d_xyzi, int n, const double rt[12]) {
+    return mapping_update(h, (const float*)d_xyzi, n, rt, 1);
+}
+
+extern "C" int pf_mapping_map_size(pf_mapping* h, int* n) {
+    PF_REQUIRE(h && n, "null argument");
+    PF_CUDA(cudaSetDevice(h->device));
+    PF_CHECK(mapping_settle(h));
+    *n = h->map_ub;
+    return PF_OK;
+}
+
+// LaserMappingClass::getMap, src/laserMappingClass.cpp:196-208: all cells in (x, y, z) cell order, each in VoxelGrid order
+extern "C" int pf_mapping_get_map(pf_mapping* h, float* xyzi_out, int cap, int* n) {
+    PF_REQUIRE(h && xyzi_out && n, "null argument");
+    PF_CUDA(cudaSetDevice(h->device));
+    PF_CHECK(mapping_settle(h));
+    PF_REQUIRE(h->map_ub <= cap, "map has %d points, buffer holds %d", h->map_ub, cap);
+    if (h->map_ub) PF_CUDA(cudaMemcpyAsync(xyzi_out, h->d_map[h->cur], sizeof(float4) * (size_t)h->map_ub, cudaMemcpyDeviceToHost, h->stream));
+    PF_CUDA(cudaStreamSynchronize(h->stream));
+    *n = h->map_ub;
+    return PF_OK;
+}
+
+extern "C" int pf_mapping_stats(pf_mapping* h, int* n_sorted, long long* dropped, uint64_t* launches) {
+    PF_REQUIRE(h, "null argument");
+    PF_CUDA(cudaSetDevice(h->device));
+    PF_CHECK(mapping_settle(h));
+    if (n_sorted) *n_sorted = h->sorted_ub;
+    if (dropped) *dropped = (long long)*h->h_dropped;
+    if (launches) *launches = h->launches;
+    return PF_OK;
+}
+
+extern "C" void* pf_mapping_stream(pf_mapping* h) { return h ? (void*)h->stream : nullptr; }
