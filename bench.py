@@ -211,6 +211,39 @@ def roofline_leg(pfb, capi, torch, scans, dev):
             "ms_per_launch_group": ms, "launches_per_group": launches, "scans_per_s_extract_only": batch / ms * 1e3}
 
 
+def extra_kernel_legs(capi, dev_index):
+    """K9 (streaming map update) and K4 (exact 5-NN) at sizes whose working set exceeds L2: an ~8 M-voxel local map
+    (uniform points in the 200 m crop box, one per occupied 0.4 m voxel), one frame's worth of new points, 1 M queries."""
+    rng = np.random.default_rng(4008)
+    peak, how = _peaks()
+    n_raw = 10_000_000
+    xyz = (rng.random((n_raw, 3), dtype=np.float32) - 0.5) * np.array([198, 198, 40], np.float32)
+    raw = capi.make_points(xyz, r=0, g=200, b=0, a=255)
+    m0 = capi.map_update(raw, (0, 0, 0), 0.4, 0, 0.4, 75, device=dev_index)        # sorted, one point per voxel
+    del raw
+    add = capi.make_points((rng.random((20000, 3), dtype=np.float32) - 0.5) * np.array([120, 120, 12], np.float32), r=0, g=1)
+    t = capi.map_merge_timed(m0, add, (0.3, 0.1, 0.0), 0.4, 0, 0.4, 75, reps=6, device=dev_index)
+    bytes_k9 = 16.0 * (len(m0) + len(add)) + 16.0 * t["n_out"]
+    k9 = {"bound": "hbm", "kernel": "k_mm_count + k_mm_write (K9 streaming map update: CropBox + voxel merge + PFilter delete + r update)",
+          "map_points": int(len(m0)), "new_points": int(len(add)), "map_points_out": t["n_out"],
+          "achieved": bytes_k9 / (t["ms_stream"] * 1e-3) / 1e9, "peak": peak, "peak_source": how, "unit": "GB/s",
+          "frac": bytes_k9 / (t["ms_stream"] * 1e-3) / 1e9 / peak, "bytes_per_map_point": 32,
+          "ms_stream_kernel": t["ms_stream"], "ms_whole_update": t["ms_total"],
+          "frac_whole_update": bytes_k9 / (t["ms_total"] * 1e-3) / 1e9 / peak}
+    nq = 1_000_000
+    sel = rng.integers(0, len(m0), nq)
+    q = np.zeros((nq, 4), np.float32)
+    q[:, 0], q[:, 1], q[:, 2] = m0["x"][sel], m0["y"][sel], m0["z"][sel]
+    q[:, :3] += rng.normal(0, 0.2, (nq, 3)).astype(np.float32)
+    idx, d2, ms_build, ms_query = capi.knn5_timed(m0, q, reps=4, device=dev_index)
+    valid = float((idx[:, 4] >= 0).mean())
+    k4 = {"kernel": "k_knn5 (K4 exact 5-NN over the 1 m grid, one warp per query)", "map_points": int(len(m0)), "queries": nq,
+          "queries_per_s": nq / (ms_query * 1e-3), "ms_query_kernel": ms_query, "ms_grid_build": ms_build,
+          "valid_fraction": valid, "algorithmic_gbs": 136.0 * nq / (ms_query * 1e-3) / 1e9,
+          "grid_build_gbs": 36.0 * len(m0) / (ms_build * 1e-3) / 1e9}
+    return {"k9_map_merge": k9, "k4_knn": k4}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -299,6 +332,7 @@ def run_ours(args):
 
     if rank == 0:
         roof = roofline_leg(pfb, capi, torch, scans[:8], dev)
+        extra = extra_kernel_legs(capi, local)
         ncpu = min(K, 40)
         cpu_sps, cpu_dt, cpu_poses, kind = cpu_pipeline(scans[:ncpu], False)
         line = {
@@ -313,6 +347,8 @@ def run_ours(args):
                     "ms_per_step": ms_e2e_max / K, "api": "pf_frame_process (host pinned scan in, pose out, synchronous)"},
             "gpu_launches": int(launches), "gpu_launches_per_step": launches / K,
             "roofline": roof,
+            "knn_queries_per_s": extra["k4_knn"]["queries_per_s"],
+            "extra_kernels": extra,
             "cpu_baseline": {"value": cpu_sps, "unit": UNIT, "cores": 1, "kind": "port",
                              "sample": f"first {ncpu} frames of the same sequence, serial on one core: extraction = the reference's own "
                                        f"laserProcessingClass.cpp ({'compiled in place, oracle/_ref' if kind == 'reference' else 'restated'}), "

@@ -171,10 +171,19 @@ int pf_map_update(int device, const pf_point* in, int n, const double center[3],
  * centroids which left their voxel by float rounding are placed behind the sorted part: out[0, *n_sorted_out) is sorted. */
 int pf_map_merge(int device, const pf_point* sorted_map, int m_sorted, const pf_point* extra, int n_extra, const double center[3],
                  float leaf, int k_new, float theta_p, int theta_max, pf_point* out, int cap_out, int* n_out, int* n_sorted_out);
+/* Micro-benchmark form of pf_map_merge: inputs are uploaded once, the merge runs `reps` times on the device (the first
+ * repetition is a warm-up when reps > 1); ms_total = whole pipeline per repetition, ms_stream = the streaming kernel
+ * (k_mm_merge) alone, both CUDA-event timed on the library's stream.  No output copy. */
+int pf_map_merge_timed(int device, const pf_point* sorted_map, int m_sorted, const pf_point* extra, int n_extra, const double center[3],
+                       float leaf, int k_new, float theta_p, int theta_max, int reps, int* n_out, int* n_sorted_out, float* ms_total,
+                       float* ms_stream);
 /* KdTreeFLANN::nearestKSearch(k = 5) (src/odomEstimationClass.cpp:299, 447): exact, float L2_Simple distances,
  * ascending, ties by lower index.  Contract: results are exact whenever d2[5q+4] < 1.0 (the only case the
  * reference uses, :300/:451); otherwise idx[5q..] = -1 and d2 = +inf. */
 int pf_knn5(int device, const pf_point* map, int m, const float* queries_xyz4, int q, int32_t* idx, float* d2);
+/* Micro-benchmark form: grid build + query kernel repeated `reps` times on the device, CUDA-event timed separately. */
+int pf_knn5_timed(int device, const pf_point* map, int m, const float* queries_xyz4, int q, int32_t* idx, float* d2, int reps,
+                  float* ms_build, float* ms_query);
 /* One association pass (addEdgeCostFactor :284-432 / addSurfCostFactor :434-578) at a given pose, weightType 0:
  * per query: flag (0 none, 1 geometric fit ok but skipped by the persistence rule, 2 residual added),
  * geometry (edge: a[3], b[3]; surf: n[3], d; 8 doubles per query, unused slots 0), query r,g after the pass;

@@ -212,6 +212,26 @@ def map_merge(sorted_map, extra, center, leaf, k_new, theta_p, theta_max, device
     return out[:n.value].copy(), ns.value
 
 
+def map_merge_timed(sorted_map, extra, center, leaf, k_new, theta_p, theta_max, reps=5, device=0):
+    """pf_map_merge_timed: returns dict(n_out, n_sorted, ms_total, ms_stream)."""
+    a, b = _pts(sorted_map), _pts(extra)
+    n, ns, mt, ms = C.c_int(), C.c_int(), C.c_float(), C.c_float()
+    c = np.asarray(center, np.float64)
+    check(lib().pf_map_merge_timed(device, _vp(a), len(a), _vp(b), len(b), _vp(c), C.c_float(leaf), k_new, C.c_float(theta_p), theta_max,
+                                   reps, C.byref(n), C.byref(ns), C.byref(mt), C.byref(ms)))
+    return {"n_out": n.value, "n_sorted": ns.value, "ms_total": mt.value, "ms_stream": ms.value}
+
+
+def knn5_timed(map_pts, queries_xyz4, reps=5, device=0):
+    m = _pts(map_pts)
+    q = np.ascontiguousarray(queries_xyz4, np.float32)
+    idx = np.empty((max(len(q), 1), 5), np.int32)
+    d2 = np.empty((max(len(q), 1), 5), np.float32)
+    mb, mq = C.c_float(), C.c_float()
+    check(lib().pf_knn5_timed(device, _vp(m), len(m), _vp(q), len(q), _vp(idx), _vp(d2), reps, C.byref(mb), C.byref(mq)))
+    return idx[:len(q)], d2[:len(q)], mb.value, mq.value
+
+
 def knn5(map_pts, queries_xyz4, device=0):
     m = _pts(map_pts)
     q = np.ascontiguousarray(queries_xyz4, np.float32)

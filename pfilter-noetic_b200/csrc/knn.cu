@@ -166,8 +166,9 @@ struct KnnTap {
 };
 }  // namespace
 
-extern "C" int pf_knn5(int device, const pf_point* map, int m, const float* queries_xyz4, int q, int32_t* idx, float* d2) {
-    PF_REQUIRE(m >= 0 && q >= 0 && (map || m == 0) && (queries_xyz4 || q == 0) && idx && d2, "bad argument");
+static int knn5_tap(int device, const pf_point* map, int m, const float* queries_xyz4, int q, int32_t* idx, float* d2, int reps,
+                    float* ms_build, float* ms_query) {
+    PF_REQUIRE(m >= 0 && q >= 0 && (map || m == 0) && (queries_xyz4 || q == 0) && idx && d2 && reps >= 1, "bad argument");
     PF_CUDA(cudaSetDevice(device));
     KnnTap t;
     PF_CUDA(cudaStreamCreateWithFlags(&t.stream, cudaStreamNonBlocking));
@@ -193,10 +194,26 @@ extern "C" int pf_knn5(int device, const pf_point* map, int m, const float* quer
     G.cell_start[0] = t.d_cs; G.cell_start[1] = t.d_cs;
     G.cell_end[0] = t.d_ce; G.cell_end[1] = t.d_ce;
     G.geom[0] = t.d_geom; G.geom[1] = t.d_geom + 6;
-    PF_CHECK(workspace_begin_step(t.ws));
-    PF_CHECK(build_grids(t.ws, G, 0, mc, 0));
+    cudaEvent_t ev[3];
+    for (int i = 0; i < 3; ++i) PF_CUDA(cudaEventCreate(&ev[i]));
     KnnGrid g{t.d_pts, t.d_cs, t.d_ce, t.d_geom};
-    if (q) k_knn5_tap<<<div_up(q, 8), 256, 0, t.stream>>>(g, t.d_q, q, t.d_idx, t.d_d2);
+    float sum_b = 0.f, sum_q = 0.f;
+    for (int r = 0; r < reps; ++r) {          // repetition 0 is the warm-up when reps > 1
+        PF_CUDA(cudaEventRecord(ev[0], t.stream));
+        PF_CHECK(workspace_begin_step(t.ws));
+        PF_CHECK(build_grids(t.ws, G, 0, mc, 0));
+        PF_CUDA(cudaEventRecord(ev[1], t.stream));
+        if (q) k_knn5_tap<<<div_up(q, 8), 256, 0, t.stream>>>(g, t.d_q, q, t.d_idx, t.d_d2);
+        PF_CUDA(cudaEventRecord(ev[2], t.stream));
+        PF_CUDA(cudaStreamSynchronize(t.stream));
+        float a = 0.f, b = 0.f;
+        PF_CUDA(cudaEventElapsedTime(&a, ev[0], ev[1]));
+        PF_CUDA(cudaEventElapsedTime(&b, ev[1], ev[2]));
+        if (r > 0 || reps == 1) { sum_b += a; sum_q += b; }
+    }
+    for (int i = 0; i < 3; ++i) cudaEventDestroy(ev[i]);
+    if (ms_build) *ms_build = sum_b / (reps > 1 ? reps - 1 : 1);
+    if (ms_query) *ms_query = sum_q / (reps > 1 ? reps - 1 : 1);
     unsigned err = 0;
     PF_CUDA(cudaMemcpyAsync(&err, t.ws.ctrl + kSlotBase + 15, sizeof(unsigned), cudaMemcpyDeviceToHost, t.stream));
     if (q) {
@@ -206,4 +223,13 @@ extern "C" int pf_knn5(int device, const pf_point* map, int m, const float* quer
     PF_CUDA(cudaStreamSynchronize(t.stream));
     if (err) { set_error("map extent exceeds the search grid capacity (%d cells of 1 m)", kGridCellCap); return PF_ERR_CAPACITY; }
     return PF_OK;
+}
+
+extern "C" int pf_knn5(int device, const pf_point* map, int m, const float* queries_xyz4, int q, int32_t* idx, float* d2) {
+    return knn5_tap(device, map, m, queries_xyz4, q, idx, d2, 1, nullptr, nullptr);
+}
+
+extern "C" int pf_knn5_timed(int device, const pf_point* map, int m, const float* queries_xyz4, int q, int32_t* idx, float* d2, int reps,
+                             float* ms_build, float* ms_query) {
+    return knn5_tap(device, map, m, queries_xyz4, q, idx, d2, reps, ms_build, ms_query);
 }

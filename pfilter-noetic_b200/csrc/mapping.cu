@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(256) k_mp_heads(MapperParams P, const uint32_t
                                                   unsigned long long* status, int status_stride, unsigned* ctrl) {
     __shared__ int s_tile;
     __shared__ int s_tmp[9];
-    __shared__ unsigned s_bcast;
+    __shared__ unsigned s_look[kScanSmemWords];
     const int nv = (int)P.state[2];
     const int mA = P.counts[0];
     const float4* bpts = P.buf + mA;
@@ -201,10 +201,10 @@ __global__ void __launch_bounds__(256) k_mp_heads(MapperParams P, const uint32_t
         const unsigned tag = (ctrl[0] << 3);
         int total_m, total_i;
         const int lm = block_scan_excl_256(matched ? 1 : 0, s_tmp, &total_m);
-        const unsigned excl_m = chained_scan_exclusive(status, tag | 2u, tile, (unsigned)total_m, &s_bcast);
+        const unsigned excl_m = chained_scan_exclusive(status, tag | 2u, tile, (unsigned)total_m, s_look);
         if (matched) { const int idx = (int)excl_m + lm; P.m_ra[idx] = rA; P.m_start[idx] = e; P.m_len[idx] = len; }
         const int li = block_scan_excl_256(ins ? 1 : 0, s_tmp, &total_i);
-        const unsigned excl_i = chained_scan_exclusive(status + status_stride, tag | 3u, tile, (unsigned)total_i, &s_bcast);
+        const unsigned excl_i = chained_scan_exclusive(status + status_stride, tag | 3u, tile, (unsigned)total_i, s_look);
         if (ins) { const int idx = (int)excl_i + li; P.i_ra[idx] = rA; P.i_pt[idx] = o; P.i_cell[idx] = cell; }
         if (tile == (nv - 1) / 256 && threadIdx.x == 0) {
             P.state[4] = excl_m + (unsigned)total_m;
@@ -240,7 +240,7 @@ __global__ void __launch_bounds__(256) k_mp_merge(MapperParams P, const uint32_t
     __shared__ int s_rng[4];
     __shared__ int s_tile;
     __shared__ int s_tmp[9];
-    __shared__ unsigned s_bcast;
+    __shared__ unsigned s_look[kScanSmemWords];
     const int mA = P.counts[0];
     const int ntiles = mA / kMpTile + 1;     // the last tile also takes the inserts behind the last map point
     const int nm = (int)P.state[4], ni = (int)P.state[6];
@@ -313,7 +313,7 @@ __global__ void __launch_bounds__(256) k_mp_merge(MapperParams P, const uint32_t
             if (tid == 255) s_pre[kMpTile] = run;
         }
         const unsigned tag = (ctrl[0] << 3) | 4u;
-        const unsigned gbase = chained_scan_exclusive(status, tag, tile, (unsigned)total, &s_bcast);
+        const unsigned gbase = chained_scan_exclusive(status, tag, tile, (unsigned)total, s_look);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             if (keep[k]) {

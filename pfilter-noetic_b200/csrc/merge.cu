@@ -3,11 +3,17 @@
 //                 cropped points -> 0xffffffff (sorted last, dropped)
 //   radix_sort  : stable, so equal keys keep their buffer order = the canonical summation order
 //   k_mm_heads  : one thread per run of equal keys in sorted B: lower_bound in the sorted map part by recomputed keys
-//                 (no key array for the map is ever stored); runs that meet a live map point are recorded as "matched",
+//                 (no key array for the map is ever stored).  A run that meets a live map point is finished right here
+//                 (map point + run, delete rule, r update) and recorded as "matched" = a replacement for that map point;
 //                 the others are reduced to finished voxels ("inserts"); both lists are compacted in key order
-//   k_mm_merge  : tiles of 1024 sorted map points: CropBox, merge with the matched run, delete rule, r update, positions
-//                 by a block scan over (kept map points + inserts before each slot) and a chained scan across tiles
+//   k_mm_tiles  : per tile of 1024 sorted map points, the first matched voxel / insert that falls into it
+//   k_mm_count  : streaming pass 1: points every tile will emit (no shared memory, no barrier)
+//   k_mm_write  : streaming pass 2: CropBox, delete rule, r update, replacements, inserts; output offsets from pass 1
 //   k_mm_finish : appends the exceptions (centroids that left their voxel) behind the sorted part and publishes the counts
+// Why two passes instead of one pass with a decoupled look-back: with ~700 tiles in flight the look-back chains every tile
+// to the slowest of its predecessors; all CTAs fall into lockstep (load burst, idle, store burst) and the single-pass
+// version measured 1.2-1.4 TB/s on an 8 M-point map.  Two independent streaming passes (16 B + 16 B read, 16 B written per
+// point) have no inter-CTA dependency at all and measure 3.0 TB/s of algorithmic bytes (4.5 TB/s of DRAM traffic).
 #include "merge.cuh"
 
 namespace pf {
@@ -68,6 +74,11 @@ __device__ __forceinline__ bool acc_finish(const VoxAcc& a, const MapMergeParams
     const int r2 = a.rmax > 250 ? 255 : a.rmax + 2;
     o->rgba = pack_rgba((unsigned)r2, (unsigned)a.gmax, 0u, 255u);
     return !drop;
+}
+// delete rule for a voxel that keeps its single map point (extractstablepoint :12-14 on the point's own counters)
+__device__ __forceinline__ bool single_point_kept(const MapMergeParams& P, uint32_t rgba) {
+    const int r = (int)pt_r(rgba), g = (int)pt_g(rgba);
+    return !(((float)g < __fmul_rn((float)r, P.theta_p)) && (r > P.k_new) && (g < P.theta_max + 1));
 }
 // a centroid that left the voxel it was averaged in cannot stay in the sorted part
 __device__ __forceinline__ bool left_voxel(const Pt& o, long long k64, float leaf, const Origin& g) { return key64_of(o, leaf, g) != k64; }
@@ -144,7 +155,7 @@ __global__ void __launch_bounds__(256) k_mm_heads(MapMergeParams P, const uint32
     const MapMergeCloud& c = P.c[cloud];
     __shared__ int s_tile;
     __shared__ int s_tmp[9];
-    __shared__ unsigned s_bcast;
+    __shared__ unsigned s_look[kScanSmemWords];
     const int nv = (int)P.state[2 + cloud];
     const int s0 = cloud == 0 ? 0 : (int)P.state[2];
     const int end = s0 + nv;
@@ -163,7 +174,7 @@ __global__ void __launch_bounds__(256) k_mm_heads(MapMergeParams P, const uint32
         if (tile * 256 >= nv) return;
         const int e = s0 + tile * 256 + threadIdx.x;
         bool matched = false, ins = false;
-        int rA = 0, len = 0;
+        int rA = 0, len = 0, delta = 0;
         Pt o{0.f, 0.f, 0.f, 0u};
         if (e < end) {
             const unsigned key = keys[e];
@@ -178,12 +189,17 @@ __global__ void __launch_bounds__(256) k_mm_heads(MapMergeParams P, const uint32
                     if (key64_of(c.buf[mid], c.leaf, g) < k64) lo = mid + 1; else hi = mid;
                 }
                 rA = lo;
+                VoxAcc acc;
+                bool a_kept = false;
                 if (rA < mA) {
                     const Pt a = c.buf[rA];
                     matched = key64_of(a, c.leaf, g) == k64 && in_box(box, a);
+                    if (matched) {      // the map point leads the voxel's sum; remember what it would have done on its own
+                        acc_add(acc, a);
+                        a_kept = single_point_kept(P, a.rgba);
+                    }
                 }
-                if (!matched) {
-                    VoxAcc acc;
+                {
                     for (int q = e; q < e2; q += 8) {
                         Pt v[8];
 #pragma unroll
@@ -193,10 +209,13 @@ __global__ void __launch_bounds__(256) k_mm_heads(MapMergeParams P, const uint32
                         for (int u = 0; u < 8; ++u)
                             if (q + u < e2) acc_add(acc, v[u]);
                     }
-                    const bool keep = acc_finish(acc, P, &o);
-                    if (keep) {
-                        if (acc.n > 1 && left_voxel(o, k64, c.leaf, g)) put_exception(P, cloud, o);
-                        else ins = true;
+                    bool keep = acc_finish(acc, P, &o);
+                    if (keep && acc.n > 1 && left_voxel(o, k64, c.leaf, g)) { put_exception(P, cloud, o); keep = false; }
+                    if (matched) {      // finished voxel replaces the map point in the streaming pass; alpha = 0 marks "not kept"
+                        if (!keep) o.rgba &= 0x00ffffffu;
+                        delta = (keep ? 1 : 0) - (a_kept ? 1 : 0);
+                    } else {
+                        ins = keep;
                     }
                 }
             }
@@ -204,13 +223,13 @@ __global__ void __launch_bounds__(256) k_mm_heads(MapMergeParams P, const uint32
         const unsigned tag = (ctrl[0] << 3);
         int total_m, total_i;
         const int lm = block_scan_excl_256(matched ? 1 : 0, s_tmp, &total_m);
-        const unsigned excl_m = chained_scan_exclusive(status + (size_t)cloud * status_stride, tag | 2u, tile, (unsigned)total_m, &s_bcast);
+        const unsigned excl_m = chained_scan_exclusive(status + (size_t)cloud * status_stride, tag | 2u, tile, (unsigned)total_m, s_look);
         if (matched) {
             const int idx = lbase + (int)excl_m + lm;
-            P.s.m_ra[idx] = rA; P.s.m_start[idx] = e; P.s.m_len[idx] = len;
+            P.s.m_ra[idx] = rA; P.s.m_pt[idx] = o; P.s.m_delta[idx] = delta;
         }
         const int li = block_scan_excl_256(ins ? 1 : 0, s_tmp, &total_i);
-        const unsigned excl_i = chained_scan_exclusive(status + (size_t)(2 + cloud) * status_stride, tag | 3u, tile, (unsigned)total_i, &s_bcast);
+        const unsigned excl_i = chained_scan_exclusive(status + (size_t)(2 + cloud) * status_stride, tag | 3u, tile, (unsigned)total_i, s_look);
         if (ins) {
             const int idx = lbase + (int)excl_i + li;
             P.s.i_ra[idx] = rA; P.s.i_pt[idx] = o;
@@ -222,107 +241,195 @@ __global__ void __launch_bounds__(256) k_mm_heads(MapMergeParams P, const uint32
     }
 }
 
-__global__ void __launch_bounds__(256) k_mm_merge(MapMergeParams P, const uint32_t* __restrict__ vals, unsigned long long* status,
-                                                  int status_stride, unsigned* ctrl, int ticket_word) {
+// Static partition of the map tiles over the CTAs of the two streaming kernels: CTA b owns tiles [b * per, (b + 1) * per).
+struct TileRange { int lo, hi, ntiles; };
+__device__ __forceinline__ TileRange tile_range(int mA) {
+    TileRange r;
+    r.ntiles = mA / kMergeTile + 1;     // the last tile also takes the inserts behind the last map point
+    const int per = (r.ntiles + (int)gridDim.x - 1) / (int)gridDim.x;
+    r.lo = min(r.ntiles, (int)blockIdx.x * per);
+    r.hi = min(r.ntiles, r.lo + per);
+    return r;
+}
+
+// per tile of the sorted map part: first matched head / first insert at or behind the tile's first map index; zeroes the
+// per-tile and per-CTA counters of the count pass
+__global__ void __launch_bounds__(256) k_mm_tiles(MapMergeParams P) {
+    const int cloud = blockIdx.y;
+    const int mA = *P.c[cloud].n_sorted;
+    const int ntiles = mA / kMergeTile + 1;
+    const int nm = (int)P.state[4 + cloud], ni = (int)P.state[6 + cloud];
+    const int* m_ra = P.s.m_ra + cloud * P.s.cap;
+    const int* i_ra = P.s.i_ra + cloud * P.s.cap;
+    int* tm = P.s.tile_m + (size_t)cloud * P.s.tile_cap;
+    int* ti = P.s.tile_i + (size_t)cloud * P.s.tile_cap;
+    int* agg = P.s.tile_agg + (size_t)cloud * P.s.tile_cap;
+    if (ntiles + 1 > P.s.tile_cap) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(&P.state[15], 8u);
+        return;
+    }
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < kMergeMaxGrid; t += gridDim.x * blockDim.x) P.s.cta_sum[cloud * kMergeMaxGrid + t] = 0;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t <= ntiles; t += gridDim.x * blockDim.x) {
+        int a = nm, b = ni;
+        if (t < ntiles) {
+            const int key = t * kMergeTile;
+            int lo = 0, hi = nm;
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if (m_ra[mid] < key) lo = mid + 1; else hi = mid; }
+            a = lo;
+            lo = 0; hi = ni;
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if (i_ra[mid] < key) lo = mid + 1; else hi = mid; }
+            b = lo;
+        }
+        tm[t] = a; ti[t] = b; agg[t] = 0;
+    }
+}
+
+// Streaming pass 1 (count): how many points every tile of the sorted map part will emit -- its own points that survive the
+// crop box and the delete rule, corrected by the matched voxels finished in k_mm_heads, plus the inserts that fall into the
+// tile.  No shared memory, no barrier: 16 B read per map point, one warp-aggregated atomic per warp and tile.
+__global__ void __launch_bounds__(256) k_mm_count(MapMergeParams P) {
     const int cloud = blockIdx.y;
     const MapMergeCloud& c = P.c[cloud];
-    __shared__ int s_link[kMergeTile];          // matched head + 1 of a slot
-    __shared__ int s_cnt[kMergeTile + 1];       // inserts in front of a slot
-    __shared__ int s_first[kMergeTile + 1];     // first insert entry of a slot
-    __shared__ int s_pre[kMergeTile + 1];       // output offset of the first insert of a slot
-    __shared__ int s_rng[4];
-    __shared__ int s_tile;
-    __shared__ int s_tmp[9];
-    __shared__ unsigned s_bcast;
     const int mA = *c.n_sorted;
-    const int ntiles = mA / kMergeTile + 1;     // the last tile also takes the inserts behind the last map point
-    const int nm = (int)P.state[4 + cloud], ni = (int)P.state[6 + cloud];
-    const int bbase = cloud == 0 ? 0 : (int)P.state[0];
+    const TileRange R = tile_range(mA);
     const int lbase = cloud * P.s.cap;
-    const int* m_ra = P.s.m_ra + lbase;
-    const int* i_ra = P.s.i_ra + lbase;
+    const int* tm = P.s.tile_m + (size_t)cloud * P.s.tile_cap;
+    const int* ti = P.s.tile_i + (size_t)cloud * P.s.tile_cap;
+    int* agg = P.s.tile_agg + (size_t)cloud * P.s.tile_cap;
     const CropBox box = crop_of(P.center);
-    const Origin g = origin_of(box, c.leaf);
-    const Pt* bpts = c.buf + mA;
     const int tid = threadIdx.x;
-    while (true) {
-        __syncthreads();
-        if (tid == 0) s_tile = (int)atomicAdd(&ctrl[ticket_word + cloud], 1u);
-        __syncthreads();
-        const int tile = s_tile;
-        if (tile >= ntiles) return;
-        const int base = tile * kMergeTile;
-        const bool last = tile == ntiles - 1;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) { s_link[tid + 256 * k] = 0; s_cnt[tid + 256 * k] = 0; s_first[tid + 256 * k] = 0x7fffffff; }
-        if (tid == 0) { s_cnt[kMergeTile] = 0; s_first[kMergeTile] = 0x7fffffff; }
-        if (tid < 32) {
-            const int a = warp_lower_bound(m_ra, nm, base);
-            const int b = last ? nm : warp_lower_bound(m_ra, nm, base + kMergeTile);
-            if (tid == 0) { s_rng[0] = a; s_rng[1] = b; }
-        } else if (tid < 64) {
-            const int a = warp_lower_bound(i_ra, ni, base);
-            const int b = last ? ni : warp_lower_bound(i_ra, ni, base + kMergeTile);
-            if (tid == 32) { s_rng[2] = a; s_rng[3] = b; }
-        }
-        __syncthreads();
-        const int mLo = s_rng[0], mHi = s_rng[1], iLo = s_rng[2], iHi = s_rng[3];
-        for (int h = mLo + tid; h < mHi; h += 256) s_link[m_ra[h] - base] = h + 1;
-        for (int e = iLo + tid; e < iHi; e += 256) {
-            const int s = i_ra[e] - base;
-            atomicAdd(&s_cnt[s], 1);
-            atomicMin(&s_first[s], e);
-        }
-        __syncthreads();
-        // the map points of the tile: thread owns 4 consecutive slots
-        Pt o[4];
-        bool keep[4];
+    int cta_part = 0;
+    const unsigned long long keep_in_l2 = l2_policy_evict_last();
+    for (int t = R.lo; t < R.hi; ++t) {
+        const int base = t * kMergeTile;
         int v = 0;
+        Pt p[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            const int slot = 4 * tid + k, i = base + slot;
-            keep[k] = false;
-            if (i < mA) {
-                const Pt p = c.buf[i];
-                if (in_box(box, p)) {
-                    VoxAcc acc;
-                    acc_add(acc, p);
-                    const int l = s_link[slot];
-                    if (l) {
-                        const int st = P.s.m_start[lbase + l - 1], ln = P.s.m_len[lbase + l - 1];
-                        for (int q = 0; q < ln; ++q) acc_add(acc, bpts[(int)vals[st + q] - bbase]);
-                    }
-                    Pt r;
-                    bool kp = acc_finish(acc, P, &r);
-                    if (kp && acc.n > 1 && left_voxel(r, key64_of(p, c.leaf, g), c.leaf, g)) { put_exception(P, cloud, r); kp = false; }
-                    keep[k] = kp;
-                    o[k] = r;
+            const int i = base + k * 256 + tid;        // coalesced: the count does not care which thread sees which point
+            p[k] = Pt{3.0e38f, 0.f, 0.f, 0u};     // far outside any crop box
+            if (i < mA) *reinterpret_cast<float4*>(&p[k]) = ld_f4_l2hint(c.buf + i, keep_in_l2);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v += (in_box(box, p[k]) && single_point_kept(P, p[k].rgba)) ? 1 : 0;
+        const int mLo = tm[t], mHi = tm[t + 1];
+        for (int h = mLo + tid; h < mHi; h += 256) v += P.s.m_delta[lbase + h];
+        if (tid == 0) v += ti[t + 1] - ti[t];
+        v = __reduce_add_sync(0xffffffffu, v);
+        if ((tid & 31) == 0 && v) atomicAdd(&agg[t], v);
+        cta_part += v;
+    }
+    if ((tid & 31) == 0 && cta_part) atomicAdd(&P.s.cta_sum[cloud * kMergeMaxGrid + blockIdx.x], cta_part);
+}
+
+// first index in [lo, hi) with a[idx] >= key (few entries: the heads / inserts that fall into one tile)
+__device__ __forceinline__ int lower_bound_i(const int* __restrict__ a, int lo, int hi, int key) {
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (a[mid] < key) lo = mid + 1; else hi = mid; }
+    return lo;
+}
+
+// Streaming pass 2 (write): same static partition, tiles walked in DESCENDING order so that the part of the map the count
+// pass read last is read again first (what is still in the 126 MB L2).  The output offset of a tile needs no communication:
+// exclusive prefix of the CTA sums + the per-tile counts of pass 1.  Inside a tile a thread owns the slots tid, tid + 256,
+// ... (coalesced 16-byte loads; kept points of a warp row land on consecutive output positions = coalesced stores); the
+// kept-prefix is 32 ballot words + one 32-lane scan, the few matched voxels / inserts of the tile are found by binary
+// search in their sorted lists, so a tile costs two barriers and 264 bytes of shared memory.
+__global__ void __launch_bounds__(256, 8) k_mm_write(MapMergeParams P) {
+    const int cloud = blockIdx.y;
+    const MapMergeCloud& c = P.c[cloud];
+    __shared__ unsigned s_mask[2][32];          // kept ballots of the 32 (row, warp) segments, double buffered by tile parity
+    __shared__ int s_segpre[2][33];             // exclusive kept-prefix of the segments, [32] = kept in the tile
+    __shared__ int s_tmp[9];
+    const int mA = *c.n_sorted;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int lbase = cloud * P.s.cap;
+    const int ni_all = (int)P.state[6 + cloud];
+    if (mA == 0) {       // first update after initMapWithPoints: everything is an insert, already in key order
+        for (int e = blockIdx.x * 256 + tid; e < ni_all; e += gridDim.x * 256) c.out[e] = P.s.i_pt[lbase + e];
+        if (blockIdx.x == 0 && tid == 0) *c.n_sorted_out = ni_all;
+        return;
+    }
+    const TileRange R = tile_range(mA);
+    if (R.lo >= R.hi) return;
+    const int* m_ra = P.s.m_ra + lbase;
+    const int* i_ra = P.s.i_ra + lbase;
+    const int* tm = P.s.tile_m + (size_t)cloud * P.s.tile_cap;
+    const int* ti = P.s.tile_i + (size_t)cloud * P.s.tile_cap;
+    const int* agg = P.s.tile_agg + (size_t)cloud * P.s.tile_cap;
+    const CropBox box = crop_of(P.center);
+    // exclusive prefix of the CTA sums in front of this CTA
+    int running;
+    {
+        int v = 0;
+        for (int b = tid; b <= (int)blockIdx.x; b += 256) v += P.s.cta_sum[cloud * kMergeMaxGrid + b];
+        int total;
+        block_scan_excl_256(v, s_tmp, &total);
+        running = total;                        // inclusive of this CTA: output end of its last tile
+    }
+    if (R.hi == R.ntiles && tid == 0) *c.n_sorted_out = running;
+    const unsigned long long use_once = l2_policy_evict_first();
+    for (int tile = R.hi - 1, par = 0; tile >= R.lo; --tile, par ^= 1) {
+        const int emit = agg[tile];
+        const int gbase = running - emit;
+        running = gbase;
+        const int base = tile * kMergeTile;
+        Pt p[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int i = base + k * 256 + tid;
+            p[k] = Pt{0.f, 0.f, 0.f, 0u};
+            if (i < mA) *reinterpret_cast<float4*>(&p[k]) = ld_f4_l2hint(c.buf + i, use_once);
+        }
+        const int mLo = tm[tile], mHi = tm[tile + 1], iLo = ti[tile], iHi = ti[tile + 1];
+        unsigned mask[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int i = base + k * 256 + tid;
+            bool keep = false;
+            if (i < mA && in_box(box, p[k])) {
+                int h = mHi;
+                if (mHi > mLo) { h = lower_bound_i(m_ra, mLo, mHi, i); if (h < mHi && m_ra[h] != i) h = mHi; }
+                if (h == mHi) {     // the voxel keeps its single point: x / 1 = x, counters from the point itself
+                    keep = single_point_kept(P, p[k].rgba);
+                    const unsigned r = pt_r(p[k].rgba);
+                    p[k].rgba = pack_rgba(r > 250u ? 255u : r + 2u, pt_g(p[k].rgba), 0u, 255u);
+                } else {            // finished in k_mm_heads
+                    p[k] = P.s.m_pt[lbase + h];
+                    keep = (p[k].rgba >> 24) != 0u;
                 }
             }
-            v += (keep[k] ? 1 : 0) + s_cnt[slot];
+            mask[k] = __ballot_sync(0xffffffffu, keep);
+            if (lane == 0) s_mask[par][k * 8 + w] = mask[k];
         }
-        if (tid == 255) v += s_cnt[kMergeTile];
-        int total;
-        const int t_excl = block_scan_excl_256(v, s_tmp, &total);
-        {
-            int run = t_excl;
+        __syncthreads();
+        if (w == 0) {
+            const int cnt = __popc(s_mask[par][lane]);
+            int x = cnt;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                s_pre[4 * tid + k] = run;
-                run += s_cnt[4 * tid + k] + (keep[k] ? 1 : 0);
+            for (int o = 1; o < 32; o <<= 1) {
+                const int y = __shfl_up_sync(0xffffffffu, x, o);
+                if (lane >= o) x += y;
             }
-            if (tid == 255) s_pre[kMergeTile] = run;
+            s_segpre[par][lane] = x - cnt;
+            if (lane == 31) s_segpre[par][32] = x;
         }
-        const unsigned tag = (ctrl[0] << 3) | 4u;
-        const unsigned gbase = chained_scan_exclusive(status + (size_t)cloud * status_stride, tag, tile, (unsigned)total, &s_bcast);
+        __syncthreads();
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-            if (keep[k]) c.out[gbase + s_pre[4 * tid + k] + s_cnt[4 * tid + k]] = o[k];
-        for (int e = iLo + tid; e < iHi; e += 256) {
-            const int s = i_ra[e] - base;
-            c.out[gbase + s_pre[s] + (e - s_first[s])] = P.s.i_pt[lbase + e];
+        for (int k = 0; k < 4; ++k) {
+            if (mask[k] >> lane & 1u) {
+                const int i = base + k * 256 + tid;
+                int pos = gbase + s_segpre[par][k * 8 + w] + __popc(mask[k] & lanemask_lt());
+                if (iHi > iLo) pos += lower_bound_i(i_ra, iLo, iHi, i + 1) - iLo;      // inserts in front of this point
+                st_f4_l2hint(c.out + pos, *reinterpret_cast<const float4*>(&p[k]), use_once);
+            }
         }
-        if (last && tid == 0) *c.n_sorted_out = (int)gbase + total;
+        const int kept = s_segpre[par][32];
+        for (int e = iLo + tid; e < iHi; e += 256) {
+            const int s = i_ra[e] - base;      // the insert goes in front of slot s; s >= 1024: behind the last map point
+            const int before = s >= kMergeTile ? kept : s_segpre[par][s >> 5] + __popc(s_mask[par][s >> 5] & ((1u << (s & 31)) - 1u));
+            c.out[gbase + before + (e - iLo)] = P.s.i_pt[lbase + e];
+        }
+        if (tid == 0 && kept + (iHi - iLo) != emit) atomicOr(&P.state[15], 16u);     // the two passes must agree
     }
 }
 
@@ -341,13 +448,18 @@ __global__ void __launch_bounds__(256) k_mm_finish(MapMergeParams P) {
 
 }  // namespace
 
-int map_merge_scratch_create(MapMergeScratch& s, int cap_b, int exc_cap) {
+int map_merge_scratch_create(MapMergeScratch& s, int cap_b, int exc_cap, int cap_a) {
     s.cap = cap_b;
     s.exc_cap = exc_cap;
+    s.tile_cap = cap_a / kMergeTile + 3;
+    PF_CUDA(cudaMalloc(&s.tile_m, sizeof(int) * 2 * (size_t)s.tile_cap));
+    PF_CUDA(cudaMalloc(&s.tile_i, sizeof(int) * 2 * (size_t)s.tile_cap));
+    PF_CUDA(cudaMalloc(&s.tile_agg, sizeof(int) * 2 * (size_t)s.tile_cap));
+    PF_CUDA(cudaMalloc(&s.cta_sum, sizeof(int) * 2 * kMergeMaxGrid));
     const size_t n = (size_t)2 * cap_b;
     PF_CUDA(cudaMalloc(&s.m_ra, sizeof(int) * n));
-    PF_CUDA(cudaMalloc(&s.m_start, sizeof(int) * n));
-    PF_CUDA(cudaMalloc(&s.m_len, sizeof(int) * n));
+    PF_CUDA(cudaMalloc(&s.m_pt, sizeof(Pt) * n));
+    PF_CUDA(cudaMalloc(&s.m_delta, sizeof(int) * n));
     PF_CUDA(cudaMalloc(&s.i_ra, sizeof(int) * n));
     PF_CUDA(cudaMalloc(&s.i_pt, sizeof(Pt) * n));
     PF_CUDA(cudaMalloc(&s.exc, sizeof(Pt) * 2 * (size_t)exc_cap));
@@ -355,7 +467,8 @@ int map_merge_scratch_create(MapMergeScratch& s, int cap_b, int exc_cap) {
 }
 
 void map_merge_scratch_destroy(MapMergeScratch& s) {
-    cudaFree(s.m_ra); cudaFree(s.m_start); cudaFree(s.m_len); cudaFree(s.i_ra); cudaFree(s.i_pt); cudaFree(s.exc);
+    cudaFree(s.m_ra); cudaFree(s.m_pt); cudaFree(s.m_delta); cudaFree(s.i_ra); cudaFree(s.i_pt); cudaFree(s.exc);
+    cudaFree(s.tile_m); cudaFree(s.tile_i); cudaFree(s.tile_agg); cudaFree(s.cta_sum);
     s = MapMergeScratch();
 }
 
@@ -375,11 +488,19 @@ int map_merge(Workspace& ws, const MapMergeParams& P_in, int capB0, int capB1, i
     int tiles = div_up(capBmax > 0 ? capBmax : 1, 256);
     if (tiles > 6 * kSMs) tiles = 6 * kSMs;
     k_mm_heads<<<dim3(tiles, 2), 256, 0, ws.stream>>>(P, ws.keys[rb], ws.vals[rb], ws.scan_status, ws.status_stride, ws.ctrl, 5);
-    int mtiles = capAmax / kMergeTile + 1;
-    if (mtiles > 4 * kSMs) mtiles = 4 * kSMs;
-    k_mm_merge<<<dim3(mtiles, 2), 256, 0, ws.stream>>>(P, ws.vals[rb], ws.scan_status, ws.status_stride, ws.ctrl, 7);
+    const int mtiles_all = capAmax / kMergeTile + 1;
+    int tblk = div_up(mtiles_all + 1, 256);
+    if (tblk > 2 * kSMs) tblk = 2 * kSMs;
+    k_mm_tiles<<<dim3(tblk, 2), 256, 0, ws.stream>>>(P);
+    int grid = mtiles_all;
+    if (grid > kMergeMaxGrid) grid = kMergeMaxGrid;
+
+    if (ws.ev_a) cudaEventRecord(ws.ev_a, ws.stream);
+    k_mm_count<<<dim3(grid, 2), 256, 0, ws.stream>>>(P);
+    k_mm_write<<<dim3(grid, 2), 256, 0, ws.stream>>>(P);      // same grid: same tile partition
+    if (ws.ev_b) cudaEventRecord(ws.ev_b, ws.stream);
     k_mm_finish<<<2, 256, 0, ws.stream>>>(P);
-    ws.launches += 3;
+    ws.launches += 5;
     PF_CUDA(cudaGetLastError());
     return PF_OK;
 }
@@ -391,12 +512,14 @@ int map_merge(Workspace& ws, const MapMergeParams& P_in, int capB0, int capB1, i
 // ------------------------------------------------------------------------------------------------------------
 using namespace pf;
 
-extern "C" int pf_map_merge(int device, const pf_point* sorted_map, int m_sorted, const pf_point* extra, int n_extra, const double center[3],
-                            float leaf, int k_new, float theta_p, int theta_max, pf_point* out, int cap_out, int* n_out, int* n_sorted_out) {
-    PF_REQUIRE(m_sorted >= 0 && n_extra >= 0 && (sorted_map || m_sorted == 0) && (extra || n_extra == 0) && center && out && n_out && n_sorted_out,
+static int map_merge_tap(int device, const pf_point* sorted_map, int m_sorted, const pf_point* extra, int n_extra, const double center[3],
+                         float leaf, int k_new, float theta_p, int theta_max, pf_point* out, int cap_out, int* n_out, int* n_sorted_out,
+                         int reps, float* ms_total, float* ms_stream) {
+    PF_REQUIRE(m_sorted >= 0 && n_extra >= 0 && (sorted_map || m_sorted == 0) && (extra || n_extra == 0) && center && n_out && n_sorted_out,
                "bad argument");
     PF_REQUIRE(leaf >= 0.2f, "leaf %g: the streaming map update needs leaf >= 0.2 m (10-bit voxel coordinates in the 200 m crop box)", leaf);
-    PF_REQUIRE(cap_out >= m_sorted + n_extra, "output buffer holds %d points, need up to %d", cap_out, m_sorted + n_extra);
+    PF_REQUIRE(!out || cap_out >= m_sorted + n_extra, "output buffer holds %d points, need up to %d", cap_out, m_sorted + n_extra);
+    PF_REQUIRE(reps >= 1, "reps must be >= 1");
     PF_CUDA(cudaSetDevice(device));
     cudaStream_t stream;
     PF_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
@@ -407,14 +530,17 @@ extern "C" int pf_map_merge(int device, const pf_point* sorted_map, int m_sorted
     Pt *d_buf = nullptr, *d_out = nullptr;
     int* d_counts = nullptr;      // [0] n_sorted, [1] n_app, [2] n_out, [3] n_sorted_out, [4..7] the empty second cloud
     double* d_center = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     int rc = PF_OK;
     auto body = [&]() -> int {
-        PF_CHECK(workspace_create(ws, tot, stream));
-        PF_CHECK(map_merge_scratch_create(sc, capb, 4096));
+        // workspace: sort capacity for the unsorted part, look-back words for the map's merge tiles (1024 points each)
+        PF_CHECK(workspace_create(ws, capb > tot / 4 ? capb : tot / 4, stream));
+        PF_CHECK(map_merge_scratch_create(sc, capb, 4096, tot));
         PF_CUDA(cudaMalloc(&d_buf, sizeof(Pt) * tot));
         PF_CUDA(cudaMalloc(&d_out, sizeof(Pt) * tot));
         PF_CUDA(cudaMalloc(&d_counts, sizeof(int) * 8));
         PF_CUDA(cudaMalloc(&d_center, sizeof(double) * 3));
+        for (int i = 0; i < 4; ++i) PF_CUDA(cudaEventCreate(&ev[i]));
         const int counts[8] = {m_sorted, m_sorted + n_extra, 0, 0, 0, 0, 0, 0};
         PF_CUDA(cudaMemcpyAsync(d_counts, counts, sizeof(counts), cudaMemcpyHostToDevice, stream));
         if (m_sorted) PF_CUDA(cudaMemcpyAsync(d_buf, sorted_map, sizeof(Pt) * m_sorted, cudaMemcpyHostToDevice, stream));
@@ -426,17 +552,31 @@ extern "C" int pf_map_merge(int device, const pf_point* sorted_map, int m_sorted
         P.center = d_center;
         P.k_new = k_new; P.theta_p = theta_p; P.theta_max = theta_max;
         P.s = sc;
-        PF_CHECK(workspace_begin_step(ws));
-        PF_CHECK(map_merge(ws, P, capb, 0, m_sorted, 0));
+        ws.ev_a = ev[2]; ws.ev_b = ev[3];
+        float tot_ms = 0.f, str_ms = 0.f;
+        for (int r = 0; r < reps; ++r) {      // every repetition merges the same input into d_out
+            PF_CUDA(cudaEventRecord(ev[0], stream));
+            PF_CHECK(workspace_begin_step(ws));
+            PF_CHECK(map_merge(ws, P, capb, 0, m_sorted, 0));
+            PF_CUDA(cudaEventRecord(ev[1], stream));
+            PF_CUDA(cudaStreamSynchronize(stream));
+            float a = 0.f, b = 0.f;
+            PF_CUDA(cudaEventElapsedTime(&a, ev[0], ev[1]));
+            PF_CUDA(cudaEventElapsedTime(&b, ev[2], ev[3]));
+            if (r > 0 || reps == 1) { tot_ms += a; str_ms += b; }     // repetition 0 is the warm-up when reps > 1
+        }
+        const int timed = reps > 1 ? reps - 1 : 1;
+        if (ms_total) *ms_total = tot_ms / timed;
+        if (ms_stream) *ms_stream = str_ms / timed;
         int res[4];
         unsigned err = 0;
         PF_CUDA(cudaMemcpyAsync(res, d_counts, sizeof(res), cudaMemcpyDeviceToHost, stream));
-        PF_CUDA(cudaMemcpyAsync(&err, ws.ctrl + kSlotBase + 3 * kSlotWords + 15, sizeof(unsigned), cudaMemcpyDeviceToHost, stream));
+        PF_CUDA(cudaMemcpyAsync(&err, map_merge_error_word(ws), sizeof(unsigned), cudaMemcpyDeviceToHost, stream));
         PF_CUDA(cudaStreamSynchronize(stream));
-        if (err) { set_error("map merge failed (error bits %u: 2 = voxel coordinates out of range, 4 = too many exceptions)", err); return PF_ERR_CAPACITY; }
+        if (err) { set_error("map merge failed (error bits %u: 2 = voxel coordinates out of range, 4 = too many exceptions, 8 / 16 = internal)", err); return PF_ERR_CAPACITY; }
         *n_out = res[2];
         *n_sorted_out = res[3];
-        if (res[2]) PF_CUDA(cudaMemcpy(out, d_out, sizeof(Pt) * res[2], cudaMemcpyDeviceToHost));
+        if (out && res[2]) PF_CUDA(cudaMemcpy(out, d_out, sizeof(Pt) * res[2], cudaMemcpyDeviceToHost));
         return PF_OK;
     };
     rc = body();
@@ -444,6 +584,21 @@ extern "C" int pf_map_merge(int device, const pf_point* sorted_map, int m_sorted
     workspace_destroy(ws);
     map_merge_scratch_destroy(sc);
     cudaFree(d_buf); cudaFree(d_out); cudaFree(d_counts); cudaFree(d_center);
+    for (int i = 0; i < 4; ++i) if (ev[i]) cudaEventDestroy(ev[i]);
     cudaStreamDestroy(stream);
     return rc;
+}
+
+extern "C" int pf_map_merge(int device, const pf_point* sorted_map, int m_sorted, const pf_point* extra, int n_extra, const double center[3],
+                            float leaf, int k_new, float theta_p, int theta_max, pf_point* out, int cap_out, int* n_out, int* n_sorted_out) {
+    PF_REQUIRE(out, "null output");
+    return map_merge_tap(device, sorted_map, m_sorted, extra, n_extra, center, leaf, k_new, theta_p, theta_max, out, cap_out, n_out, n_sorted_out,
+                         1, nullptr, nullptr);
+}
+
+extern "C" int pf_map_merge_timed(int device, const pf_point* sorted_map, int m_sorted, const pf_point* extra, int n_extra,
+                                  const double center[3], float leaf, int k_new, float theta_p, int theta_max, int reps, int* n_out,
+                                  int* n_sorted_out, float* ms_total, float* ms_stream) {
+    return map_merge_tap(device, sorted_map, m_sorted, extra, n_extra, center, leaf, k_new, theta_p, theta_max, nullptr, 0, n_out, n_sorted_out,
+                         reps, ms_total, ms_stream);
 }

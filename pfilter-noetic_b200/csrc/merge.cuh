@@ -20,6 +20,8 @@
 
 namespace pf {
 
+constexpr int kMergeMaxGrid = 8 * kSMs;   // CTAs per cloud of the two streaming passes
+
 struct MapMergeCloud {
     const Pt* buf;           // current map buffer (layout above)
     const int* n_sorted;     // device counts
@@ -31,10 +33,12 @@ struct MapMergeCloud {
 };
 
 struct MapMergeScratch {     // sized by the capacity of B (both clouds together)
-    int* m_ra;    int* m_start;  int* m_len;      // matched heads: map index, first position in sorted B, run length
+    int* m_ra;    Pt* m_pt;      int* m_delta;    // matched voxels: map index, finished point (alpha 0 = not kept), count change
     int* i_ra;    Pt* i_pt;                       // inserted voxels (new, kept): insertion index, finished point
     Pt* exc;      int exc_cap;                    // [2][exc_cap] exceptions of this update
     int cap;                                      // entries per list and cloud half: cloud c uses [c * cap, (c + 1) * cap)
+    int* tile_m;  int* tile_i;   int tile_cap;    // [2][tile_cap] first matched head / insert of every 1024-point map tile
+    int* tile_agg; int* cta_sum;                  // [2][tile_cap] points a tile emits; [2][kMergeMaxGrid] per CTA of the count pass
 };
 
 struct MapMergeParams {
@@ -49,7 +53,8 @@ struct MapMergeParams {
 int map_merge(Workspace& ws, const MapMergeParams& P, int capB0, int capB1, int capA0, int capA1);
 // device word holding the error bits of the last map_merge of `ws` (2 = voxel coordinates out of range, 4 = exceptions overflowed)
 inline const unsigned* map_merge_error_word(const Workspace& ws) { return ws.ctrl + kSlotBase + 3 * kSlotWords + 15; }
-int map_merge_scratch_create(MapMergeScratch& s, int cap_b, int exc_cap);
+// cap_b: capacity of the unsorted part per cloud; cap_a: capacity of the sorted part (map buffer) per cloud
+int map_merge_scratch_create(MapMergeScratch& s, int cap_b, int exc_cap, int cap_a);
 void map_merge_scratch_destroy(MapMergeScratch& s);
 
 }  // namespace pf

@@ -124,7 +124,7 @@ __global__ void __launch_bounds__(256) k_init_map(InitParams I) {
 __global__ void k_check_map_cap(const int* n_map0, const int* n_map1, int cap, OdomShared* sh, long long frame, const unsigned* merge_err) {
     if (threadIdx.x != 0) return;
     if (*n_map0 > cap || *n_map1 > cap) atomicOr(&sh->err, 1);
-    if (*merge_err) atomicOr(&sh->err, (int)(*merge_err & 6u));
+    if (*merge_err) atomicOr(&sh->err, (int)(*merge_err & 14u));
     sh->n_map[0] = *n_map0;
     sh->n_map[1] = *n_map1;
     sh->frame = frame;
@@ -215,7 +215,7 @@ int odom_alloc(pf_odom* h) {
         PF_CUDA(cudaMemset(h->d_flag[k], 0, fcap));
         PF_CUDA(cudaMalloc(&h->d_g8[k], sizeof(double) * 8 * fcap));
     }
-    PF_CHECK(map_merge_scratch_create(h->msc, 2 * fcap + kMergeExcCap, kMergeExcCap));
+    PF_CHECK(map_merge_scratch_create(h->msc, 2 * fcap + kMergeExcCap, kMergeExcCap, bufcap));
     PF_CUDA(cudaMalloc(&h->d_state, sizeof(LmState)));
     PF_CUDA(cudaMemset(h->d_state, 0, sizeof(LmState)));
     PF_CUDA(cudaMalloc(&h->d_iter_poses, sizeof(double) * 16 * 7));
@@ -391,7 +391,7 @@ int finish_frame(pf_odom* h, double pose_out[7]) {
         set_error("local map exceeded max_map_points = %d", h->mcap);
         return PF_ERR_CAPACITY;
     }
-    if (h->h_sh->err & 6) {
+    if (h->h_sh->err & 14) {
         set_error("map update failed (bits %d: 2 = map_resolution below 0.2 m, 4 = more than %d centroids left their voxel)", h->h_sh->err & 6, kMergeExcCap);
         return PF_ERR_CAPACITY;
     }

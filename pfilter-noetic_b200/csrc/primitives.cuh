@@ -31,6 +31,7 @@ struct Workspace {
     unsigned int* ctrl = nullptr;             // [kCtrlWords]
     uint64_t launches = 0;
     int coop_blocks = 0;                      // grid of the cooperative sort (SMs x resident CTAs), set on first use
+    cudaEvent_t ev_a = nullptr, ev_b = nullptr;   // optional (timed stage taps): recorded around the dominant kernel of a pipeline
 };
 
 int workspace_create(Workspace& ws, int cap, cudaStream_t stream);
@@ -68,47 +69,48 @@ __device__ __forceinline__ int block_scan_excl_256(int v, int* tmp, int* total) 
     return woff + x - v;
 }
 
-// Chained scan across the tiles of one kernel (decoupled look-back, single pass).
+// Chained scan across the tiles of one kernel (decoupled look-back, single pass), for 256-thread CTAs.
 // status word: epoch[63:34] | flag[33:32] | value[31:0]; flag 1 = tile aggregate, 2 = inclusive prefix.
-// Must be called by all threads of the CTA; `tile` must come from an atomic ticket so that every predecessor
-// tile is already running.  Returns the exclusive prefix of this tile's aggregate.
+// The status word carries its whole message (no other memory is published through it), so relaxed accesses suffice.
+// The look-back is done by the WHOLE CTA: thread j inspects tile (look - j), so one round covers 256 predecessors.  With
+// hundreds of tiles in flight at once the nearest finished prefix is typically several hundred tiles back; a 32-wide window
+// made every tile pay ~20 dependent L2 round trips (measured: 65% of all warp samples stalled on the barrier behind it).
+// Must be called by all 256 threads of the CTA; `tile` must come from an atomic ticket so that every predecessor tile is
+// already running.  `sm`: kScanSmemWords words of shared memory.  Returns the exclusive prefix of this tile's aggregate.
+constexpr int kScanSmemWords = 20;
 __device__ __forceinline__ unsigned chained_scan_exclusive(unsigned long long* status, unsigned epoch, int tile, unsigned aggregate,
-                                                           unsigned* smem_bcast) {
+                                                           unsigned* sm) {
     const unsigned long long ep = ((unsigned long long)(epoch & 0x3fffffffu)) << 34;
-    if (threadIdx.x < 32) {
-        const int lane = threadIdx.x;
-        unsigned excl = 0;
-        if (tile == 0) {
-            if (lane == 0) st_release_u64(status, ep | (2ull << 32) | aggregate);
-        } else {
-            if (lane == 0) st_release_u64(status + tile, ep | (1ull << 32) | aggregate);
-            int look = tile - 1;
-            while (true) {
-                const int t = look - lane;
-                unsigned long long v = 0;
-                unsigned flag = 2, val = 0;
-                if (t >= 0) {
-                    do { v = ld_acquire_u64(status + t); } while ((v >> 34) != (ep >> 34) || ((v >> 32) & 3ull) == 0);
-                    flag = (unsigned)((v >> 32) & 3ull);
-                    val = (unsigned)v;
-                } else {
-                    val = 0;   // virtual tiles before tile 0: inclusive prefix 0
-                }
-                const unsigned pmask = __ballot_sync(0xffffffffu, flag == 2);
-                const int first_p = __ffs(pmask) - 1;   // nearest predecessor (smallest lane) holding an inclusive prefix
-                unsigned contrib = (pmask == 0 || lane <= first_p) ? val : 0;
-                excl += __reduce_add_sync(0xffffffffu, contrib);
-                if (pmask != 0) break;
-                look -= 32;
-            }
-            if (lane == 0) st_release_u64(status + tile, ep | (2ull << 32) | (excl + aggregate));
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    if (tid == 0) st_relaxed_u64(status + tile, ep | ((tile == 0 ? 2ull : 1ull) << 32) | aggregate);
+    unsigned excl = 0;
+    int look = tile - 1;
+    while (look >= 0) {       // uniform over the CTA
+        const int t = look - tid;
+        unsigned flag = 2, val = 0;          // virtual tiles before tile 0: inclusive prefix 0
+        if (t >= 0) {
+            unsigned long long v;
+            do { v = ld_relaxed_u64(status + t); } while ((v >> 34) != (ep >> 34) || ((v >> 32) & 3ull) == 0);
+            flag = (unsigned)((v >> 32) & 3ull);
+            val = (unsigned)v;
         }
-        if (lane == 0) *smem_bcast = excl;
+        const unsigned pmask = __ballot_sync(0xffffffffu, flag == 2);
+        const int first_p = __ffs(pmask) - 1;          // nearest predecessor of this warp's window holding an inclusive prefix
+        const unsigned contrib = (pmask == 0 || lane <= first_p) ? val : 0;
+        const unsigned wsum = __reduce_add_sync(0xffffffffu, contrib);
+        if (lane == 0) { sm[w] = wsum; sm[8 + w] = pmask != 0 ? 1u : 0u; }
+        __syncthreads();
+        bool found = false;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            if (!found) { excl += sm[k]; found = sm[8 + k] != 0; }
+        }
+        __syncthreads();
+        if (found) break;
+        look -= 256;
     }
-    __syncthreads();
-    unsigned r = *smem_bcast;
-    __syncthreads();
-    return r;
+    if (tid == 0 && tile != 0) st_relaxed_u64(status + tile, ep | (2ull << 32) | (excl + aggregate));
+    return excl;
 }
 #endif
 

@@ -147,7 +147,7 @@ __global__ void __launch_bounds__(256) k_vox_reduce(VoxParams P, const uint32_t*
     const VoxCloud& c = P.c[cloud];
     __shared__ int s_tile;
     __shared__ int s_tmp[9];
-    __shared__ unsigned s_bcast;
+    __shared__ unsigned s_look[kScanSmemWords];
     const int* st = reinterpret_cast<const int*>(P.state);
     const int start = cloud == 0 ? 0 : st[12];
     const int len = st[12 + cloud];
@@ -215,7 +215,7 @@ __global__ void __launch_bounds__(256) k_vox_reduce(VoxParams P, const uint32_t*
     int total;
     const int local = block_scan_excl_256(keep ? 1 : 0, s_tmp, &total);
     const unsigned tag = (ctrl[0] << 3) | (unsigned)site;
-    const unsigned excl = chained_scan_exclusive(status + (size_t)cloud * status_stride, tag, tile, (unsigned)total, &s_bcast);
+    const unsigned excl = chained_scan_exclusive(status + (size_t)cloud * status_stride, tag, tile, (unsigned)total, s_look);
     if (keep) c.out[excl + local] = o;
     if (tile == (len - 1) / 256 && threadIdx.x == 0) *c.n_out = (int)excl + total;
     }
