@@ -135,6 +135,7 @@ __global__ void __launch_bounds__(kSortThreads) k_sort_coop(uint32_t* keys0, uin
                                                             uint32_t* totals, int nb_cap) {
     cooperative_groups::grid_group grid = cooperative_groups::this_grid();
     const int n = *n_dev;
+    if (n <= kSmallSort) return;      // sorted by k_sort_small (uniform over the grid: no barrier is skipped by a subset)
     const int ntiles = (n + kSortTile - 1) / kSortTile;
     const int fused = ntiles <= 96 ? 1 : 0;
     for (int p = 0; p < passes; ++p) {
@@ -151,6 +152,79 @@ __global__ void __launch_bounds__(kSortThreads) k_sort_coop(uint32_t* keys0, uin
         }
         d_sort_scatter(kin, (p == 0 && vals_iota) ? nullptr : vin, kout, vout, n, shift, hist, totals, nb_cap, fused);
         if (p + 1 < passes) grid.sync();
+    }
+}
+
+// Small inputs (n <= kSmallSort): the whole sort in ONE CTA of 1024 threads, passes separated by __syncthreads only.  The frame
+// loop sorts a few thousand new map points every frame; four cooperative passes with two grid barriers each cost ~50 us for
+// them, this kernel ~10 us.  Warp w owns the contiguous keys [256 w, 256 w + 256) and ranks them in 8 ordered rounds of 32
+// (warp-private digit counters keep the sort stable).
+__global__ void __launch_bounds__(1024) k_sort_small(uint32_t* keys0, uint32_t* vals0, uint32_t* keys1, uint32_t* vals1,
+                                                     const int* __restrict__ n_dev, int passes, int vals_iota) {
+    const int n = *n_dev;
+    if (n > kSmallSort || n <= 0) return;      // large inputs are sorted by k_sort_coop
+    __shared__ unsigned wc[32][kRadix];
+    __shared__ unsigned dbase[kRadix];
+    __shared__ unsigned wtot[8];
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    for (int p = 0; p < passes; ++p) {
+        const uint32_t* kin = (p & 1) ? keys1 : keys0;
+        const uint32_t* vin = (p & 1) ? vals1 : vals0;
+        uint32_t* kout = (p & 1) ? keys0 : keys1;
+        uint32_t* vout = (p & 1) ? vals0 : vals1;
+        const int shift = p * kRadixBits;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) wc[(tid >> 8) + 4 * k][tid & 255] = 0;
+        __syncthreads();
+        unsigned key[8], val[8], rank[8];
+        const int wstart = w * 256;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int i = wstart + k * 32 + lane;
+            const bool ok = i < n;
+            key[k] = ok ? kin[i] : 0xffffffffu;
+            val[k] = ok ? ((p == 0 && vals_iota) ? (unsigned)i : vin[i]) : 0u;
+            const unsigned d = (key[k] >> shift) & (kRadix - 1);
+            const unsigned act = __ballot_sync(0xffffffffu, ok);
+            rank[k] = 0;
+            if (ok) {
+                const unsigned m = __match_any_sync(act, d);
+                const unsigned before = wc[w][d];
+                rank[k] = before + __popc(m & lanemask_lt());
+                __syncwarp(act);
+                if (lane == __ffs(m) - 1) wc[w][d] = before + __popc(m);
+            }
+            __syncwarp();
+        }
+        __syncthreads();
+        if (tid < kRadix) {       // digit tid: exclusive prefix over the 32 warps, then over the digits
+            unsigned run = 0;
+#pragma unroll 8
+            for (int k = 0; k < 32; ++k) { const unsigned c = wc[k][tid]; wc[k][tid] = run; run += c; }
+            unsigned x = run;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const unsigned y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+            if (lane == 31) wtot[w] = x;
+            dbase[tid] = x - run;     // exclusive inside the warp of 32 digits
+        }
+        __syncthreads();
+        if (tid < kRadix) {
+            unsigned off = 0;
+            for (int k = 0; k < w; ++k) off += wtot[k];
+            dbase[tid] += off;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int i = wstart + k * 32 + lane;
+            if (i < n) {
+                const unsigned d = (key[k] >> shift) & (kRadix - 1);
+                const unsigned pos = dbase[d] + wc[w][d] + rank[k];
+                kout[pos] = key[k];
+                vout[pos] = val[k];
+            }
+        }
+        __syncthreads();      // global writes of this CTA are visible to it after the barrier
     }
 }
 
@@ -205,6 +279,8 @@ int radix_sort(Workspace& ws, const int* n_dev, int n_cap, int passes, bool vals
     }
     if (nb > ws.coop_blocks) nb = ws.coop_blocks;
     int iota = vals_iota ? 1 : 0, nb_cap = ws.nb_cap;
+    k_sort_small<<<1, 1024, 0, ws.stream>>>(ws.keys[0], ws.vals[0], ws.keys[1], ws.vals[1], n_dev, passes, iota);
+    ws.launches += 1;
     void* args[] = {&ws.keys[0], &ws.vals[0], &ws.keys[1], &ws.vals[1], (void*)&n_dev, &passes, &iota, &ws.hist, &ws.totals, &nb_cap};
     PF_CUDA(cudaLaunchCooperativeKernel((const void*)k_sort_coop, dim3(nb), dim3(kSortThreads), args, 0, ws.stream));
     ws.launches += 1;

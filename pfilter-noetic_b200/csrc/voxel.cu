@@ -141,6 +141,11 @@ __global__ void __launch_bounds__(256) k_vox_keys(VoxParams P, uint32_t* __restr
     }
 }
 
+// One CTA per tile of 256 sorted entries (persistent, tiles by ticket).  The runs of equal keys that START in the tile are
+// its voxels; a warp takes one voxel at a time, gathers the run 32 points per step (the gather of the next step is in
+// flight while the current one is summed) and adds them up in sorted order = ascending input index -- the ordered float sum
+// is inherently sequential, but its latency is one gather per 32 points (near-range ground voxels hold > 250 points of a
+// 64-ring scan).  Finished voxels are compacted in key order by a chained scan; output is written once, coalesced.
 __global__ void __launch_bounds__(256) k_vox_reduce(VoxParams P, const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals,
                                                     unsigned long long* status, int status_stride, unsigned* ctrl, int ticket_word, int site) {
     const int cloud = blockIdx.y;
@@ -148,76 +153,99 @@ __global__ void __launch_bounds__(256) k_vox_reduce(VoxParams P, const uint32_t*
     __shared__ int s_tile;
     __shared__ int s_tmp[9];
     __shared__ unsigned s_look[kScanSmemWords];
+    __shared__ int s_head[256];          // sorted position of the tile's k-th voxel
+    __shared__ Pt s_out[256];            // its finished point
+    __shared__ uint8_t s_keep[256];
     const int* st = reinterpret_cast<const int*>(P.state);
     const int start = cloud == 0 ? 0 : st[12];
     const int len = st[12 + cloud];
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const bool pcl = P.mode == VOX_PCL;
     while (true) {   // persistent CTAs pull tiles by ticket until the cloud is exhausted
-    __syncthreads();
-    if (threadIdx.x == 0) s_tile = (int)atomicAdd(&ctrl[ticket_word + cloud], 1u);
-    __syncthreads();
-    const int tile = s_tile;
-    if (len == 0) {
-        if (tile == 0 && threadIdx.x == 0) *c.n_out = 0;
-        return;
-    }
-    if (tile * 256 >= len) return;
-    const int n0 = P.c[0].n_in ? *P.c[0].n_in : 0;
-    const int ibase = cloud == 0 ? 0 : n0;
-    const int end = start + len;
-    const int p = start + tile * 256 + threadIdx.x;
-    bool keep = false;
-    Pt o{0.f, 0.f, 0.f, 0u};
-    if (p < end) {
-        const unsigned key = keys[p];
-        const bool head = (p == start) || (keys[p - 1] != key);
-        if (head) {
-            // segment end first (contiguous key reads), then the ordered sum with 8 independent gathers in flight
-            int e = p + 1;
-            while (e < end && keys[e] == key) ++e;
-            float sx = 0.f, sy = 0.f, sz = 0.f;
-            float sr = 0.f, sg = 0.f, sb = 0.f, sa = 0.f;
-            int rmax = -1, gmax = -1;
-            const bool pcl = P.mode == VOX_PCL;
-            for (int q = p; q < e; q += 8) {
-                Pt v[8];
-#pragma unroll
-                for (int u = 0; u < 8; ++u)
-                    if (q + u < e) v[u] = load_pt(c, (int)vals[q + u] - ibase);
-#pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    if (q + u < e) {
-                        sx = __fadd_rn(sx, v[u].x); sy = __fadd_rn(sy, v[u].y); sz = __fadd_rn(sz, v[u].z);
-                        if (pcl) {
-                            sr += (float)(v[u].rgba & 0xff); sg += (float)((v[u].rgba >> 8) & 0xff);
-                            sb += (float)((v[u].rgba >> 16) & 0xff); sa += (float)(v[u].rgba >> 24);
-                        } else {
-                            rmax = max(rmax, (int)pt_r(v[u].rgba));
-                            gmax = max(gmax, (int)pt_g(v[u].rgba));
-                        }
-                    }
+        __syncthreads();
+        if (tid == 0) s_tile = (int)atomicAdd(&ctrl[ticket_word + cloud], 1u);
+        __syncthreads();
+        const int tile = s_tile;
+        if (len == 0) {
+            if (tile == 0 && tid == 0) *c.n_out = 0;
+            return;
+        }
+        if (tile * 256 >= len) return;
+        const int n0 = P.c[0].n_in ? *P.c[0].n_in : 0;
+        const int ibase = cloud == 0 ? 0 : n0;
+        const int end = start + len;
+        const int tile_end = min(end, start + (tile + 1) * 256);
+        const int p = start + tile * 256 + tid;
+        const bool head = p < end && (p == start || keys[p - 1] != keys[p]);
+        int nheads;
+        const int hidx = block_scan_excl_256(head ? 1 : 0, s_tmp, &nheads);
+        if (head) s_head[hidx] = p;
+        __syncthreads();
+        for (int hh = w; hh < nheads; hh += 8) {
+            const int ps = s_head[hh];
+            int e;
+            if (hh + 1 < nheads) {
+                e = s_head[hh + 1];
+            } else {     // the last voxel of the tile may run on into the following tiles
+                const unsigned key = keys[ps];
+                e = tile_end;
+                while (e < end) {
+                    const bool same = e + lane < end && keys[e + lane] == key;
+                    const unsigned m = __ballot_sync(0xffffffffu, same);
+                    if (m != 0xffffffffu) { e += __ffs(~m) - 1; break; }
+                    e += 32;
                 }
             }
-            const float fn = (float)(e - p);
-            o.x = __fdiv_rn(sx, fn); o.y = __fdiv_rn(sy, fn); o.z = __fdiv_rn(sz, fn);
-            if (pcl) {
-                o.rgba = pack_rgba((unsigned)__fdiv_rn(sr, fn) & 0xff, (unsigned)__fdiv_rn(sg, fn) & 0xff,
-                                   (unsigned)__fdiv_rn(sb, fn) & 0xff, (unsigned)__fdiv_rn(sa, fn) & 0xff);
-                keep = true;
-            } else {
-                // extractstablepoint (:12-14): drop if g < r*theta_p && r > k_new && g < theta_max + 1
-                const bool drop = ((float)gmax < __fmul_rn((float)rmax, P.theta_p)) && (rmax > P.k_new) && (gmax < P.theta_max + 1);
-                keep = !drop;
-                const int r2 = rmax > 250 ? 255 : rmax + 2;   // :634-646
-                o.rgba = pack_rgba((unsigned)r2, (unsigned)gmax, 0u, 255u);
+            float sx = 0.f, sy = 0.f, sz = 0.f, sr = 0.f, sg = 0.f, sb = 0.f, sa = 0.f;
+            int rmax = -1, gmax = -1;
+            Pt cur{0.f, 0.f, 0.f, 0u};
+            if (ps + lane < e) cur = load_pt(c, (int)vals[ps + lane] - ibase);
+            for (int q = ps; q < e; q += 32) {
+                Pt nxt{0.f, 0.f, 0.f, 0u};
+                if (q + 32 + lane < e) nxt = load_pt(c, (int)vals[q + 32 + lane] - ibase);
+                const int cnt = min(32, e - q);
+                for (int j = 0; j < cnt; ++j) {
+                    const float x = __shfl_sync(0xffffffffu, cur.x, j), y = __shfl_sync(0xffffffffu, cur.y, j), z = __shfl_sync(0xffffffffu, cur.z, j);
+                    const unsigned rgba = __shfl_sync(0xffffffffu, cur.rgba, j);
+                    sx = __fadd_rn(sx, x); sy = __fadd_rn(sy, y); sz = __fadd_rn(sz, z);
+                    if (pcl) {
+                        sr += (float)(rgba & 0xff); sg += (float)((rgba >> 8) & 0xff);
+                        sb += (float)((rgba >> 16) & 0xff); sa += (float)(rgba >> 24);
+                    } else {
+                        rmax = max(rmax, (int)pt_r(rgba));
+                        gmax = max(gmax, (int)pt_g(rgba));
+                    }
+                }
+                cur = nxt;
+            }
+            if (lane == 0) {
+                const float fn = (float)(e - ps);
+                Pt o;
+                bool keep;
+                o.x = __fdiv_rn(sx, fn); o.y = __fdiv_rn(sy, fn); o.z = __fdiv_rn(sz, fn);
+                if (pcl) {
+                    o.rgba = pack_rgba((unsigned)__fdiv_rn(sr, fn) & 0xff, (unsigned)__fdiv_rn(sg, fn) & 0xff,
+                                       (unsigned)__fdiv_rn(sb, fn) & 0xff, (unsigned)__fdiv_rn(sa, fn) & 0xff);
+                    keep = true;
+                } else {
+                    // extractstablepoint (:12-14): drop if g < r*theta_p && r > k_new && g < theta_max + 1
+                    const bool drop = ((float)gmax < __fmul_rn((float)rmax, P.theta_p)) && (rmax > P.k_new) && (gmax < P.theta_max + 1);
+                    keep = !drop;
+                    const int r2 = rmax > 250 ? 255 : rmax + 2;   // :634-646
+                    o.rgba = pack_rgba((unsigned)r2, (unsigned)gmax, 0u, 255u);
+                }
+                s_out[hh] = o;
+                s_keep[hh] = keep ? 1 : 0;
             }
         }
-    }
-    int total;
-    const int local = block_scan_excl_256(keep ? 1 : 0, s_tmp, &total);
-    const unsigned tag = (ctrl[0] << 3) | (unsigned)site;
-    const unsigned excl = chained_scan_exclusive(status + (size_t)cloud * status_stride, tag, tile, (unsigned)total, s_look);
-    if (keep) c.out[excl + local] = o;
-    if (tile == (len - 1) / 256 && threadIdx.x == 0) *c.n_out = (int)excl + total;
+        __syncthreads();
+        const bool keep = tid < nheads && s_keep[tid];
+        int total;
+        const int local = block_scan_excl_256(keep ? 1 : 0, s_tmp, &total);
+        const unsigned tag = (ctrl[0] << 3) | (unsigned)site;
+        const unsigned excl = chained_scan_exclusive(status + (size_t)cloud * status_stride, tag, tile, (unsigned)total, s_look);
+        if (keep) c.out[excl + local] = s_out[tid];
+        if (tile == (len - 1) / 256 && tid == 0) *c.n_out = (int)excl + total;
     }
 }
 
