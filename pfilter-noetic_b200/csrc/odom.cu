@@ -347,7 +347,7 @@ int enqueue_update(pf_odom* h, const float4* const feat[2], const int* const n_f
     for (int it = 0; it < passes; ++it) {
         PF_CHECK(associate_pass(h->stream, A, ub_e, ub_s, &ws.launches));
         if (it == passes - 1) mark(3);
-        PF_CHECK(lm_solve(h->stream, L, nullptr, it == 0, &ws.launches));
+        PF_CHECK(lm_solve(h->stream, L, nullptr, it == 0, &ws.launches, ub_e, ub_s));
     }
     mark(4);
     // append + map maintenance

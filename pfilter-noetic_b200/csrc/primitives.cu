@@ -179,11 +179,15 @@ __global__ void __launch_bounds__(1024) k_sort_small(uint32_t* keys0, uint32_t* 
         unsigned key[8], val[8], rank[8];
         const int wstart = w * 256;
 #pragma unroll
+        for (int k = 0; k < 8; ++k) {      // all loads first: one memory latency per pass, not eight
+            const int i = wstart + k * 32 + lane;
+            key[k] = i < n ? kin[i] : 0xffffffffu;
+            val[k] = i < n ? ((p == 0 && vals_iota) ? (unsigned)i : vin[i]) : 0u;
+        }
+#pragma unroll
         for (int k = 0; k < 8; ++k) {
             const int i = wstart + k * 32 + lane;
             const bool ok = i < n;
-            key[k] = ok ? kin[i] : 0xffffffffu;
-            val[k] = ok ? ((p == 0 && vals_iota) ? (unsigned)i : vin[i]) : 0u;
             const unsigned d = (key[k] >> shift) & (kRadix - 1);
             const unsigned act = __ballot_sync(0xffffffffu, ok);
             rank[k] = 0;

@@ -20,37 +20,42 @@ namespace pf {
 
 constexpr int kAcc = 29;   // 21 H + 6 g + cost + count
 
-__device__ __forceinline__ void eval_one(int kind, D3 p, const double* ge, const double* pose, double acc[kAcc]) {
-    const D3 lp = pose_apply(pose, p);
-    double r, J[6];
+// One residual block at the pose (R, t).  Edge: with u = (a - b) / |a - b| the reference's nu = (lp-a) x (lp-b) equals
+// |a-b| (lp-a) x u, so r = |(lp-a) x u| and J = w^T [u]x [ -[lp]x  I ] with w = -nu/|nu|: the same numbers as
+// src/lidarOptimization.cpp:18-41 with one square root and two reciprocals on the critical path instead of eleven fp64
+// divisions / roots.  Huber: sqrt(s) = |r|.
+__device__ __forceinline__ void eval_one(int kind, D3 p, const double* ge, const double* Rm, const double* tv, double acc[kAcc]) {
+    const D3 lp = d3(Rm[0] * p.x + Rm[1] * p.y + Rm[2] * p.z + tv[0], Rm[3] * p.x + Rm[4] * p.y + Rm[5] * p.z + tv[1],
+                     Rm[6] * p.x + Rm[7] * p.y + Rm[8] * p.z + tv[2]);
+    double r, ar, J[6];
     if (kind == 0) {
         const D3 a = d3(ge[0], ge[1], ge[2]), b = d3(ge[3], ge[4], ge[5]);
-        const D3 nu = cross3(lp - a, lp - b);
         const D3 de = a - b;
-        const double de_norm = norm3(de), nu_norm = norm3(nu);
-        r = nu_norm / de_norm;
-        const D3 w = (-1.0 / nu_norm) * nu;
-        const D3 m = cross3(w, de);          // w^T [de]x
+        const double inv_de = 1.0 / norm3(de);
+        const D3 u = inv_de * de;
+        const D3 nu = cross3(lp - a, u);
+        r = norm3(nu);
+        ar = r;
+        const D3 w = (-1.0 / r) * nu;
+        const D3 m = cross3(w, u);           // w^T [u]x
         const D3 jr = cross3(lp, m);         // m^T (-[lp]x)
-        J[0] = jr.x / de_norm; J[1] = jr.y / de_norm; J[2] = jr.z / de_norm;
-        J[3] = m.x / de_norm; J[4] = m.y / de_norm; J[5] = m.z / de_norm;
+        J[0] = jr.x; J[1] = jr.y; J[2] = jr.z; J[3] = m.x; J[4] = m.y; J[5] = m.z;
     } else {
         const D3 n = d3(ge[0], ge[1], ge[2]);
         r = dot3(n, lp) + ge[3];
+        ar = fabs(r);
         const D3 jr = cross3(lp, n);
         J[0] = jr.x; J[1] = jr.y; J[2] = jr.z; J[3] = n.x; J[4] = n.y; J[5] = n.z;
     }
     // HuberLoss(0.1): rho(s), s = r^2
     const double s = r * r;
-    double rho0, rho1;
+    double rho0, sc;
     if (s > 0.01) {
-        const double rs = sqrt(s);
-        rho0 = 0.2 * rs - 0.01;
-        rho1 = fmax(2.2250738585072014e-308, 0.1 / rs);
+        rho0 = 0.2 * ar - 0.01;
+        sc = sqrt(fmax(2.2250738585072014e-308, 0.1 / ar));
     } else {
-        rho0 = s; rho1 = 1.0;
+        rho0 = s; sc = 1.0;
     }
-    const double sc = sqrt(rho1);
     r *= sc;
 #pragma unroll
     for (int k = 0; k < 6; ++k) J[k] *= sc;
@@ -87,16 +92,16 @@ __device__ double gradient_max_norm(const double* x, const double* g) {
     return m;
 }
 
-__device__ void lm_finish(const LmParams& P, LmState* S) {
+__device__ void lm_finish(const LmParams& P, LmState* S, bool writer = true) {
     S->phase = 2;
-    if (P.iter_poses && S->pass < 16)
+    if (writer && P.iter_poses && S->pass < 16)
         for (int k = 0; k < 7; ++k) P.iter_poses[7 * S->pass + k] = S->x[k];
 }
 
 // Compute the next trust-region step from (H, g) at x; invalid steps shrink the radius without an evaluation.
-__device__ void lm_propose(const LmParams& P, LmState* S) {
+__device__ void lm_propose(const LmParams& P, LmState* S, bool writer) {
     while (true) {
-        if (S->iter >= 4) { lm_finish(P, S); return; }               // max_num_iterations = 4 (:265)
+        if (S->iter >= 4) { lm_finish(P, S, writer); return; }               // max_num_iterations = 4 (:265)
         S->iter += 1;
         double Hs[21], gs[6], sc[6];
 #pragma unroll
@@ -147,7 +152,7 @@ __device__ void lm_propose(const LmParams& P, LmState* S) {
         if (!ok || !(mcc > 0)) {                                      // invalid step == rejected with zero quality
             S->radius /= S->decrease;
             S->decrease *= 2.0;
-            if (S->radius < 1e-32) { lm_finish(P, S); return; }
+            if (S->radius < 1e-32) { lm_finish(P, S, writer); return; }
             continue;
         }
         S->model_cost_change = mcc;
@@ -159,32 +164,32 @@ __device__ void lm_propose(const LmParams& P, LmState* S) {
     }
 }
 
-__device__ __noinline__ void lm_advance(const LmParams& P, LmState* S, const double* sum) {
+__device__ __noinline__ void lm_advance(const LmParams& P, LmState* S, const double* sum, bool writer) {
     for (int k = 0; k < 21; ++k) S->last_H[k] = sum[k];
     for (int k = 0; k < 6; ++k) S->last_g[k] = sum[21 + k];
     S->last_cost = sum[27];
     S->n_res = (int)sum[28];
     if (P.eval_only) { S->phase = 2; return; }
     if (S->phase == 0) {
-        if (S->n_res == 0) { lm_finish(P, S); return; }               // no residual blocks: parameters untouched
+        if (S->n_res == 0) { lm_finish(P, S, writer); return; }               // no residual blocks: parameters untouched
         for (int k = 0; k < 21; ++k) S->H[k] = sum[k];
         for (int k = 0; k < 6; ++k) S->g[k] = sum[21 + k];
         S->cost = sum[27];
         const int dpos[6] = {0, 6, 11, 15, 18, 20};
         for (int a = 0; a < 6; ++a) S->scale[a] = 1.0 / (1.0 + sqrt(S->H[dpos[a]]));   // jacobi_scaling
-        if (gradient_max_norm(S->x, S->g) <= 1e-10) { lm_finish(P, S); return; }
+        if (gradient_max_norm(S->x, S->g) <= 1e-10) { lm_finish(P, S, writer); return; }
         S->radius = 1e4; S->decrease = 2.0; S->reuse_diag = 0; S->iter = 0;
         S->x_norm = vec_norm7(S->x);
-        lm_propose(P, S);
+        lm_propose(P, S, writer);
         return;
     }
     // phase 1: the candidate xc has been evaluated
     const double cand = sum[27];
     double sn = 0;
     for (int k = 0; k < 7; ++k) sn += (S->x[k] - S->xc[k]) * (S->x[k] - S->xc[k]);
-    if (sqrt(sn) <= 1e-8 * (S->x_norm + 1e-8)) { lm_finish(P, S); return; }            // parameter_tolerance
+    if (sqrt(sn) <= 1e-8 * (S->x_norm + 1e-8)) { lm_finish(P, S, writer); return; }            // parameter_tolerance
     const double cost_change = S->cost - cand;
-    if (fabs(cost_change) <= 1e-6 * S->cost) { lm_finish(P, S); return; }               // function_tolerance
+    if (fabs(cost_change) <= 1e-6 * S->cost) { lm_finish(P, S, writer); return; }               // function_tolerance
     const double rel = cost_change / S->model_cost_change;
     if (rel > 1e-3) {                                                                   // min_relative_decrease
         for (int k = 0; k < 7; ++k) S->x[k] = S->xc[k];
@@ -196,37 +201,43 @@ __device__ __noinline__ void lm_advance(const LmParams& P, LmState* S, const dou
         S->radius = fmin(1e16, S->radius / fmax(1.0 / 3.0, 1.0 - q * q * q));
         S->decrease = 2.0;
         S->reuse_diag = 0;
-        if (gradient_max_norm(S->x, S->g) <= 1e-10) { lm_finish(P, S); return; }
+        if (gradient_max_norm(S->x, S->g) <= 1e-10) { lm_finish(P, S, writer); return; }
     } else {
         S->radius /= S->decrease;
         S->decrease *= 2.0;
     }
-    if (S->radius < 1e-32) { lm_finish(P, S); return; }
-    lm_propose(P, S);
+    if (S->radius < 1e-32) { lm_finish(P, S, writer); return; }
+    lm_propose(P, S, writer);
 }
 
-// One launch = one complete solve (ceres::Solve with max_num_iterations = 4): a cluster of kLmCluster CTAs evaluates the
-// residual blocks (one grid-stride sweep per evaluation), reduces the 29 sums deterministically (warp shuffles -> shared
-// memory -> rank 0 reads the CTA partials of its peers through distributed shared memory, fixed order) and thread 0 of
-// rank 0 runs the trust-region state machine on a shared-memory copy of the state; the next candidate pose travels back to
-// the peers through the same distributed shared memory.  Two cluster barriers per evaluation, nothing returns to the host.
-__global__ void __cluster_dims__(kLmCluster, 1, 1) __launch_bounds__(kLmThreads) k_lm_solve(LmParams P, const double* pose_src, int first_pass) {
+// One launch = one complete solve (ceres::Solve with max_num_iterations = 4) by a cluster of kLmCluster CTAs.
+//   * CTA r owns the r-th slice of both query clouds and compacts the indices of its residual blocks (flag == 2) into shared
+//     memory once, in query order, so every evaluation is a dense loop over them.
+//   * One evaluation = every thread sums its blocks, warp shuffle tree, shared memory, ONE cluster barrier; then every CTA
+//     adds up the partials of all CTAs in the same fixed order through distributed shared memory (deterministic, identical
+//     in every CTA) and runs the trust-region state machine on its own copy of the state -- the next candidate pose never
+//     has to travel, so there is one cluster barrier per evaluation (the partials are double buffered by round parity).
+// Nothing returns to the host; rank 0 writes the state back at the end.
+__global__ void __cluster_dims__(kLmCluster, 1, 1) __launch_bounds__(kLmThreads) k_lm_solve(LmParams P, const double* pose_src, int first_pass,
+                                                                                                int list_cap) {
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
     const unsigned rank = cluster.block_rank();
     constexpr int NW = kLmThreads / 32;
+    extern __shared__ int s_list[];          // [list_cap] compacted residual blocks of this CTA: kind << 30 | query index
     __shared__ double s_red[NW][kAcc];
     __shared__ int s_cnt[NW];
-    __shared__ double s_part[32];          // this CTA's partial sums ([31] = edge count)
-    __shared__ double s_sum[32];           // rank 0: cluster totals
-    __shared__ LmState s_state;            // rank 0: the solver state
-    __shared__ double s_pose[8];           // pose to evaluate at; [7] = phase (as double) -- peers read rank 0's copy
+    __shared__ double s_part[2][32];       // this CTA's partial sums, by round parity ([31] = edge count)
+    __shared__ double s_sum[32];           // cluster totals
+    __shared__ LmState s_state;            // every CTA keeps the whole solver state
+    __shared__ int s_n, s_scan[NW + 1];
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
 
-    if (rank == 0) {
+    {
         const unsigned* src = reinterpret_cast<const unsigned*>(P.state);
         unsigned* dst = reinterpret_cast<unsigned*>(&s_state);
         for (unsigned i = tid; i < sizeof(LmState) / 4; i += blockDim.x) dst[i] = src[i];
+        if (tid == 0) s_n = 0;
         __syncthreads();
         if (tid == 0) {   // lm_begin
             if (pose_src) for (int k = 0; k < 7; ++k) s_state.x[k] = pose_src[k];
@@ -234,38 +245,58 @@ __global__ void __cluster_dims__(kLmCluster, 1, 1) __launch_bounds__(kLmThreads)
             s_state.iter = 0;
             s_state.reuse_diag = 0;
             s_state.pass = first_pass ? 0 : s_state.pass + 1;
-            for (int k = 0; k < 7; ++k) s_pose[k] = s_state.x[k];
-            s_pose[7] = 0.0;
         }
     }
-    cluster.sync();
-    const double* pose0 = cluster.map_shared_rank(s_pose, 0);
+    // compaction of this CTA's slices, order preserving (chunks of kLmThreads entries: ballot + warp counts)
+    int overflow = 0;
+#pragma unroll
+    for (int kind = 0; kind < 2; ++kind) {
+        const ResidualSrc& R = P.src[kind];
+        const int n = R.n ? *R.n : 0;
+        const int per = (n + kLmCluster - 1) / kLmCluster;
+        const int lo = min(n, (int)rank * per), hi = min(n, lo + per);
+        for (int base = lo; base < hi; base += kLmThreads) {
+            const int i = base + tid;
+            const bool v = i < hi && R.flag[i] == 2;
+            const unsigned m = __ballot_sync(0xffffffffu, v);
+            if (lane == 0) s_scan[w] = __popc(m);
+            __syncthreads();
+            int off = s_n, tot = 0;
+#pragma unroll
+            for (int k = 0; k < NW; ++k) { const int c = s_scan[k]; if (k < w) off += c; tot += c; }
+            if (v) {
+                const int pos = off + __popc(m & lanemask_lt());
+                if (pos < list_cap) s_list[pos] = (kind << 30) | i; else overflow = 1;
+            }
+            __syncthreads();
+            if (tid == 0) s_n += tot;
+            __syncthreads();
+        }
+    }
+    const int n_list = min(s_n, list_cap);
+    const int my_edges = [&] { int c = 0; for (int k = tid; k < n_list; k += kLmThreads) c += (s_list[k] >> 30) == 0 ? 1 : 0; return c; }();
+    (void)overflow;     // cannot happen: list_cap covers the whole slice (host side)
     const double* part_of[kLmCluster];
 #pragma unroll
-    for (int r = 0; r < kLmCluster; ++r) part_of[r] = cluster.map_shared_rank(s_part, r);
+    for (int r = 0; r < kLmCluster; ++r) part_of[r] = cluster.map_shared_rank(&s_part[0][0], r);
+    __syncthreads();
 
-    const int gtid = rank * blockDim.x + tid, gstride = kLmCluster * blockDim.x;
     for (int round = 0; round < 8; ++round) {
-        double pose[7];
-#pragma unroll
-        for (int k = 0; k < 7; ++k) pose[k] = pose0[k];
-        if (pose0[7] != 0.0) break;           // finished (uniform across the cluster: read after a cluster barrier)
+        if (s_state.phase == 2) break;        // identical in every CTA
+        const double* x = s_state.phase == 1 ? s_state.xc : s_state.x;
+        double Rm[9], tv[3];
+        quat_to_mat(x, Rm);
+        tv[0] = x[4]; tv[1] = x[5]; tv[2] = x[6];
         double acc[kAcc];
 #pragma unroll
         for (int k = 0; k < kAcc; ++k) acc[k] = 0.0;
-        int cnt_edge = 0;
-#pragma unroll
-        for (int kind = 0; kind < 2; ++kind) {
+        for (int k = tid; k < n_list; k += kLmThreads) {
+            const int e = s_list[k], kind = e >> 30, i = e & 0x3fffffff;
             const ResidualSrc& R = P.src[kind];
-            const int n = R.n ? *R.n : 0;
-            for (int i = gtid; i < n; i += gstride) {
-                if (R.flag[i] != 2) continue;
-                D3 p;
-                if (R.p_override) p = d3(R.p_override[3 * i], R.p_override[3 * i + 1], R.p_override[3 * i + 2]);
-                else { const Pt q = R.queries[i]; p = d3((double)q.x, (double)q.y, (double)q.z); }
-                eval_one(kind, p, R.geom + 8 * (size_t)i, pose, acc);
-                if (kind == 0) ++cnt_edge;
-            }
+            D3 p;
+            if (R.p_override) p = d3(R.p_override[3 * i], R.p_override[3 * i + 1], R.p_override[3 * i + 2]);
+            else { const Pt q = R.queries[i]; p = d3((double)q.x, (double)q.y, (double)q.z); }
+            eval_one(kind, p, R.geom + 8 * (size_t)i, Rm, tv, acc);
         }
         // warp reduction, fixed tree (skipped by warps that evaluated nothing: their partial is exactly zero)
         if (__any_sync(0xffffffffu, acc[28] != 0.0)) {
@@ -275,56 +306,60 @@ __global__ void __cluster_dims__(kLmCluster, 1, 1) __launch_bounds__(kLmThreads)
                 for (int o = 16; o >= 1; o >>= 1) acc[k] += __shfl_down_sync(0xffffffffu, acc[k], o);
             }
         }
-        cnt_edge = __reduce_add_sync(0xffffffffu, cnt_edge);
+        const int cnt_edge = __reduce_add_sync(0xffffffffu, my_edges);
         if (lane == 0) {
 #pragma unroll
             for (int k = 0; k < kAcc; ++k) s_red[w][k] = acc[k];
             s_cnt[w] = cnt_edge;
         }
         __syncthreads();
+        const int par = round & 1;
         if (tid < kAcc) {
-            double s = 0;
+            double sum = 0;
 #pragma unroll
-            for (int k = 0; k < NW; ++k) s += s_red[k][tid];
-            s_part[tid] = s;
+            for (int k = 0; k < NW; ++k) sum += s_red[k][tid];
+            s_part[par][tid] = sum;
         }
         if (tid == 31) {
             int c = 0;
 #pragma unroll
             for (int k = 0; k < NW; ++k) c += s_cnt[k];
-            s_part[31] = (double)c;
+            s_part[par][31] = (double)c;
         }
-        cluster.sync();                        // all partials visible
-        if (rank == 0) {
-            if (tid < 32 && (tid < kAcc || tid == 31)) {
-                double s = 0;
+        cluster.sync();                        // all partials of this round visible
+        if (tid < 32 && (tid < kAcc || tid == 31)) {
+            double sum = 0;
 #pragma unroll
-                for (int r = 0; r < kLmCluster; ++r) s += part_of[r][tid];   // fixed order: deterministic
-                s_sum[tid] = s;
-            }
-            __syncthreads();
-            if (tid == 0) {
-                s_state.n_edge_res = (int)s_sum[31];
-                s_state.n_surf_res = (int)s_sum[28] - (int)s_sum[31];
-                lm_advance(P, &s_state, s_sum);
-                const double* nx = s_state.phase == 1 ? s_state.xc : s_state.x;
-                for (int k = 0; k < 7; ++k) s_pose[k] = nx[k];
-                s_pose[7] = s_state.phase == 2 ? 1.0 : 0.0;
-            }
+            for (int r = 0; r < kLmCluster; ++r) sum += part_of[r][par * 32 + tid];   // fixed order: deterministic
+            s_sum[tid] = sum;
         }
-        cluster.sync();                        // next pose / phase visible; partials may be overwritten
+        __syncthreads();
+        if (tid == 0) {
+            s_state.n_edge_res = (int)s_sum[31];
+            s_state.n_surf_res = (int)s_sum[28] - (int)s_sum[31];
+            lm_advance(P, &s_state, s_sum, rank == 0);
+        }
+        __syncthreads();
     }
     if (rank == 0) {
-        __syncthreads();
         unsigned* dst = reinterpret_cast<unsigned*>(P.state);
         const unsigned* src = reinterpret_cast<const unsigned*>(&s_state);
         for (unsigned i = tid; i < sizeof(LmState) / 4; i += blockDim.x) dst[i] = src[i];
     }
-    cluster.sync();                            // peers must not exit while rank 0 may still read their shared memory
+    cluster.sync();                            // peers must not exit while others may still read their shared memory
 }
 
-int lm_solve(cudaStream_t stream, const LmParams& P, const double* pose_src, int first_pass, uint64_t* launches) {
-    k_lm_solve<<<kLmCluster, kLmThreads, 0, stream>>>(P, pose_src, first_pass);
+int lm_solve(cudaStream_t stream, const LmParams& P, const double* pose_src, int first_pass, uint64_t* launches, int ub_edge, int ub_surf) {
+    // shared-memory list: the largest slice a CTA can own
+    const int list_cap = (ub_edge + kLmCluster - 1) / kLmCluster + (ub_surf + kLmCluster - 1) / kLmCluster + 8;
+    const size_t smem = sizeof(int) * (size_t)list_cap;
+    PF_REQUIRE(smem <= 160 * 1024, "lm_solve: %d + %d residual candidates exceed the solver's shared-memory list", ub_edge, ub_surf);
+    static size_t smem_set = 0;
+    if (smem > smem_set) {
+        PF_CUDA(cudaFuncSetAttribute(k_lm_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem > 48 * 1024 ? smem : 48 * 1024)));
+        smem_set = smem > 48 * 1024 ? smem : 48 * 1024;
+    }
+    k_lm_solve<<<kLmCluster, kLmThreads, smem, stream>>>(P, pose_src, first_pass, list_cap);
     if (launches) *launches += 1;
     PF_CUDA(cudaGetLastError());
     return PF_OK;
@@ -400,7 +435,7 @@ extern "C" int pf_eval_normal_eq(int device, const double pose[7], const double*
     LmParams P{};
     PF_CHECK(solve_tap_setup(t, device, pose, edge9, n_edge, surf7, n_surf, P));
     P.eval_only = 1;
-    PF_CHECK(lm_solve(t.stream, P, nullptr, 1, nullptr));
+    PF_CHECK(lm_solve(t.stream, P, nullptr, 1, nullptr, n_edge, n_surf));
     LmState S;
     PF_CUDA(cudaMemcpyAsync(&S, t.d_state, sizeof(S), cudaMemcpyDeviceToHost, t.stream));
     PF_CUDA(cudaStreamSynchronize(t.stream));
@@ -417,7 +452,7 @@ extern "C" int pf_lm_solve(int device, double pose_io[7], const double* edge9, i
     LmParams P{};
     PF_CHECK(solve_tap_setup(t, device, pose_io, edge9, n_edge, surf7, n_surf, P));
     P.eval_only = 0;
-    PF_CHECK(lm_solve(t.stream, P, nullptr, 1, nullptr));
+    PF_CHECK(lm_solve(t.stream, P, nullptr, 1, nullptr, n_edge, n_surf));
     LmState S;
     PF_CUDA(cudaMemcpyAsync(&S, t.d_state, sizeof(S), cudaMemcpyDeviceToHost, t.stream));
     PF_CUDA(cudaStreamSynchronize(t.stream));

@@ -45,6 +45,7 @@ constexpr int kLmThreads = 256;  // 2048 threads; 255 registers per thread keep 
 
 // One launch = one complete solve: at most 1 + 4 evaluations (max_num_iterations = 4) and the trust-region state machine.
 // pose_src: device pose to start from (null: keep state->x); first_pass resets the outer-iteration counter.
-int lm_solve(cudaStream_t stream, const LmParams& P, const double* pose_src, int first_pass, uint64_t* launches);
+// ub_edge / ub_surf: upper bounds of the two query counts (size the shared-memory list of residual blocks).
+int lm_solve(cudaStream_t stream, const LmParams& P, const double* pose_src, int first_pass, uint64_t* launches, int ub_edge, int ub_surf);
 
 }  // namespace pf

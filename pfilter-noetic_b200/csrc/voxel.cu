@@ -141,20 +141,52 @@ __global__ void __launch_bounds__(256) k_vox_keys(VoxParams P, uint32_t* __restr
     }
 }
 
+struct VoxSum {
+    float sx = 0.f, sy = 0.f, sz = 0.f, sr = 0.f, sg = 0.f, sb = 0.f, sa = 0.f;
+    int rmax = -1, gmax = -1;
+};
+__device__ __forceinline__ void vox_add(VoxSum& a, bool pcl, float x, float y, float z, unsigned rgba) {
+    a.sx = __fadd_rn(a.sx, x); a.sy = __fadd_rn(a.sy, y); a.sz = __fadd_rn(a.sz, z);
+    if (pcl) {
+        a.sr += (float)(rgba & 0xff); a.sg += (float)((rgba >> 8) & 0xff);
+        a.sb += (float)((rgba >> 16) & 0xff); a.sa += (float)(rgba >> 24);
+    } else {
+        a.rmax = max(a.rmax, (int)pt_r(rgba));
+        a.gmax = max(a.gmax, (int)pt_g(rgba));
+    }
+}
+__device__ __forceinline__ bool vox_finish(const VoxSum& a, const VoxParams& P, bool pcl, int n, Pt* o) {
+    const float fn = (float)n;
+    o->x = __fdiv_rn(a.sx, fn); o->y = __fdiv_rn(a.sy, fn); o->z = __fdiv_rn(a.sz, fn);
+    if (pcl) {
+        o->rgba = pack_rgba((unsigned)__fdiv_rn(a.sr, fn) & 0xff, (unsigned)__fdiv_rn(a.sg, fn) & 0xff,
+                            (unsigned)__fdiv_rn(a.sb, fn) & 0xff, (unsigned)__fdiv_rn(a.sa, fn) & 0xff);
+        return true;
+    }
+    // extractstablepoint (:12-14): drop if g < r*theta_p && r > k_new && g < theta_max + 1
+    const bool drop = ((float)a.gmax < __fmul_rn((float)a.rmax, P.theta_p)) && (a.rmax > P.k_new) && (a.gmax < P.theta_max + 1);
+    const int r2 = a.rmax > 250 ? 255 : a.rmax + 2;   // :634-646
+    o->rgba = pack_rgba((unsigned)r2, (unsigned)a.gmax, 0u, 255u);
+    return !drop;
+}
+
 // One CTA per tile of 256 sorted entries (persistent, tiles by ticket).  The runs of equal keys that START in the tile are
-// its voxels; a warp takes one voxel at a time, gathers the run 32 points per step (the gather of the next step is in
-// flight while the current one is summed) and adds them up in sorted order = ascending input index -- the ordered float sum
-// is inherently sequential, but its latency is one gather per 32 points (near-range ground voxels hold > 250 points of a
-// 64-ring scan).  Finished voxels are compacted in key order by a chained scan; output is written once, coalesced.
+// its voxels.  The ordered float sum of a voxel (ascending input index) is inherently sequential; what matters is how many
+// dependent gather latencies it costs.  Short runs (<= 16 points: the bulk of the voxels) are summed by one thread each, all
+// in parallel; long runs (near-range ground voxels of a 64-ring scan hold > 250 points) are taken by a warp, which gathers 32
+// points per step with the next step's gather already in flight.  Finished voxels are compacted in key order by a chained
+// scan; the output is written once, coalesced.
+constexpr int kVoxShortRun = 16;
 __global__ void __launch_bounds__(256) k_vox_reduce(VoxParams P, const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals,
                                                     unsigned long long* status, int status_stride, unsigned* ctrl, int ticket_word, int site) {
     const int cloud = blockIdx.y;
     const VoxCloud& c = P.c[cloud];
-    __shared__ int s_tile;
+    __shared__ int s_tile, s_nlong;
     __shared__ int s_tmp[9];
     __shared__ unsigned s_look[kScanSmemWords];
     __shared__ int s_head[256];          // sorted position of the tile's k-th voxel
-    __shared__ Pt s_out[256];            // its finished point
+    __shared__ int s_long[256];          // voxels left to the warps
+    __shared__ Pt s_out[256];            // finished points
     __shared__ uint8_t s_keep[256];
     const int* st = reinterpret_cast<const int*>(P.state);
     const int start = cloud == 0 ? 0 : st[12];
@@ -163,7 +195,7 @@ __global__ void __launch_bounds__(256) k_vox_reduce(VoxParams P, const uint32_t*
     const bool pcl = P.mode == VOX_PCL;
     while (true) {   // persistent CTAs pull tiles by ticket until the cloud is exhausted
         __syncthreads();
-        if (tid == 0) s_tile = (int)atomicAdd(&ctrl[ticket_word + cloud], 1u);
+        if (tid == 0) { s_tile = (int)atomicAdd(&ctrl[ticket_word + cloud], 1u); s_nlong = 0; }
         __syncthreads();
         const int tile = s_tile;
         if (len == 0) {
@@ -181,12 +213,36 @@ __global__ void __launch_bounds__(256) k_vox_reduce(VoxParams P, const uint32_t*
         const int hidx = block_scan_excl_256(head ? 1 : 0, s_tmp, &nheads);
         if (head) s_head[hidx] = p;
         __syncthreads();
-        for (int hh = w; hh < nheads; hh += 8) {
+        if (tid < nheads) {
+            const int ps = s_head[tid];
+            const int e = tid + 1 < nheads ? s_head[tid + 1] : -1;      // the last voxel may run on into the following tiles
+            if (e >= 0 && e - ps <= kVoxShortRun) {
+                VoxSum a;
+                for (int q = ps; q < e; q += 8) {
+                    Pt v[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u)
+                        if (q + u < e) v[u] = load_pt(c, (int)vals[q + u] - ibase);
+#pragma unroll
+                    for (int u = 0; u < 8; ++u)
+                        if (q + u < e) vox_add(a, pcl, v[u].x, v[u].y, v[u].z, v[u].rgba);
+                }
+                Pt o;
+                s_keep[tid] = vox_finish(a, P, pcl, e - ps, &o) ? 1 : 0;
+                s_out[tid] = o;
+            } else {
+                s_long[atomicAdd(&s_nlong, 1)] = tid;
+            }
+        }
+        __syncthreads();
+        const int nlong = s_nlong;
+        for (int j = w; j < nlong; j += 8) {
+            const int hh = s_long[j];
             const int ps = s_head[hh];
             int e;
             if (hh + 1 < nheads) {
                 e = s_head[hh + 1];
-            } else {     // the last voxel of the tile may run on into the following tiles
+            } else {
                 const unsigned key = keys[ps];
                 e = tile_end;
                 while (e < end) {
@@ -196,46 +252,22 @@ __global__ void __launch_bounds__(256) k_vox_reduce(VoxParams P, const uint32_t*
                     e += 32;
                 }
             }
-            float sx = 0.f, sy = 0.f, sz = 0.f, sr = 0.f, sg = 0.f, sb = 0.f, sa = 0.f;
-            int rmax = -1, gmax = -1;
+            VoxSum a;
             Pt cur{0.f, 0.f, 0.f, 0u};
             if (ps + lane < e) cur = load_pt(c, (int)vals[ps + lane] - ibase);
             for (int q = ps; q < e; q += 32) {
                 Pt nxt{0.f, 0.f, 0.f, 0u};
                 if (q + 32 + lane < e) nxt = load_pt(c, (int)vals[q + 32 + lane] - ibase);
                 const int cnt = min(32, e - q);
-                for (int j = 0; j < cnt; ++j) {
-                    const float x = __shfl_sync(0xffffffffu, cur.x, j), y = __shfl_sync(0xffffffffu, cur.y, j), z = __shfl_sync(0xffffffffu, cur.z, j);
-                    const unsigned rgba = __shfl_sync(0xffffffffu, cur.rgba, j);
-                    sx = __fadd_rn(sx, x); sy = __fadd_rn(sy, y); sz = __fadd_rn(sz, z);
-                    if (pcl) {
-                        sr += (float)(rgba & 0xff); sg += (float)((rgba >> 8) & 0xff);
-                        sb += (float)((rgba >> 16) & 0xff); sa += (float)(rgba >> 24);
-                    } else {
-                        rmax = max(rmax, (int)pt_r(rgba));
-                        gmax = max(gmax, (int)pt_g(rgba));
-                    }
-                }
+                for (int u = 0; u < cnt; ++u)
+                    vox_add(a, pcl, __shfl_sync(0xffffffffu, cur.x, u), __shfl_sync(0xffffffffu, cur.y, u), __shfl_sync(0xffffffffu, cur.z, u),
+                            __shfl_sync(0xffffffffu, cur.rgba, u));
                 cur = nxt;
             }
             if (lane == 0) {
-                const float fn = (float)(e - ps);
                 Pt o;
-                bool keep;
-                o.x = __fdiv_rn(sx, fn); o.y = __fdiv_rn(sy, fn); o.z = __fdiv_rn(sz, fn);
-                if (pcl) {
-                    o.rgba = pack_rgba((unsigned)__fdiv_rn(sr, fn) & 0xff, (unsigned)__fdiv_rn(sg, fn) & 0xff,
-                                       (unsigned)__fdiv_rn(sb, fn) & 0xff, (unsigned)__fdiv_rn(sa, fn) & 0xff);
-                    keep = true;
-                } else {
-                    // extractstablepoint (:12-14): drop if g < r*theta_p && r > k_new && g < theta_max + 1
-                    const bool drop = ((float)gmax < __fmul_rn((float)rmax, P.theta_p)) && (rmax > P.k_new) && (gmax < P.theta_max + 1);
-                    keep = !drop;
-                    const int r2 = rmax > 250 ? 255 : rmax + 2;   // :634-646
-                    o.rgba = pack_rgba((unsigned)r2, (unsigned)gmax, 0u, 255u);
-                }
+                s_keep[hh] = vox_finish(a, P, pcl, e - ps, &o) ? 1 : 0;
                 s_out[hh] = o;
-                s_keep[hh] = keep ? 1 : 0;
             }
         }
         __syncthreads();
