@@ -103,7 +103,7 @@ typedef struct pf_odom_params {
     int32_t k_new;             /* PFilter parameters (launch/pfilter_kitti.launch:59-64) */
     float theta_p;
     int32_t theta_max;
-    double weight_type;        /* 0 (class default), 1, 2 or 12 (src/odomEstimationClass.cpp:389-423) */
+    double weight_type;        /* 0 (class default), 1 observe, 2 sparsity, 12 both (src/odomEstimationClass.cpp:389-423); other values are rejected */
     int32_t max_map_points;    /* capacity of EACH local map (edge, surf); 0 = default 2M */
     int32_t max_features;      /* capacity of each per-frame feature cloud passed in; 0 = default 131072 */
 } pf_odom_params;

@@ -779,7 +779,7 @@ void associate(int kind, const Searcher& knn, std::vector<OPoint>& map, std::vec
             for (int j = 0; j < 5; ++j)
                 if (std::fabs(nv.x * nb[j].x + nv.y * nb[j].y + nv.z * nb[j].z + negOA) > 0.2) { valid = false; break; }   // :466-476
             if (!valid) continue;
-            R.a = nv; R.b = {negOA, 0, 0};
+            R.a = nv; R.b = {(double)(float)negOA, 0, 0};   // surfInfo::negative_OA_dot_norm is a float (include/odomEstimationClass.h:93-94)
         }
         // persistence bookkeeping (:332-355 / :480-504) -- sequential: later queries see the incremented g
         int sg = 0, sr = 0;

@@ -21,6 +21,8 @@ __global__ void __launch_bounds__(256) k_assoc_match(AssocParams P) {
     const unsigned lane = lane_id();
     const int nq = *c.n_q;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    if (P.weight_type != 0 && blockIdx.x == 0 && threadIdx.x < 4)     // min / max slots of this pass (read by k_assoc_persist, which follows)
+        P.w_minmax[4 * kind + threadIdx.x] = (threadIdx.x & 1) ? 0ull : ~0ull;
     for (int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; q < nq; q += nwarps) {
     const bool guard = P.min_edge_map == 0 || (*P.c[0].n_map > P.min_edge_map && *P.c[1].n_map > P.min_surf_map);   // :247
     unsigned flag = 0;
@@ -68,7 +70,8 @@ __global__ void __launch_bounds__(256) k_assoc_match(AssocParams P) {
 #pragma unroll
                 for (int j = 0; j < 5; ++j)
                     if (fabs(n[0] * nb[j].x + n[1] * nb[j].y + n[2] * nb[j].z + negOA) > 0.2) valid = false;   // :466-476 (NaN -> stays valid, as in the reference)
-                g8[0] = n[0]; g8[1] = n[1]; g8[2] = n[2]; g8[3] = negOA;
+                g8[0] = n[0]; g8[1] = n[1]; g8[2] = n[2];
+                g8[3] = (double)(float)negOA;   // surfInfo::negative_OA_dot_norm is a float (include/odomEstimationClass.h:93-94)
             }
             if (valid) {
                 flag = 1;
@@ -114,6 +117,28 @@ __global__ void __launch_bounds__(128) k_assoc_persist(AssocParams P) {
         Pt* qp = c.queries + q;
         qp->rgba = (qp->rgba & 0xffff0000u) | r | (g << 8);
         c.flag[q] = 2;
+        if (P.weight_type != 0) {     // weight inputs of the residual block (:360-385): observe, mean distance of the 5 neighbours to their centroid
+            D3 nb[5], cn = d3(0, 0, 0);
+#pragma unroll
+            for (int j = 0; j < 5; ++j) {
+                const Pt mp = c.map[m[j]];
+                nb[j] = d3((double)mp.x, (double)mp.y, (double)mp.z);
+                cn = cn + nb[j];
+            }
+            cn = d3(cn.x / 5, cn.y / 5, cn.z / 5);
+            float sum = 0.f;
+#pragma unroll
+            for (int j = 0; j < 5; ++j) sum = __fadd_rn(sum, (float)norm3(cn - nb[j]));      // float sum += double norm
+            const double spa = (double)(float)((double)sum / 5.0);                            // sum /= 5.0 (float), pushed as double
+            const double obs = (double)observe;
+            c.w_obs[q] = observe;
+            c.w_spa[q] = spa;
+            unsigned long long* mm = P.w_minmax + 4 * kind;
+            atomicMin(mm + 0, (unsigned long long)__double_as_longlong(obs));
+            atomicMax(mm + 1, (unsigned long long)__double_as_longlong(obs));
+            atomicMin(mm + 2, (unsigned long long)__double_as_longlong(spa));
+            atomicMax(mm + 3, (unsigned long long)__double_as_longlong(spa));
+        }
     }
     // release the lists; the last reader of a map point commits its counter and empties the list
 #pragma unroll
@@ -204,7 +229,7 @@ extern "C" int pf_associate(int device, int kind, pf_point* map, int m, pf_point
     PF_CHECK(build_grids(t.ws, G, 0, mc, 0));
     AssocParams P{};
     AssocCloud live{t.d_q, t.d_counts + 2, t.d_map, t.d_counts, KnnGrid{t.d_pts, t.d_cs, t.d_ce, t.d_geom}, t.d_head, t.d_hits, t.d_next, t.d_nn,
-                    t.d_flag, t.d_g8};
+                    t.d_flag, t.d_g8, nullptr, nullptr};
     AssocCloud dead = live;
     dead.n_q = t.d_counts + 3;
     dead.n_map = t.d_counts + 1;
@@ -213,6 +238,7 @@ extern "C" int pf_associate(int device, int kind, pf_point* map, int m, pf_point
     P.pose = t.d_pose;
     P.k_new = k_new; P.theta_p = theta_p; P.theta_max = theta_max;
     P.min_edge_map = 0; P.min_surf_map = 0;
+    P.weight_type = 0; P.w_minmax = nullptr;
     uint64_t launches = 0;
     PF_CHECK(associate_pass(t.stream, P, kind == 0 ? qc : 0, kind == 1 ? qc : 0, &launches));
     unsigned err = 0;

@@ -17,6 +17,8 @@ struct AssocCloud {
     int* nn_idx;           // [5 * query capacity]
     uint8_t* flag;         // [query capacity] 0 none, 1 fit ok but skipped by the persistence rule, 2 residual block
     double* geom;          // [8 * query capacity] edge: a[3] b[3]; surf: n[3] d
+    float* w_obs;          // [query capacity] weightType != 0: the residual's observe value (:360 / :509)
+    double* w_spa;         // [query capacity] weightType != 0: point sparsity (:367-385 / :513-531)
 };
 
 struct AssocParams {
@@ -24,6 +26,9 @@ struct AssocParams {
     const double* pose;    // device [qx qy qz qw tx ty tz]
     int k_new; float theta_p; int theta_max;
     int min_edge_map, min_surf_map;   // guard :247 (10 / 50); 0 disables (stage tap)
+    int weight_type;       // 0, 1, 2 or 12 (src/odomEstimationClass.cpp:389-423)
+    unsigned long long* w_minmax;   // [2][4] per kind: min / max of observe, min / max of sparsity over the pass's residual blocks
+                                    // (bit patterns of non-negative doubles: ordered as unsigned integers)
 };
 
 // Enqueues the two association kernels (match, persist) for one pass on `stream`.

@@ -160,6 +160,9 @@ struct pf_odom {
     int *d_head[2] = {nullptr, nullptr}, *d_hits[2] = {nullptr, nullptr}, *d_next[2] = {nullptr, nullptr}, *d_nn[2] = {nullptr, nullptr};
     uint8_t* d_flag[2] = {nullptr, nullptr};
     double* d_g8[2] = {nullptr, nullptr};
+    float* d_wobs[2] = {nullptr, nullptr};           // residual weights (weightType 1 / 2 / 12)
+    double* d_wspa[2] = {nullptr, nullptr};
+    unsigned long long* d_wminmax = nullptr;         // [2][4]
     LmState* d_state = nullptr;
     double* d_iter_poses = nullptr;
     OdomShared* d_sh = nullptr;
@@ -214,7 +217,11 @@ int odom_alloc(pf_odom* h) {
         PF_CUDA(cudaMalloc(&h->d_flag[k], fcap));
         PF_CUDA(cudaMemset(h->d_flag[k], 0, fcap));
         PF_CUDA(cudaMalloc(&h->d_g8[k], sizeof(double) * 8 * fcap));
+        PF_CUDA(cudaMalloc(&h->d_wobs[k], sizeof(float) * fcap));
+        PF_CUDA(cudaMalloc(&h->d_wspa[k], sizeof(double) * fcap));
     }
+    PF_CUDA(cudaMalloc(&h->d_wminmax, sizeof(unsigned long long) * 8));
+    PF_CUDA(cudaMemset(h->d_wminmax, 0, sizeof(unsigned long long) * 8));
     PF_CHECK(map_merge_scratch_create(h->msc, 2 * fcap + kMergeExcCap, kMergeExcCap, bufcap));
     PF_CUDA(cudaMalloc(&h->d_state, sizeof(LmState)));
     PF_CUDA(cudaMemset(h->d_state, 0, sizeof(LmState)));
@@ -337,12 +344,14 @@ int enqueue_update(pf_odom* h, const float4* const feat[2], const int* const n_f
     for (int k = 0; k < 2; ++k) {
         A.c[k] = AssocCloud{h->d_ds[k], h->d_nds + k, h->d_map[cur][k], h->d_nmap[cur] + k,
                             KnnGrid{h->d_gpts[k], h->d_cs[k], h->d_ce[k], h->d_geom + 6 * k},
-                            h->d_head[k], h->d_hits[k], h->d_next[k], h->d_nn[k], h->d_flag[k], h->d_g8[k]};
-        L.src[k] = ResidualSrc{h->d_ds[k], nullptr, h->d_flag[k], h->d_g8[k], h->d_nds + k};
+                            h->d_head[k], h->d_hits[k], h->d_next[k], h->d_nn[k], h->d_flag[k], h->d_g8[k], h->d_wobs[k], h->d_wspa[k]};
+        L.src[k] = ResidualSrc{h->d_ds[k], nullptr, h->d_flag[k], h->d_g8[k], h->d_nds + k, h->d_wobs[k], h->d_wspa[k]};
     }
     A.pose = h->d_state->x;
     A.k_new = h->prm.k_new; A.theta_p = h->prm.theta_p; A.theta_max = h->prm.theta_max;
     A.min_edge_map = 10; A.min_surf_map = 50;   // :247
+    A.weight_type = (int)h->prm.weight_type; A.w_minmax = h->d_wminmax;
+    L.weight_type = (int)h->prm.weight_type; L.w_minmax = h->d_wminmax;
     L.state = h->d_state; L.iter_poses = h->d_iter_poses; L.eval_only = 0;
     for (int it = 0; it < passes; ++it) {
         PF_CHECK(associate_pass(h->stream, A, ub_e, ub_s, &ws.launches));
@@ -409,7 +418,8 @@ extern "C" int pf_odom_create(const pf_odom_params* p, int device, pf_odom** out
     PF_REQUIRE(p && out, "null argument");
     PF_REQUIRE(p->map_resolution >= 0.2, "map_resolution %g: the streaming map update keeps 10-bit voxel coordinates inside the 200 m crop box (needs >= 0.2 m)",
                p->map_resolution);
-    PF_REQUIRE(p->weight_type == 0.0, "weight_type %g: only 0 (the class default) is implemented in this round", p->weight_type);
+    PF_REQUIRE(p->weight_type == 0.0 || p->weight_type == 1.0 || p->weight_type == 2.0 || p->weight_type == 12.0,
+               "weight_type %g: the reference knows 0, 1, 2 and 12 (src/odomEstimationClass.cpp:405-421)", p->weight_type);
     int ndev = 0;
     PF_CUDA(cudaGetDeviceCount(&ndev));
     PF_REQUIRE(device >= 0 && device < ndev, "device %d not available (%d devices)", device, ndev);
@@ -444,7 +454,9 @@ extern "C" int pf_odom_destroy(pf_odom* h) {
         cudaFree(h->d_feat[k]); cudaFree(h->d_ds[k]); cudaFree(h->d_map[0][k]); cudaFree(h->d_map[1][k]); cudaFree(h->d_nmap[k]);
         cudaFree(h->d_gpts[k]); cudaFree(h->d_cs[k]); cudaFree(h->d_ce[k]); cudaFree(h->d_head[k]); cudaFree(h->d_hits[k]);
         cudaFree(h->d_next[k]); cudaFree(h->d_nn[k]); cudaFree(h->d_flag[k]); cudaFree(h->d_g8[k]);
+        cudaFree(h->d_wobs[k]); cudaFree(h->d_wspa[k]);
     }
+    cudaFree(h->d_wminmax);
     cudaFree(h->d_state); cudaFree(h->d_iter_poses); cudaFree(h->d_sh); cudaFree(h->d_pose_hist);
     cudaFreeHost(h->h_sh); cudaFreeHost(h->h_state); cudaFreeHost(h->h_counts); cudaFreeHost(h->h_iter); cudaFreeHost(h->h_ring);
     for (int i = 0; i < pf_odom::kRing; ++i) if (h->ring_ev[i]) cudaEventDestroy(h->ring_ev[i]);

@@ -24,7 +24,23 @@ constexpr int kAcc = 29;   // 21 H + 6 g + cost + count
 // |a-b| (lp-a) x u, so r = |(lp-a) x u| and J = w^T [u]x [ -[lp]x  I ] with w = -nu/|nu|: the same numbers as
 // src/lidarOptimization.cpp:18-41 with one square root and two reciprocals on the critical path instead of eleven fp64
 // divisions / roots.  Huber: sqrt(s) = |r|.
-__device__ __forceinline__ void eval_one(int kind, D3 p, const double* ge, const double* Rm, const double* tv, double acc[kAcc]) {
+// The residual weights of weightType 1 / 2 / 12: min-max normalised observe (observeMean, src/odomEstimationClass.cpp:136-160) and
+// point sparsity (pointSparsityMean, include/odomEstimationClass.h:111-126).  mm = {min obs, max obs, min spa, max spa}.
+__device__ __forceinline__ double residual_weight(int weight_type, double obs, double spa, const double* mm) {
+    if (weight_type == 1 || weight_type == 12) {
+        const double len = mm[1] - mm[0];
+        if (len != 0) { obs = (obs - mm[0]) / len; obs -= 1.0; obs = fabs(obs); obs *= 2.0; obs = fmax(0.1, obs); }
+    }
+    if (weight_type == 2 || weight_type == 12) {
+        const double len = mm[3] - mm[2];
+        if (len != 0) { spa = (spa - mm[2]) / len; spa -= 1.0; spa = fabs(spa); spa *= 2.0; }
+    }
+    return weight_type == 1 ? obs : weight_type == 2 ? spa : (spa + obs) / 2;
+}
+
+// `weight` scales the RESIDUAL only, never the Jacobian, and only when the functor's own test passes: the edge functor
+// wants exactly 1, 2 or 12 (src/lidarOptimization.cpp:25-28), the surf functor anything but 0 (:62-63).
+__device__ __forceinline__ void eval_one(int kind, D3 p, const double* ge, const double* Rm, const double* tv, double weight, double acc[kAcc]) {
     const D3 lp = d3(Rm[0] * p.x + Rm[1] * p.y + Rm[2] * p.z + tv[0], Rm[3] * p.x + Rm[4] * p.y + Rm[5] * p.z + tv[1],
                      Rm[6] * p.x + Rm[7] * p.y + Rm[8] * p.z + tv[2]);
     double r, ar, J[6];
@@ -35,18 +51,19 @@ __device__ __forceinline__ void eval_one(int kind, D3 p, const double* ge, const
         const D3 u = inv_de * de;
         const D3 nu = cross3(lp - a, u);
         r = norm3(nu);
-        ar = r;
         const D3 w = (-1.0 / r) * nu;
         const D3 m = cross3(w, u);           // w^T [u]x
         const D3 jr = cross3(lp, m);         // m^T (-[lp]x)
         J[0] = jr.x; J[1] = jr.y; J[2] = jr.z; J[3] = m.x; J[4] = m.y; J[5] = m.z;
+        if (weight == 1 || weight == 2 || weight == 12) r = weight * r;
     } else {
         const D3 n = d3(ge[0], ge[1], ge[2]);
         r = dot3(n, lp) + ge[3];
-        ar = fabs(r);
+        if (weight != 0) r = weight * r;
         const D3 jr = cross3(lp, n);
         J[0] = jr.x; J[1] = jr.y; J[2] = jr.z; J[3] = n.x; J[4] = n.y; J[5] = n.z;
     }
+    ar = fabs(r);
     // HuberLoss(0.1): rho(s), s = r^2
     const double s = r * r;
     double rho0, sc;
@@ -231,7 +248,9 @@ __global__ void __cluster_dims__(kLmCluster, 1, 1) __launch_bounds__(kLmThreads)
     __shared__ double s_sum[32];           // cluster totals
     __shared__ LmState s_state;            // every CTA keeps the whole solver state
     __shared__ int s_n, s_scan[NW + 1];
+    __shared__ double s_mm[8];             // weightType != 0: min / max of observe and sparsity per kind
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    if (P.weight_type != 0 && tid < 8) s_mm[tid] = __longlong_as_double((long long)P.w_minmax[tid]);
 
     {
         const unsigned* src = reinterpret_cast<const unsigned*>(P.state);
@@ -296,7 +315,8 @@ __global__ void __cluster_dims__(kLmCluster, 1, 1) __launch_bounds__(kLmThreads)
             D3 p;
             if (R.p_override) p = d3(R.p_override[3 * i], R.p_override[3 * i + 1], R.p_override[3 * i + 2]);
             else { const Pt q = R.queries[i]; p = d3((double)q.x, (double)q.y, (double)q.z); }
-            eval_one(kind, p, R.geom + 8 * (size_t)i, Rm, tv, acc);
+            const double weight = P.weight_type != 0 ? residual_weight(P.weight_type, (double)R.w_obs[i], R.w_spa[i], s_mm + 4 * kind) : 0.0;
+            eval_one(kind, p, R.geom + 8 * (size_t)i, Rm, tv, weight, acc);
         }
         // warp reduction, fixed tree (skipped by warps that evaluated nothing: their partial is exactly zero)
         if (__any_sync(0xffffffffu, acc[28] != 0.0)) {
@@ -416,13 +436,14 @@ int solve_tap_setup(SolveTap& t, int device, const double pose[7], const double*
             PF_CUDA(cudaMemcpyAsync(t.d_p[k], hp[k].data(), sizeof(double) * 3 * n[k], cudaMemcpyHostToDevice, t.stream));
             PF_CUDA(cudaMemcpyAsync(t.d_geom[k], hg[k].data(), sizeof(double) * 8 * n[k], cudaMemcpyHostToDevice, t.stream));
         }
-        P.src[k] = ResidualSrc{nullptr, t.d_p[k], t.d_flag[k], t.d_geom[k], t.d_n + k};
+        P.src[k] = ResidualSrc{nullptr, t.d_p[k], t.d_flag[k], t.d_geom[k], t.d_n + k, nullptr, nullptr};
     }
     PF_CUDA(cudaMalloc(&t.d_state, sizeof(LmState)));
     PF_CUDA(cudaMemsetAsync(t.d_state, 0, sizeof(LmState), t.stream));
     PF_CUDA(cudaMemcpyAsync(t.d_state->x, pose, sizeof(double) * 7, cudaMemcpyHostToDevice, t.stream));
     P.state = t.d_state;
     P.iter_poses = nullptr;
+    P.weight_type = 0; P.w_minmax = nullptr;
     PF_CUDA(cudaStreamSynchronize(t.stream));   // the staging vectors go out of scope
     return PF_OK;
 }

@@ -12,6 +12,8 @@ struct ResidualSrc {          // one feature kind
     const uint8_t* flag;      // 2 = residual block present
     const double* geom;       // [8 n] edge: a[3] b[3]; surf: n[3] d
     const int* n;             // device count
+    const float* w_obs;       // weightType != 0: observe value of the residual block
+    const double* w_spa;      // weightType != 0: point sparsity of the residual block
 };
 
 struct LmState {
@@ -38,6 +40,8 @@ struct LmParams {
     LmState* state;
     double* iter_poses;       // [16][7] pose after every outer iteration (may be null)
     int eval_only;            // stage tap: evaluate at state->x and stop
+    int weight_type;          // 0, 1, 2, 12: residual weights (src/odomEstimationClass.cpp:389-423, src/lidarOptimization.cpp:25-28, :62-63)
+    const unsigned long long* w_minmax;   // [2][4] min / max of observe and sparsity per kind (see match.cuh)
 };
 
 constexpr int kLmCluster = 8;    // CTAs of the solver cluster (8 SMs, distributed shared memory reduction)

@@ -40,7 +40,7 @@ def test_no_cpu_fallback_paths(pfb):
     cfg = capi.ExtractConfig(1000, 1, 0)
     assert lib.pf_extract_create(C.byref(lidar), C.byref(cfg), 0, C.byref(h)) == -1
     assert b"num_lines" in lib.pf_last_error()
-    prm = capi.OdomParams(0.4, 0, 0.4, 75, 2.0, 0, 0)   # weight types 1/2/12 are SURVEY section 8 row F3 (not built yet)
+    prm = capi.OdomParams(0.4, 0, 0.4, 75, 3.0, 0, 0)   # the reference knows weight types 0, 1, 2, 12 only
     assert lib.pf_odom_create(C.byref(prm), 0, C.byref(h)) == -1
     import inspect
     src = inspect.getsource(capi)
