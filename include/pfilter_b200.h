@@ -143,6 +143,20 @@ void* pf_odom_stream(pf_odom* h);
 int pf_odom_get_phase_ms(pf_odom* h, float ms[5]);
 int pf_odom_kernel_launches(pf_odom* h, uint64_t* launches);
 
+/* ------------------------------------------------------------------------------------------------
+ * Odom_BPF_EstimationClass (include/odomEstimationClass.h:169-205, src/odomEstimationClass.cpp:649-1306): the reference's
+ * second odometry class -- the same arithmetic over three feature kinds: beam and pillar (point-to-line residuals, leaf =
+ * map_resolution) and facade (point-to-plane, leaf = 2 x map_resolution).  Same handle type and accessors as above:
+ * pf_odom_get_pose, pf_odom_map_size / pf_odom_get_map_part (which = 0 beam, 1 pillar, 2 facade), pf_odom_get_map (beam, pillar,
+ * facade order of :683-689), pf_odom_get_iter_poses, pf_odom_get_stats (edge fields = beam, surf fields = facade; residual
+ * counts = line-type and plane-type totals), pf_odom_destroy.
+ * ---------------------------------------------------------------------------------------------- */
+int pf_odom_bpf_create(const pf_odom_params* p, int device, pf_odom** out);                       /* init :649-681 */
+int pf_odom_bpf_init_map(pf_odom* h, const float* beam, int n_beam, const float* pillar, int n_pillar, const float* facade,
+                         int n_facade);                                                            /* initMapWithPoints :692-698 */
+int pf_odom_bpf_update(pf_odom* h, const float* beam, int n_beam, const float* pillar, int n_pillar, const float* facade, int n_facade,
+                       double pose_out[7]);                                                        /* updatePointsToMap :706-760 */
+
 /* Device-resident hand-off: consume the outputs of the last single-scan extraction of `ex` (same device)
  * without a host round trip.  Frame 0 initialises the map, later frames update it. */
 int pf_odom_process_extracted(pf_odom* h, pf_extract* ex, double pose_out[7]);

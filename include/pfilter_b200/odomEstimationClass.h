@@ -98,3 +98,71 @@ class Odom_ES_EstimationClass {
 };
 
 typedef Odom_ES_EstimationClass OdomEstimationClass;
+
+// Odom_BPF_EstimationClass (/root/reference/include/odomEstimationClass.h:169-205): beam / pillar / facade feature kinds.
+class Odom_BPF_EstimationClass {
+   public:
+    using Cloud = pfilter_b200::PointCloud<PointType>;
+
+    Odom_BPF_EstimationClass() {}
+    ~Odom_BPF_EstimationClass() { if (h_) pf_odom_destroy(h_); }
+    Odom_BPF_EstimationClass(const Odom_BPF_EstimationClass&) = delete;
+    Odom_BPF_EstimationClass& operator=(const Odom_BPF_EstimationClass&) = delete;
+
+    void init(lidar::Lidar /*lidar_param*/, double map_resolution_in, int k_new_para, float theta_p_para, int theta_max_para,
+              double weightType_para, int device = 0, int max_map_points = 0) {
+        if (h_) { pf_odom_destroy(h_); h_ = nullptr; }
+        pf_odom_params p{map_resolution_in, k_new_para, theta_p_para, theta_max_para, weightType_para, max_map_points, 0};
+        status_ = pf_odom_bpf_create(&p, device, &h_);
+        if (status_ != PF_OK) std::fprintf(stderr, "Odom_BPF_EstimationClass::init: %s\n", pf_last_error());
+    }
+
+    void initMapWithPoints(const Cloud::Ptr& beam_in, const Cloud::Ptr& pillar_in, const Cloud::Ptr& facade_in) {
+        if (!h_) return;
+        status_ = pf_odom_bpf_init_map(h_, data(beam_in), size(beam_in), data(pillar_in), size(pillar_in), data(facade_in), size(facade_in));
+        if (status_ != PF_OK) std::fprintf(stderr, "initMapWithPoints: %s\n", pf_last_error());
+    }
+
+    void updatePointsToMap(const Cloud::Ptr& beam_in, const Cloud::Ptr& pillar_in, const Cloud::Ptr& facade_in) {
+        if (!h_) return;
+        double pose[7];
+        status_ = pf_odom_bpf_update(h_, data(beam_in), size(beam_in), data(pillar_in), size(pillar_in), data(facade_in), size(facade_in), pose);
+        if (status_ != PF_OK) { std::fprintf(stderr, "updatePointsToMap: %s\n", pf_last_error()); return; }
+        std::memcpy(odom.q, pose, sizeof(double) * 4);
+        std::memcpy(odom.t, pose + 4, sizeof(double) * 3);
+    }
+
+    // *laserCloudMap += beam map; += pillar map; += facade map  (src/odomEstimationClass.cpp:683-689)
+    void getMap(Cloud::Ptr& laserCloudMap) {
+        if (!h_) return;
+        int total = 0, n = 0;
+        for (int which = 0; which < 3; ++which) { int m = 0; pf_odom_map_size(h_, which, &m); total += m; }
+        const size_t old = laserCloudMap->points.size();
+        laserCloudMap->points.resize(old + total);
+        status_ = pf_odom_get_map(h_, reinterpret_cast<pf_point*>(laserCloudMap->points.data() + old), total, &n);
+        laserCloudMap->points.resize(old + (status_ == PF_OK ? n : 0));
+    }
+
+    Cloud::Ptr laserCloudBeamMap() { return fetch(0); }
+    Cloud::Ptr laserCloudPillarMap() { return fetch(1); }
+    Cloud::Ptr laserCloudFacadeMap() { return fetch(2); }
+
+    OdomPose odom;
+    int status() const { return status_; }
+    pf_odom* handle() { return h_; }
+
+   private:
+    static const float* data(const Cloud::Ptr& c) { return reinterpret_cast<const float*>(c->points.data()); }
+    static int size(const Cloud::Ptr& c) { return (int)c->points.size(); }
+    Cloud::Ptr fetch(int which) {
+        Cloud::Ptr c(new Cloud());
+        if (!h_) return c;
+        int n = 0;
+        pf_odom_map_size(h_, which, &n);
+        c->points.resize(n > 0 ? n : 0);
+        if (n > 0) pf_odom_get_map_part(h_, which, reinterpret_cast<pf_point*>(c->points.data()), n, &n);
+        return c;
+    }
+    pf_odom* h_ = nullptr;
+    int status_ = PF_OK;
+};

@@ -239,3 +239,45 @@ class Mapping:
         out = np.empty((max(n, 1), 4), np.float32)
         lib().pforacle_mapping_get_map(self.h, _vp(out))
         return out[:n].copy()
+
+
+class OdomBPF:
+    """Restated Odom_BPF_EstimationClass (CPU): beam, pillar (line residuals) and facade (plane residuals)."""
+
+    def __init__(self, map_resolution=0.4, k_new=0, theta_p=0.4, theta_max=75, weight_type=0.0):
+        L = lib()
+        L.pforacle_bpf_create.restype = C.c_void_p
+        self.h = C.c_void_p(L.pforacle_bpf_create(C.c_double(map_resolution), k_new, C.c_float(theta_p), theta_max, C.c_double(weight_type)))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().pforacle_bpf_destroy(self.h)
+            self.h = None
+
+    def _frame(self, init, beam, pillar, facade):
+        a = [np.ascontiguousarray(x, np.float32).reshape(-1, 4) for x in (beam, pillar, facade)]
+        pose = np.zeros(7)
+        lib().pforacle_bpf_frame(self.h, init, _vp(a[0]), len(a[0]), _vp(a[1]), len(a[1]), _vp(a[2]), len(a[2]), _vp(pose))
+        return pose
+
+    def init_map(self, beam, pillar, facade):
+        self._frame(1, beam, pillar, facade)
+
+    def update(self, beam, pillar, facade):
+        return self._frame(0, beam, pillar, facade)
+
+    def get_map(self, which):
+        n = lib().pforacle_bpf_map_size(self.h, which)
+        out = np.empty(max(n, 1), POINT_DTYPE)
+        lib().pforacle_bpf_get_map(self.h, which, _vp(out))
+        return out[:n].copy()
+
+    def iter_poses(self):
+        out = np.zeros((16, 7))
+        n = lib().pforacle_bpf_iter_poses(self.h, _vp(out), 16)
+        return out[:n].copy()
+
+    def stats(self):
+        out = np.zeros(8, np.int32)
+        lib().pforacle_bpf_stats(self.h, _vp(out))
+        return dict(zip(("n_beam_ds", "n_pillar_ds", "n_facade_ds", "n_line_res", "n_plane_res", "passes", "lm_iterations"), out.tolist()))

@@ -919,6 +919,67 @@ struct OracleOdom {
     }
 };
 
+// ---------------------------------------------------------------------------------------------------------
+// Odom_BPF_EstimationClass (src/odomEstimationClass.cpp:649-1306): the same arithmetic over beam, pillar (line) and facade (plane)
+// ---------------------------------------------------------------------------------------------------------
+struct OracleOdomBPF {
+    double map_resolution; int k_new; float theta_p; int theta_max; double weightType;
+    double parameters[7] = {0, 0, 0, 1, 0, 0, 0};
+    Iso odom = iso_identity(), last_odom = iso_identity();
+    int optimization_count = 2;
+    std::vector<OPoint> map[3];      // beam, pillar, facade
+    std::vector<double> iter_poses;
+    int n_ds[3] = {0, 0, 0}, n_line_res = 0, n_plane_res = 0, lm_iterations = 0, passes = 0;
+
+    void init_map(const std::vector<OPoint> in[3]) {   // :692-698
+        for (int k = 0; k < 3; ++k) map[k].insert(map[k].end(), in[k].begin(), in[k].end());
+        optimization_count = 12;
+    }
+
+    void update(const std::vector<OPoint> in[3]) {     // :706-760
+        if (optimization_count > 2) optimization_count--;
+        Iso pred = iso_mul(odom, iso_mul(iso_inv(last_odom), odom));
+        last_odom = odom;
+        odom = pred;
+        Quat q = mat_to_quat(odom.R);
+        parameters[0] = q.x; parameters[1] = q.y; parameters[2] = q.z; parameters[3] = q.w;
+        parameters[4] = odom.t[0]; parameters[5] = odom.t[1]; parameters[6] = odom.t[2];
+        const int type[3] = {0, 0, 1};
+        const double leaf_mul[3] = {1, 1, 2};                                   // :658-660
+        std::vector<OPoint> D[3];
+        for (int k = 0; k < 3; ++k) { voxel_grid_pcl(in[k], (float)(map_resolution * leaf_mul[k]), D[k]); n_ds[k] = (int)D[k].size(); }
+        iter_poses.clear();
+        passes = 0;
+        if (map[0].size() > 10 && map[1].size() > 10 && map[2].size() > 50) {   // :720
+            KdTree tree[3];
+            for (int k = 0; k < 3; ++k) tree[k].build(map[k]);
+            for (int it = 0; it < optimization_count; ++it) {
+                std::vector<Residual> res;
+                for (int k = 0; k < 3; ++k)                                     // addBeam / addPillar / addFacadeCostFactor :733-735
+                    associate(type[k], TreeKnn{&tree[k]}, map[k], D[k], parameters, k_new, theta_p, theta_max, weightType, res, AssocOut{});
+                n_line_res = n_plane_res = 0;
+                for (const Residual& r : res) (r.kind == 0 ? n_line_res : n_plane_res) += 1;
+                LmInfo li = lm_solve(res, parameters);
+                lm_iterations = li.iterations;
+                iter_poses.insert(iter_poses.end(), parameters, parameters + 7);
+                ++passes;
+            }
+        }
+        Quat qf{parameters[0], parameters[1], parameters[2], parameters[3]};
+        quat_to_mat(qf, odom.R);
+        odom.t[0] = parameters[4]; odom.t[1] = parameters[5]; odom.t[2] = parameters[6];
+        V3 t{parameters[4], parameters[5], parameters[6]};
+        for (int k = 0; k < 3; ++k)                                              // addPointsToMap :1217-1295
+            for (const OPoint& p : D[k]) {
+                V3 w = rotate(qf, V3{(double)p.x, (double)p.y, (double)p.z}) + t;
+                OPoint o = p; o.x = (float)w.x; o.y = (float)w.y; o.z = (float)w.z; o.a = 255;
+                map[k].push_back(o);
+            }
+        double c[3] = {odom.t[0], odom.t[1], odom.t[2]};
+        for (int k = 0; k < 3; ++k) map_maintain(map[k], c, (float)map_resolution * (float)leaf_mul[k], k_new, theta_p, theta_max);
+    }
+};
+
 std::vector<OPoint> from_xyz4(const float* p, int n) {
     std::vector<OPoint> v(n);
     for (int i = 0; i < n; ++i) v[i] = {p[4 * i], p[4 * i + 1], p[4 * i + 2], 0, 0, 0, 255};   // copyPointCloud XYZI -> XYZRGB
@@ -1064,6 +1125,38 @@ int pforacle_odom_iter_poses(void* h, double* out, int cap) {
     std::memcpy(out, o->iter_poses.data(), sizeof(double) * 7 * n);
     return n;
 }
+void* pforacle_bpf_create(double map_resolution, int k_new, float theta_p, int theta_max, double weight_type) {
+    OracleOdomBPF* o = new OracleOdomBPF();
+    o->map_resolution = map_resolution; o->k_new = k_new; o->theta_p = theta_p; o->theta_max = theta_max; o->weightType = weight_type;
+    return o;
+}
+void pforacle_bpf_destroy(void* h) { delete (OracleOdomBPF*)h; }
+int pforacle_bpf_frame(void* h, int init, const float* beam, int nb, const float* pillar, int np, const float* facade, int nf, double pose_out[7]) {
+    OracleOdomBPF* o = (OracleOdomBPF*)h;
+    const std::vector<OPoint> in[3] = {from_xyz4(beam, nb), from_xyz4(pillar, np), from_xyz4(facade, nf)};
+    if (init) o->init_map(in); else o->update(in);
+    std::memcpy(pose_out, o->parameters, sizeof(double) * 7);
+    return 0;
+}
+int pforacle_bpf_map_size(void* h, int which) { return (int)((OracleOdomBPF*)h)->map[which].size(); }
+int pforacle_bpf_get_map(void* h, int which, OPoint* out) {
+    const std::vector<OPoint>& m = ((OracleOdomBPF*)h)->map[which];
+    std::memcpy(out, m.data(), m.size() * sizeof(OPoint));
+    return (int)m.size();
+}
+void pforacle_bpf_stats(void* h, int out[8]) {
+    OracleOdomBPF* o = (OracleOdomBPF*)h;
+    out[0] = o->n_ds[0]; out[1] = o->n_ds[1]; out[2] = o->n_ds[2]; out[3] = o->n_line_res; out[4] = o->n_plane_res;
+    out[5] = o->passes; out[6] = o->lm_iterations; out[7] = 0;
+}
+int pforacle_bpf_iter_poses(void* h, double* out, int cap) {
+    OracleOdomBPF* o = (OracleOdomBPF*)h;
+    int n = (int)o->iter_poses.size() / 7;
+    if (n > cap) n = cap;
+    std::memcpy(out, o->iter_poses.data(), sizeof(double) * 7 * n);
+    return n;
+}
+
 void pforacle_odom_stats(void* h, int out[8]) {
     OracleOdom* o = (OracleOdom*)h;
     out[0] = o->n_edge_ds; out[1] = o->n_surf_ds; out[2] = o->n_edge_res; out[3] = o->n_surf_res;

@@ -5,6 +5,7 @@ a ROS-free harness of the reference:
 
   LaserProcessingClass   /root/reference/include/laserProcessingClass.h:30-42
   Odom_ES_EstimationClass (alias OdomEstimationClass)   /root/reference/include/odomEstimationClass.h:140-167
+  Odom_BPF_EstimationClass  /root/reference/include/odomEstimationClass.h:169-205
   LaserMappingClass      /root/reference/include/laserMappingClass.h:32-58
   Lidar                  /root/reference/include/lidar.h:9-32
 
@@ -138,6 +139,42 @@ class Odom_ES_EstimationClass:
 
 
 OdomEstimationClass = Odom_ES_EstimationClass
+
+
+class Odom_BPF_EstimationClass(Odom_ES_EstimationClass):
+    """init / initMapWithPoints(beam, pillar, facade) / updatePointsToMap(beam, pillar, facade) / getMap
+    (/root/reference/include/odomEstimationClass.h:169-205); maps: laserCloudBeamMap, laserCloudPillarMap, laserCloudFacadeMap."""
+
+    def init(self, lidar_param, map_resolution, k_new, theta_p, theta_max, weightType=0.0):
+        self._od = capi.OdometryBPF(map_resolution, k_new, theta_p, theta_max, weightType, self._mm, self._mf, self._device)
+
+    def initMapWithPoints(self, beam_in, pillar_in, facade_in):
+        try:
+            self._od.init_map(beam_in, pillar_in, facade_in)
+            self.status = 0
+        except capi.PfError as e:
+            _report("initMapWithPoints", e)
+            self.status = e.status
+
+    def updatePointsToMap(self, beam_in, pillar_in, facade_in):
+        try:
+            self._set_pose(self._od.update(beam_in, pillar_in, facade_in))
+            self.status = 0
+        except capi.PfError as e:
+            _report("updatePointsToMap", e)
+            self.status = e.status
+
+    @property
+    def laserCloudBeamMap(self):
+        return self._od.map_part(0)
+
+    @property
+    def laserCloudPillarMap(self):
+        return self._od.map_part(1)
+
+    @property
+    def laserCloudFacadeMap(self):
+        return self._od.map_part(2)
 
 
 class LaserMappingClass:

@@ -350,6 +350,37 @@ class Odometry:
         return v.value
 
 
+class OdometryBPF(Odometry):
+    """Handle of pf_odom_bpf_* (replaces Odom_BPF_EstimationClass): beam / pillar / facade feature kinds."""
+
+    def __init__(self, map_resolution=0.4, k_new=0, theta_p=0.4, theta_max=75, weight_type=0.0, max_map_points=0, max_features=0,
+                 device=0):
+        self.prm = OdomParams(map_resolution, k_new, theta_p, theta_max, weight_type, max_map_points, max_features)
+        self.h = C.c_void_p()
+        check(lib().pf_odom_bpf_create(C.byref(self.prm), device, C.byref(self.h)))
+
+    def init_map(self, beam4, pillar4, facade4):
+        b, p, f = as_points(beam4), as_points(pillar4), as_points(facade4)
+        check(lib().pf_odom_bpf_init_map(self.h, _vp(b), len(b), _vp(p), len(p), _vp(f), len(f)))
+
+    def update(self, beam4, pillar4, facade4):
+        b, p, f = as_points(beam4), as_points(pillar4), as_points(facade4)
+        pose = np.zeros(7)
+        check(lib().pf_odom_bpf_update(self.h, _vp(b), len(b), _vp(p), len(p), _vp(f), len(f), _vp(pose)))
+        return pose
+
+    def get_map(self):
+        sizes = []
+        for which in range(3):
+            n = C.c_int()
+            check(lib().pf_odom_map_size(self.h, which, C.byref(n)))
+            sizes.append(n.value)
+        out = np.empty(max(sum(sizes), 1), POINT_DTYPE)
+        n = C.c_int()
+        check(lib().pf_odom_get_map(self.h, _vp(out), len(out), C.byref(n)))
+        return out[:n.value].copy()
+
+
 def pose_to_rt(pose7):
     """[qx qy qz qw tx ty tz] -> row-major 3x4 [R | t] (Eigen::Quaterniond::toRotationMatrix, double)."""
     x, y, z, w = (float(v) for v in pose7[:4])

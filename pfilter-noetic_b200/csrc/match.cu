@@ -24,7 +24,7 @@ __global__ void __launch_bounds__(256) k_assoc_match(AssocParams P) {
     if (P.weight_type != 0 && blockIdx.x == 0 && threadIdx.x < 4)     // min / max slots of this pass (read by k_assoc_persist, which follows)
         P.w_minmax[4 * kind + threadIdx.x] = (threadIdx.x & 1) ? 0ull : ~0ull;
     for (int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; q < nq; q += nwarps) {
-    const bool guard = P.min_edge_map == 0 || (*P.c[0].n_map > P.min_edge_map && *P.c[1].n_map > P.min_surf_map);   // :247
+    const bool guard = P.guard == nullptr || *P.guard != 0;   // :247
     unsigned flag = 0;
     if (guard) {
         const Pt qp = c.queries[q];
@@ -237,7 +237,7 @@ extern "C" int pf_associate(int device, int kind, pf_point* map, int m, pf_point
     P.c[1 - kind] = dead;
     P.pose = t.d_pose;
     P.k_new = k_new; P.theta_p = theta_p; P.theta_max = theta_max;
-    P.min_edge_map = 0; P.min_surf_map = 0;
+    P.guard = nullptr;
     P.weight_type = 0; P.w_minmax = nullptr;
     uint64_t launches = 0;
     PF_CHECK(associate_pass(t.stream, P, kind == 0 ? qc : 0, kind == 1 ? qc : 0, &launches));

@@ -25,7 +25,7 @@ struct AssocParams {
     AssocCloud c[2];       // 0 = edge (line fit), 1 = surf (plane fit)
     const double* pose;    // device [qx qy qz qw tx ty tz]
     int k_new; float theta_p; int theta_max;
-    int min_edge_map, min_surf_map;   // guard :247 (10 / 50); 0 disables (stage tap)
+    const int* guard;      // device flag: the maps hold enough points to associate (:247); null = always (stage tap)
     int weight_type;       // 0, 1, 2 or 12 (src/odomEstimationClass.cpp:389-423)
     unsigned long long* w_minmax;   // [2][4] per kind: min / max of observe, min / max of sparsity over the pass's residual blocks
                                     // (bit patterns of non-negative doubles: ordered as unsigned integers)

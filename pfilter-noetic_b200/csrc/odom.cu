@@ -9,6 +9,12 @@
 //   k_append         transform all down-sampled points with the final pose and append them to the maps      (:592-604)
 //   map_merge        CropBox + rgbds + extractstablepoint + r += 2 as a streaming merge (merge.cuh) (:606-647)
 // and finally copies the 7-double pose to the host.  Maps, counters and the pose stay in HBM between frames.
+//
+// The same machinery runs Odom_BPF_EstimationClass (include/odomEstimationClass.h:169-205, src/odomEstimationClass.cpp:649-1306),
+// the reference's second odometry class: identical arithmetic over three feature kinds -- beam and pillar (point-to-line, leaf
+// = map_resolution) and facade (point-to-plane, leaf = 2 x map_resolution).  The kernels process feature kinds in PAIRS (one
+// line-type + one plane-type cloud per launch, blockIdx.y); the ES path is one pair (edge, surf), the BPF path two pairs
+// (beam, facade) and (pillar, <empty>).
 #include <vector>
 
 #include "match.cuh"
@@ -24,12 +30,14 @@ struct IsoDev { double R[9]; double t[3]; };
 struct OdomShared {   // small device-resident block
     IsoDev odom, last_odom;
     double pose[7];        // pose of the last finished update (what the caller reads)
-    int n_app[2];          // map sizes after appending the new points
-    int err;               // bit 0: map capacity exceeded; bits 1..2: map merge (voxel coordinate range, exception capacity)
-    int pad;
-    int n_map[2];          // map sizes after the last update (read back with the pose: tight launch bounds for the next frame)
+    int n_app[4];          // map sizes after appending the new points (per kind slot)
+    int err;               // bit 0: map capacity exceeded; bits 1..3: map merge (voxel coordinate range, exception capacity, internal)
+    int guard;             // the maps hold enough points to associate (:247 / BPF :720)
+    int n_map[4];          // map sizes after the last update (read back with the pose: tight launch bounds for the next frame)
     long long frame;       // frame index this block describes
 };
+
+constexpr int kKinds = 4;     // kind slots of a handle: ES uses 0 (edge) 1 (surf); BPF 0 (beam) 1 (pillar) 2 (facade); slot 3 stays empty
 
 __global__ void k_odom_reset(OdomShared* sh, LmState* S) {
     if (threadIdx.x != 0) return;
@@ -37,14 +45,22 @@ __global__ void k_odom_reset(OdomShared* sh, LmState* S) {
     for (int i = 0; i < 3; ++i) { sh->odom.t[i] = 0; sh->last_odom.t[i] = 0; }
     const double id[7] = {0, 0, 0, 1, 0, 0, 0};
     for (int i = 0; i < 7; ++i) { sh->pose[i] = id[i]; S->x[i] = id[i]; }
-    sh->n_app[0] = sh->n_app[1] = 0;
+    for (int k = 0; k < 4; ++k) { sh->n_app[k] = 0; sh->n_map[k] = 0; }
     sh->err = 0;
+    sh->guard = 0;
 }
 
 // odom_prediction = odom * (last_odom.inverse() * odom); last_odom = odom; odom = prediction;
 // q_w_curr = Quaterniond(odom.rotation()); t_w_curr = odom.translation()                     (:235-240)
-__global__ void k_predict(OdomShared* sh, LmState* S) {
+struct GuardSpec { const int* n_map[3]; int min_pts[3]; int count; };
+
+__global__ void k_predict(OdomShared* sh, LmState* S, GuardSpec G) {
     if (threadIdx.x != 0) return;
+    {   // laserCloudCornerMap->points.size() > 10 && laserCloudSurfMap->points.size() > 50 (:247); BPF: beam, pillar > 10, facade > 50 (:720)
+        int ok = 1;
+        for (int k = 0; k < G.count; ++k) ok &= (*G.n_map[k] > G.min_pts[k]) ? 1 : 0;
+        sh->guard = ok;
+    }
     const IsoDev a = sh->odom, l = sh->last_odom;
     IsoDev li, m, p;
     for (int i = 0; i < 3; ++i)
@@ -72,6 +88,8 @@ constexpr int kMergeExcCap = 4096;   // centroids per update that may leave thei
 struct AppendParams {
     const Pt* ds[2]; const int* n_ds[2];
     Pt* map[2]; const int* n_map[2];
+    int slot[2];      // kind slots of the pair (index into OdomShared::n_app)
+    int write_pose;   // first pair of the frame: publish the pose
     OdomShared* sh; const LmState* S;
     int map_cap;      // capacity of the map buffers (points)
     double* pose_hist; int hist_slot;
@@ -87,8 +105,8 @@ __global__ void __launch_bounds__(256) k_append(AppendParams A) {
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         int tot = m + n;
         if (tot > A.map_cap) { atomicOr(&A.sh->err, 1); tot = A.map_cap; }
-        A.sh->n_app[kind] = tot;
-        if (kind == 0) {
+        A.sh->n_app[A.slot[kind]] = tot;
+        if (kind == 0 && A.write_pose) {
             quat_to_mat(s_pose, A.sh->odom.R);
             for (int i = 0; i < 3; ++i) A.sh->odom.t[i] = s_pose[4 + i];
             for (int i = 0; i < 7; ++i) { A.sh->pose[i] = s_pose[i]; A.pose_hist[7 * A.hist_slot + i] = s_pose[i]; }
@@ -105,14 +123,14 @@ __global__ void __launch_bounds__(256) k_append(AppendParams A) {
     }
 }
 
-struct InitParams { const float4* feat[2]; const int* n_feat[2]; Pt* map[2]; int* n_map[2]; int* n_sorted[2]; int map_cap; OdomShared* sh; };
+struct InitParams { const float4* feat[2]; const int* n_feat[2]; Pt* map[2]; int* n_map[2]; int* n_sorted[2]; int slot[2]; int map_cap; OdomShared* sh; };
 
 // initMapWithPoints (:217-222): the raw first-frame clouds become the maps
 __global__ void __launch_bounds__(256) k_init_map(InitParams I) {
     const int kind = blockIdx.y;
     int n = *I.n_feat[kind];
     if (n > I.map_cap) { n = I.map_cap; if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(&I.sh->err, 1); }
-    if (blockIdx.x == 0 && threadIdx.x == 0) { *I.n_map[kind] = n; *I.n_sorted[kind] = 0; I.sh->n_map[kind] = n; I.sh->frame = 0; }
+    if (blockIdx.x == 0 && threadIdx.x == 0) { *I.n_map[kind] = n; *I.n_sorted[kind] = 0; I.sh->n_map[I.slot[kind]] = n; I.sh->frame = 0; }
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const float4 f = I.feat[kind][i];
         Pt o;
@@ -121,12 +139,13 @@ __global__ void __launch_bounds__(256) k_init_map(InitParams I) {
     }
 }
 
-__global__ void k_check_map_cap(const int* n_map0, const int* n_map1, int cap, OdomShared* sh, long long frame, const unsigned* merge_err) {
+__global__ void k_check_map_cap(const int* n_map0, const int* n_map1, int slot0, int slot1, int cap, OdomShared* sh, long long frame,
+                                const unsigned* merge_err) {
     if (threadIdx.x != 0) return;
     if (*n_map0 > cap || *n_map1 > cap) atomicOr(&sh->err, 1);
-    if (*merge_err) atomicOr(&sh->err, (int)(*merge_err & 14u));
-    sh->n_map[0] = *n_map0;
-    sh->n_map[1] = *n_map1;
+    if (*merge_err) atomicOr(&sh->err, (int)(*merge_err & 30u));
+    sh->n_map[slot0] = *n_map0;
+    sh->n_map[slot1] = *n_map1;
     sh->frame = frame;
 }
 
@@ -145,24 +164,31 @@ struct pf_odom {
     cudaEvent_t ev = nullptr, ev_done = nullptr;
     pf_odom_params prm{};
     int fcap = 0, mcap = 0, bufcap = 0;
+    // feature kinds and the pairs they are processed in
+    int nk = 2;                          // live kinds: 2 (ES: edge, surf) or 3 (BPF: beam, pillar, facade)
+    int type[kKinds] = {0, 1, 0, 0};     // 0 point-to-line, 1 point-to-plane
+    int leaf_mul[kKinds] = {1, 2, 1, 1}; // leaf = map_resolution x this (:189-190, :658-660)
+    int min_map[kKinds] = {10, 50, 0, 0};// guard thresholds (:247, :720)
+    int npairs = 1;
+    int pair[2][2] = {{0, 1}, {0, 0}};   // [pair] = {line-type kind, plane-type kind}; the null kind (kKinds - 1) stands in for "none"
     Workspace ws;
-    float4* d_feat[2] = {nullptr, nullptr};
-    int* d_nfeat = nullptr;              // [2]
-    Pt* d_ds[2] = {nullptr, nullptr};
-    int* d_nds = nullptr;                // [2]
-    Pt* d_map[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // [buffer][kind]
-    int* d_nmap[2] = {nullptr, nullptr}; // [buffer] -> 4 ints: n_map[kind], n_sorted[kind] (merge.cuh: sorted prefix of the map)
+    float4* d_feat[kKinds] = {};
+    int* d_nfeat = nullptr;              // [kKinds]
+    Pt* d_ds[kKinds] = {};
+    int* d_nds = nullptr;                // [kKinds]
+    Pt* d_map[2][kKinds] = {};           // [buffer][kind]
+    int* d_nmap[2] = {nullptr, nullptr}; // [buffer] -> 2 * kKinds ints: n_map[kind], then n_sorted[kind] (merge.cuh: sorted prefix)
     MapMergeScratch msc{};
     bool sorted_known = false;           // false until the first update after init: the raw first-frame maps are unsorted
     int cur = 0;
-    float4* d_gpts[2] = {nullptr, nullptr};
-    int *d_cs[2] = {nullptr, nullptr}, *d_ce[2] = {nullptr, nullptr}, *d_geom = nullptr;
-    int *d_head[2] = {nullptr, nullptr}, *d_hits[2] = {nullptr, nullptr}, *d_next[2] = {nullptr, nullptr}, *d_nn[2] = {nullptr, nullptr};
-    uint8_t* d_flag[2] = {nullptr, nullptr};
-    double* d_g8[2] = {nullptr, nullptr};
-    float* d_wobs[2] = {nullptr, nullptr};           // residual weights (weightType 1 / 2 / 12)
-    double* d_wspa[2] = {nullptr, nullptr};
-    unsigned long long* d_wminmax = nullptr;         // [2][4]
+    float4* d_gpts[kKinds] = {};
+    int *d_cs[kKinds] = {}, *d_ce[kKinds] = {}, *d_geom = nullptr;
+    int *d_head[kKinds] = {}, *d_hits[kKinds] = {}, *d_next[kKinds] = {}, *d_nn[kKinds] = {};
+    uint8_t* d_flag[kKinds] = {};
+    double* d_g8[kKinds] = {};
+    float* d_wobs[kKinds] = {};          // residual weights (weightType 1 / 2 / 12)
+    double* d_wspa[kKinds] = {};
+    unsigned long long* d_wminmax = nullptr;   // [kKinds][4]
     LmState* d_state = nullptr;
     double* d_iter_poses = nullptr;
     OdomShared* d_sh = nullptr;
@@ -171,57 +197,67 @@ struct pf_odom {
     // pinned host mirrors
     OdomShared* h_sh = nullptr;
     LmState* h_state = nullptr;
-    int* h_counts = nullptr;             // [8]
+    int* h_counts = nullptr;             // [16]
     double* h_iter = nullptr;            // [16*7]
     bool inited = false;
     int optimization_count = 2;          // :198
     int last_passes = 0;
     // host-side upper bounds of the device-resident counts (launch geometry only; the kernels read the exact counts)
-    int map_ub[2] = {0, 0};
+    int map_ub[kKinds] = {};
     static constexpr int kRing = 32;
     OdomShared* h_ring = nullptr;        // pinned [kRing]: asynchronous read-back of the shared block after every frame
     cudaEvent_t ring_ev[kRing] = {};
     long long ring_frame[kRing] = {};
-    int ring_add[kRing][2] = {};
+    int ring_add[kRing][kKinds] = {};
     long long ring_head = 0;             // frames recorded in the ring
     long long known_frame = -1;          // newest frame whose exact map sizes have been folded into map_ub
     // optional phase timing (PF_ODOM_TIMING=1): CUDA events at the phase boundaries of the last update
     bool timing = false;
     cudaEvent_t tev[8] = {};
     float phase_ms[8] = {};
+    int cap_of(int k) const { return k == kKinds - 1 ? 16 : 0; }   // the null kind gets token buffers
 };
 
 namespace {
 
+constexpr int kNull = kKinds - 1;
+
 int odom_alloc(pf_odom* h) {
     const int fcap = h->fcap, bufcap = h->bufcap;
     PF_CHECK(workspace_create(h->ws, 2 * bufcap, h->stream));
-    PF_CUDA(cudaMalloc(&h->d_nfeat, sizeof(int) * 2));
-    PF_CUDA(cudaMalloc(&h->d_nds, sizeof(int) * 2));
-    PF_CUDA(cudaMalloc(&h->d_geom, sizeof(int) * 12));
-    for (int k = 0; k < 2; ++k) {
-        PF_CUDA(cudaMalloc(&h->d_feat[k], sizeof(float4) * fcap));
-        PF_CUDA(cudaMalloc(&h->d_ds[k], sizeof(Pt) * fcap));
-        for (int b = 0; b < 2; ++b) PF_CUDA(cudaMalloc(&h->d_map[b][k], sizeof(Pt) * bufcap));
-        PF_CUDA(cudaMalloc(&h->d_nmap[k], sizeof(int) * 4));
-        PF_CUDA(cudaMemset(h->d_nmap[k], 0, sizeof(int) * 4));
-        PF_CUDA(cudaMalloc(&h->d_gpts[k], sizeof(float4) * bufcap));
-        PF_CUDA(cudaMalloc(&h->d_cs[k], sizeof(int) * (size_t)kGridCellCap));
-        PF_CUDA(cudaMalloc(&h->d_ce[k], sizeof(int) * (size_t)kGridCellCap));
-        PF_CUDA(cudaMalloc(&h->d_head[k], sizeof(int) * bufcap));
-        PF_CUDA(cudaMalloc(&h->d_hits[k], sizeof(int) * bufcap));
-        PF_CUDA(cudaMemset(h->d_head[k], 0xff, sizeof(int) * bufcap));
-        PF_CUDA(cudaMemset(h->d_hits[k], 0, sizeof(int) * bufcap));
-        PF_CUDA(cudaMalloc(&h->d_next[k], sizeof(int) * 5 * fcap));
-        PF_CUDA(cudaMalloc(&h->d_nn[k], sizeof(int) * 5 * fcap));
-        PF_CUDA(cudaMalloc(&h->d_flag[k], fcap));
-        PF_CUDA(cudaMemset(h->d_flag[k], 0, fcap));
-        PF_CUDA(cudaMalloc(&h->d_g8[k], sizeof(double) * 8 * fcap));
-        PF_CUDA(cudaMalloc(&h->d_wobs[k], sizeof(float) * fcap));
-        PF_CUDA(cudaMalloc(&h->d_wspa[k], sizeof(double) * fcap));
+    PF_CUDA(cudaMalloc(&h->d_nfeat, sizeof(int) * kKinds));
+    PF_CUDA(cudaMalloc(&h->d_nds, sizeof(int) * kKinds));
+    PF_CUDA(cudaMemset(h->d_nfeat, 0, sizeof(int) * kKinds));
+    PF_CUDA(cudaMemset(h->d_nds, 0, sizeof(int) * kKinds));
+    PF_CUDA(cudaMalloc(&h->d_geom, sizeof(int) * 6 * kKinds));
+    for (int b = 0; b < 2; ++b) {
+        PF_CUDA(cudaMalloc(&h->d_nmap[b], sizeof(int) * 2 * kKinds));
+        PF_CUDA(cudaMemset(h->d_nmap[b], 0, sizeof(int) * 2 * kKinds));
     }
-    PF_CUDA(cudaMalloc(&h->d_wminmax, sizeof(unsigned long long) * 8));
-    PF_CUDA(cudaMemset(h->d_wminmax, 0, sizeof(unsigned long long) * 8));
+    for (int k = 0; k < kKinds; ++k) {
+        if (k >= h->nk && k != kNull) continue;
+        const int fc = k == kNull ? 16 : fcap, bc = k == kNull ? 16 : bufcap;
+        PF_CUDA(cudaMalloc(&h->d_feat[k], sizeof(float4) * fc));
+        PF_CUDA(cudaMalloc(&h->d_ds[k], sizeof(Pt) * fc));
+        for (int b = 0; b < 2; ++b) PF_CUDA(cudaMalloc(&h->d_map[b][k], sizeof(Pt) * bc));
+        PF_CUDA(cudaMalloc(&h->d_gpts[k], sizeof(float4) * bc));
+        const size_t cells = k == kNull ? 16 : (size_t)kGridCellCap;
+        PF_CUDA(cudaMalloc(&h->d_cs[k], sizeof(int) * cells));
+        PF_CUDA(cudaMalloc(&h->d_ce[k], sizeof(int) * cells));
+        PF_CUDA(cudaMalloc(&h->d_head[k], sizeof(int) * bc));
+        PF_CUDA(cudaMalloc(&h->d_hits[k], sizeof(int) * bc));
+        PF_CUDA(cudaMemset(h->d_head[k], 0xff, sizeof(int) * bc));
+        PF_CUDA(cudaMemset(h->d_hits[k], 0, sizeof(int) * bc));
+        PF_CUDA(cudaMalloc(&h->d_next[k], sizeof(int) * 5 * fc));
+        PF_CUDA(cudaMalloc(&h->d_nn[k], sizeof(int) * 5 * fc));
+        PF_CUDA(cudaMalloc(&h->d_flag[k], fc));
+        PF_CUDA(cudaMemset(h->d_flag[k], 0, fc));
+        PF_CUDA(cudaMalloc(&h->d_g8[k], sizeof(double) * 8 * fc));
+        PF_CUDA(cudaMalloc(&h->d_wobs[k], sizeof(float) * fc));
+        PF_CUDA(cudaMalloc(&h->d_wspa[k], sizeof(double) * fc));
+    }
+    PF_CUDA(cudaMalloc(&h->d_wminmax, sizeof(unsigned long long) * 4 * kKinds));
+    PF_CUDA(cudaMemset(h->d_wminmax, 0, sizeof(unsigned long long) * 4 * kKinds));
     PF_CHECK(map_merge_scratch_create(h->msc, 2 * fcap + kMergeExcCap, kMergeExcCap, bufcap));
     PF_CUDA(cudaMalloc(&h->d_state, sizeof(LmState)));
     PF_CUDA(cudaMemset(h->d_state, 0, sizeof(LmState)));
@@ -232,7 +268,7 @@ int odom_alloc(pf_odom* h) {
     PF_CUDA(cudaMemset(h->d_pose_hist, 0, sizeof(double) * 7 * kPoseHist));
     PF_CUDA(cudaMallocHost(&h->h_sh, sizeof(OdomShared)));
     PF_CUDA(cudaMallocHost(&h->h_state, sizeof(LmState)));
-    PF_CUDA(cudaMallocHost(&h->h_counts, sizeof(int) * 8));
+    PF_CUDA(cudaMallocHost(&h->h_counts, sizeof(int) * 16));
     PF_CUDA(cudaMallocHost(&h->h_iter, sizeof(double) * 16 * 7));
     PF_CUDA(cudaMallocHost(&h->h_ring, sizeof(OdomShared) * pf_odom::kRing));
     h->timing = getenv("PF_ODOM_TIMING") != nullptr;
@@ -243,23 +279,26 @@ int odom_alloc(pf_odom* h) {
     return PF_OK;
 }
 
-int upload_features(pf_odom* h, const float* edge, int ne, const float* surf, int ns) {
-    PF_REQUIRE(ne >= 0 && ns >= 0 && (edge || ne == 0) && (surf || ns == 0), "bad feature arrays");
-    PF_REQUIRE(ne <= h->fcap && ns <= h->fcap, "feature cloud (%d / %d points) exceeds max_features %d", ne, ns, h->fcap);
-    h->h_counts[0] = ne; h->h_counts[1] = ns;
-    PF_CUDA(cudaMemcpyAsync(h->d_nfeat, h->h_counts, sizeof(int) * 2, cudaMemcpyHostToDevice, h->stream));
-    if (ne) PF_CUDA(cudaMemcpyAsync(h->d_feat[0], edge, sizeof(float4) * ne, cudaMemcpyHostToDevice, h->stream));
-    if (ns) PF_CUDA(cudaMemcpyAsync(h->d_feat[1], surf, sizeof(float4) * ns, cudaMemcpyHostToDevice, h->stream));
+int upload_features(pf_odom* h, const float* const feat[], const int n[]) {
+    for (int k = 0; k < h->nk; ++k) {
+        PF_REQUIRE(n[k] >= 0 && (feat[k] || n[k] == 0), "bad feature arrays");
+        PF_REQUIRE(n[k] <= h->fcap, "feature cloud of %d points exceeds max_features %d", n[k], h->fcap);
+        h->h_counts[k] = n[k];
+    }
+    for (int k = h->nk; k < kKinds; ++k) h->h_counts[k] = 0;
+    PF_CUDA(cudaMemcpyAsync(h->d_nfeat, h->h_counts, sizeof(int) * kKinds, cudaMemcpyHostToDevice, h->stream));
+    for (int k = 0; k < h->nk; ++k)
+        if (n[k]) PF_CUDA(cudaMemcpyAsync(h->d_feat[k], feat[k], sizeof(float4) * n[k], cudaMemcpyHostToDevice, h->stream));
     return PF_OK;
 }
 
 // asynchronous read-back of the shared block: lets later frames size their launches from exact map counts
-int ring_record(pf_odom* h, int add_e, int add_s) {
+int ring_record(pf_odom* h, const int add[kKinds]) {
     const int slot = (int)(h->ring_head % pf_odom::kRing);
     PF_CUDA(cudaMemcpyAsync(h->h_ring + slot, h->d_sh, sizeof(OdomShared), cudaMemcpyDeviceToHost, h->stream));
     PF_CUDA(cudaEventRecord(h->ring_ev[slot], h->stream));
     h->ring_frame[slot] = h->frame;
-    h->ring_add[slot][0] = add_e; h->ring_add[slot][1] = add_s;
+    for (int k = 0; k < kKinds; ++k) h->ring_add[slot][k] = add[k];
     h->ring_head += 1;
     return PF_OK;
 }
@@ -271,48 +310,63 @@ void ring_refresh(pf_odom* h) {
         const int slot = (int)(i % pf_odom::kRing);
         if (h->ring_frame[slot] <= h->known_frame) break;
         if (cudaEventQuery(h->ring_ev[slot]) != cudaSuccess) continue;
-        int ub[2] = {h->h_ring[slot].n_map[0], h->h_ring[slot].n_map[1]};
+        int ub[kKinds];
+        for (int k = 0; k < kKinds; ++k) ub[k] = h->h_ring[slot].n_map[k];
         for (long long j = i + 1; j < h->ring_head; ++j) {
             const int sj = (int)(j % pf_odom::kRing);
-            ub[0] += h->ring_add[sj][0]; ub[1] += h->ring_add[sj][1];
+            for (int k = 0; k < kKinds; ++k) ub[k] += h->ring_add[sj][k];
         }
-        for (int k = 0; k < 2; ++k) h->map_ub[k] = ub[k] < h->bufcap ? ub[k] : h->bufcap;
+        for (int k = 0; k < kKinds; ++k) h->map_ub[k] = ub[k] < h->bufcap ? ub[k] : h->bufcap;
         h->known_frame = h->ring_frame[slot];
         break;
     }
     cudaGetLastError();   // cudaErrorNotReady from the queries is not an error
 }
 
-int enqueue_init(pf_odom* h, const float4* const feat[2], const int* const n_feat[2], int ub_e, int ub_s) {
-    InitParams I{};
-    for (int k = 0; k < 2; ++k) {
-        I.feat[k] = feat[k]; I.n_feat[k] = n_feat[k]; I.map[k] = h->d_map[h->cur][k];
-        I.n_map[k] = h->d_nmap[h->cur] + k; I.n_sorted[k] = h->d_nmap[h->cur] + 2 + k;
+// feat / n_feat / ub are indexed by kind slot; unused slots may be null
+int enqueue_init(pf_odom* h, const float4* const feat[kKinds], const int* const n_feat[kKinds], const int ub[kKinds]) {
+    for (int p = 0; p < h->npairs; ++p) {
+        InitParams I{};
+        for (int j = 0; j < 2; ++j) {
+            const int k = h->pair[p][j];
+            I.feat[j] = k == kNull ? h->d_feat[kNull] : feat[k];
+            I.n_feat[j] = k == kNull ? h->d_nfeat + kNull : n_feat[k];
+            I.map[j] = h->d_map[h->cur][k];
+            I.n_map[j] = h->d_nmap[h->cur] + k; I.n_sorted[j] = h->d_nmap[h->cur] + kKinds + k;
+            I.slot[j] = k;
+        }
+        I.map_cap = h->mcap;
+        I.sh = h->d_sh;
+        k_init_map<<<dim3(2 * kSMs, 2), 256, 0, h->stream>>>(I);
+        h->ws.launches += 1;
     }
-    I.map_cap = h->mcap;
-    I.sh = h->d_sh;
-    k_init_map<<<dim3(2 * kSMs, 2), 256, 0, h->stream>>>(I);
-    h->ws.launches += 1;
     PF_CUDA(cudaGetLastError());
     h->optimization_count = 12;   // :221
     h->inited = true;
     h->sorted_known = false;
-    h->map_ub[0] = ub_e < h->mcap ? ub_e : h->mcap;
-    h->map_ub[1] = ub_s < h->mcap ? ub_s : h->mcap;
+    for (int k = 0; k < kKinds; ++k) h->map_ub[k] = k < h->nk ? (ub[k] < h->mcap ? ub[k] : h->mcap) : 0;
     h->frame = 0;
-    PF_CHECK(ring_record(h, 0, 0));
+    const int none[kKinds] = {0, 0, 0, 0};
+    PF_CHECK(ring_record(h, none));
     h->frame = 1;
     return PF_OK;
 }
 
-int enqueue_update(pf_odom* h, const float4* const feat[2], const int* const n_feat[2], int ub_e, int ub_s) {
+int enqueue_update(pf_odom* h, const float4* const feat_in[kKinds], const int* const n_feat_in[kKinds], const int ub_in[kKinds]) {
     if (h->optimization_count > 2) h->optimization_count--;   // :232-233
     ring_refresh(h);
-    if (ub_e > h->fcap) ub_e = h->fcap;
-    if (ub_s > h->fcap) ub_s = h->fcap;
-    if (ub_e < 1) ub_e = 1;
-    if (ub_s < 1) ub_s = 1;
-    const int mub_e = h->map_ub[0] > 1 ? h->map_ub[0] : 1, mub_s = h->map_ub[1] > 1 ? h->map_ub[1] : 1;
+    const float4* feat[kKinds];
+    const int* n_feat[kKinds];
+    int ub[kKinds], mub[kKinds];
+    for (int k = 0; k < kKinds; ++k) {
+        const bool live = k < h->nk;
+        feat[k] = live ? feat_in[k] : h->d_feat[kNull];
+        n_feat[k] = live ? n_feat_in[k] : h->d_nfeat + kNull;
+        ub[k] = live ? ub_in[k] : 0;
+        if (ub[k] > h->fcap) ub[k] = h->fcap;
+        if (live && ub[k] < 1) ub[k] = 1;
+        mub[k] = live ? (h->map_ub[k] > 1 ? h->map_ub[k] : 1) : 0;
+    }
     const int passes = h->optimization_count;
     h->last_passes = passes;
     Workspace& ws = h->ws;
@@ -320,75 +374,119 @@ int enqueue_update(pf_odom* h, const float4* const feat[2], const int* const n_f
     auto mark = [&](int i) { if (h->timing) cudaEventRecord(h->tev[i], h->stream); };
     mark(0);
     PF_CHECK(workspace_begin_step(ws));
-    k_predict<<<1, 32, 0, h->stream>>>(h->d_sh, h->d_state);
-    ws.launches += 1;
+    {
+        GuardSpec G{};
+        G.count = h->nk;
+        for (int k = 0; k < h->nk; ++k) { G.n_map[k] = h->d_nmap[cur] + k; G.min_pts[k] = h->min_map[k]; }
+        k_predict<<<1, 32, 0, h->stream>>>(h->d_sh, h->d_state, G);
+        ws.launches += 1;
+    }
     // VoxelGrid down-sampling, leaf sizes as set by init (:189-190): setLeafSize takes floats
-    VoxParams V{};
-    V.mode = VOX_PCL;
-    const float leaf[2] = {(float)h->prm.map_resolution, (float)(h->prm.map_resolution * 2)};
-    for (int k = 0; k < 2; ++k)
-        V.c[k] = VoxCloud{reinterpret_cast<const Pt*>(feat[k]), n_feat[k], h->d_ds[k], h->d_nds + k, leaf[k], 1};
-    PF_CHECK(voxelize(ws, V, 0, ub_e, ub_s));
+    for (int p = 0; p < h->npairs; ++p) {
+        VoxParams V{};
+        V.mode = VOX_PCL;
+        for (int j = 0; j < 2; ++j) {
+            const int k = h->pair[p][j];
+            V.c[j] = VoxCloud{reinterpret_cast<const Pt*>(feat[k]), n_feat[k], h->d_ds[k], h->d_nds + k,
+                              (float)(h->prm.map_resolution * h->leaf_mul[k]), 1};
+        }
+        PF_CHECK(voxelize(ws, V, p, ub[h->pair[p][0]], ub[h->pair[p][1]]));
+    }
     mark(1);
     // search grids over the current maps
-    GridBuild G{};
-    for (int k = 0; k < 2; ++k) {
-        G.map[k] = h->d_map[cur][k]; G.n_map[k] = h->d_nmap[cur] + k; G.pts[k] = h->d_gpts[k];
-        G.cell_start[k] = h->d_cs[k]; G.cell_end[k] = h->d_ce[k]; G.geom[k] = h->d_geom + 6 * k;
+    for (int p = 0; p < h->npairs; ++p) {
+        if (p > 0) PF_CHECK(workspace_begin_step(ws));      // the second pair reuses the tickets and state slots
+        GridBuild G{};
+        for (int j = 0; j < 2; ++j) {
+            const int k = h->pair[p][j];
+            G.map[j] = h->d_map[cur][k]; G.n_map[j] = h->d_nmap[cur] + k; G.pts[j] = h->d_gpts[k];
+            G.cell_start[j] = h->d_cs[k]; G.cell_end[j] = h->d_ce[k]; G.geom[j] = h->d_geom + 6 * k;
+        }
+        PF_CHECK(build_grids(ws, G, 2, mub[h->pair[p][0]], mub[h->pair[p][1]]));
     }
-    PF_CHECK(build_grids(ws, G, 2, mub_e, mub_s));
     mark(2);
     // optimisation passes
-    AssocParams A{};
+    AssocParams A[2]{};
     LmParams L{};
-    for (int k = 0; k < 2; ++k) {
-        A.c[k] = AssocCloud{h->d_ds[k], h->d_nds + k, h->d_map[cur][k], h->d_nmap[cur] + k,
-                            KnnGrid{h->d_gpts[k], h->d_cs[k], h->d_ce[k], h->d_geom + 6 * k},
-                            h->d_head[k], h->d_hits[k], h->d_next[k], h->d_nn[k], h->d_flag[k], h->d_g8[k], h->d_wobs[k], h->d_wspa[k]};
-        L.src[k] = ResidualSrc{h->d_ds[k], nullptr, h->d_flag[k], h->d_g8[k], h->d_nds + k, h->d_wobs[k], h->d_wspa[k]};
+    for (int p = 0; p < h->npairs; ++p) {
+        for (int j = 0; j < 2; ++j) {
+            const int k = h->pair[p][j];
+            A[p].c[j] = AssocCloud{h->d_ds[k], h->d_nds + k, h->d_map[cur][k], h->d_nmap[cur] + k,
+                                   KnnGrid{h->d_gpts[k], h->d_cs[k], h->d_ce[k], h->d_geom + 6 * k},
+                                   h->d_head[k], h->d_hits[k], h->d_next[k], h->d_nn[k], h->d_flag[k], h->d_g8[k], h->d_wobs[k], h->d_wspa[k]};
+        }
+        A[p].pose = h->d_state->x;
+        A[p].k_new = h->prm.k_new; A[p].theta_p = h->prm.theta_p; A[p].theta_max = h->prm.theta_max;
+        A[p].guard = &h->d_sh->guard;
+        A[p].weight_type = (int)h->prm.weight_type;
+        A[p].w_minmax = h->d_wminmax + 8 * p;           // [2][4] of this pair
     }
-    A.pose = h->d_state->x;
-    A.k_new = h->prm.k_new; A.theta_p = h->prm.theta_p; A.theta_max = h->prm.theta_max;
-    A.min_edge_map = 10; A.min_surf_map = 50;   // :247
-    A.weight_type = (int)h->prm.weight_type; A.w_minmax = h->d_wminmax;
-    L.weight_type = (int)h->prm.weight_type; L.w_minmax = h->d_wminmax;
+    // residual blocks in the order the reference adds them: kinds 0, 1, (2)
+    int ub_src[kLmMaxSrc] = {0, 0, 0};
+    L.nsrc = h->nk;
+    for (int k = 0; k < h->nk; ++k) {
+        int pp = 0, jj = 0;
+        for (int p = 0; p < h->npairs; ++p)
+            for (int j = 0; j < 2; ++j)
+                if (h->pair[p][j] == k) { pp = p; jj = j; }
+        L.src[k] = ResidualSrc{h->type[k], h->d_ds[k], nullptr, h->d_flag[k], h->d_g8[k], h->d_nds + k, h->d_wobs[k], h->d_wspa[k],
+                               h->d_wminmax + 8 * pp + 4 * jj};
+        ub_src[k] = ub[k];
+    }
     L.state = h->d_state; L.iter_poses = h->d_iter_poses; L.eval_only = 0;
+    L.weight_type = (int)h->prm.weight_type;
     for (int it = 0; it < passes; ++it) {
-        PF_CHECK(associate_pass(h->stream, A, ub_e, ub_s, &ws.launches));
+        for (int p = 0; p < h->npairs; ++p) PF_CHECK(associate_pass(h->stream, A[p], ub[h->pair[p][0]], ub[h->pair[p][1]], &ws.launches));
         if (it == passes - 1) mark(3);
-        PF_CHECK(lm_solve(h->stream, L, nullptr, it == 0, &ws.launches, ub_e, ub_s));
+        PF_CHECK(lm_solve(h->stream, L, nullptr, it == 0, &ws.launches, ub_src));
     }
     mark(4);
     // append + map maintenance
-    AppendParams P{};
-    for (int k = 0; k < 2; ++k) { P.ds[k] = h->d_ds[k]; P.n_ds[k] = h->d_nds + k; P.map[k] = h->d_map[cur][k]; P.n_map[k] = h->d_nmap[cur] + k; }
-    P.sh = h->d_sh; P.S = h->d_state; P.map_cap = h->bufcap;
-    P.pose_hist = h->d_pose_hist; P.hist_slot = (int)(h->frame % kPoseHist);
-    k_append<<<dim3(kSMs, 2), 256, 0, h->stream>>>(P);
-    ws.launches += 1;
-    // rgbds(tmpSurf, map_resolution * 2) / rgbds(tmpCorner, map_resolution) with the float member map_resolution (:625-626)
-    const float mres = (float)h->prm.map_resolution;
-    const float mleaf[2] = {mres, mres * 2};
-    MapMergeParams M{};
-    for (int k = 0; k < 2; ++k)
-        M.c[k] = MapMergeCloud{h->d_map[cur][k], h->d_nmap[cur] + 2 + k, h->d_sh->n_app + k, h->d_map[nxt][k], h->d_nmap[nxt] + k,
-                               h->d_nmap[nxt] + 2 + k, mleaf[k]};
-    M.center = h->d_sh->odom.t;
-    M.k_new = h->prm.k_new; M.theta_p = h->prm.theta_p; M.theta_max = h->prm.theta_max;
-    M.s = h->msc;
-    const int app_e = mub_e + ub_e < h->bufcap ? mub_e + ub_e : h->bufcap, app_s = mub_s + ub_s < h->bufcap ? mub_s + ub_s : h->bufcap;
-    // unsorted part: everything on the first update (raw first-frame maps), later last update's exceptions + this frame's points
-    const int capb_e = h->sorted_known ? (kMergeExcCap + ub_e < app_e ? kMergeExcCap + ub_e : app_e) : app_e;
-    const int capb_s = h->sorted_known ? (kMergeExcCap + ub_s < app_s ? kMergeExcCap + ub_s : app_s) : app_s;
-    PF_CHECK(map_merge(ws, M, capb_e, capb_s, mub_e, mub_s));
+    const float mres = (float)h->prm.map_resolution;   // rgbds(tmp, map_resolution [* 2]) with the float member map_resolution (:625-626)
+    int app[kKinds] = {0, 0, 0, 0};
+    for (int p = 0; p < h->npairs; ++p) {
+        AppendParams P{};
+        for (int j = 0; j < 2; ++j) {
+            const int k = h->pair[p][j];
+            P.ds[j] = h->d_ds[k]; P.n_ds[j] = h->d_nds + k; P.map[j] = h->d_map[cur][k]; P.n_map[j] = h->d_nmap[cur] + k; P.slot[j] = k;
+        }
+        P.write_pose = p == 0;
+        P.sh = h->d_sh; P.S = h->d_state; P.map_cap = h->bufcap;
+        P.pose_hist = h->d_pose_hist; P.hist_slot = (int)(h->frame % kPoseHist);
+        k_append<<<dim3(kSMs, 2), 256, 0, h->stream>>>(P);
+        ws.launches += 1;
+    }
+    for (int p = 0; p < h->npairs; ++p) {
+        if (p > 0) PF_CHECK(workspace_begin_step(ws));
+        const int ka = h->pair[p][0], kb = h->pair[p][1];
+        MapMergeParams M{};
+        for (int j = 0; j < 2; ++j) {
+            const int k = h->pair[p][j];
+            M.c[j] = MapMergeCloud{h->d_map[cur][k], h->d_nmap[cur] + kKinds + k, h->d_sh->n_app + k, h->d_map[nxt][k], h->d_nmap[nxt] + k,
+                                   h->d_nmap[nxt] + kKinds + k, mres * (float)h->leaf_mul[k]};
+        }
+        M.center = h->d_sh->odom.t;
+        M.k_new = h->prm.k_new; M.theta_p = h->prm.theta_p; M.theta_max = h->prm.theta_max;
+        M.s = h->msc;
+        int capb[2], capa[2];
+        for (int j = 0; j < 2; ++j) {
+            const int k = h->pair[p][j];
+            app[k] = mub[k] + ub[k] < h->bufcap ? mub[k] + ub[k] : h->bufcap;
+            // unsorted part: everything on the first update (raw first-frame maps), later last update's exceptions + this frame's points
+            capb[j] = h->sorted_known ? (kMergeExcCap + ub[k] < app[k] ? kMergeExcCap + ub[k] : app[k]) : app[k];
+            if (k == kNull) capb[j] = 0;
+            capa[j] = mub[k];
+        }
+        PF_CHECK(map_merge(ws, M, capb[0], capb[1], capa[0], capa[1]));
+        k_check_map_cap<<<1, 32, 0, h->stream>>>(h->d_nmap[nxt] + ka, h->d_nmap[nxt] + kb, ka, kb, h->mcap, h->d_sh, h->frame, map_merge_error_word(ws));
+        ws.launches += 1;
+    }
     h->sorted_known = true;
-    k_check_map_cap<<<1, 32, 0, h->stream>>>(h->d_nmap[nxt], h->d_nmap[nxt] + 1, h->mcap, h->d_sh, h->frame, map_merge_error_word(ws));
-    ws.launches += 1;
     PF_CUDA(cudaGetLastError());
     h->cur = nxt;
     mark(5);
-    h->map_ub[0] = app_e; h->map_ub[1] = app_s;     // the update never grows a map beyond old + appended
-    PF_CHECK(ring_record(h, ub_e, ub_s));
+    for (int k = 0; k < kKinds; ++k) h->map_ub[k] = app[k];     // the update never grows a map beyond old + appended
+    PF_CHECK(ring_record(h, ub));
     h->frame += 1;
     return PF_OK;
 }
@@ -400,21 +498,20 @@ int finish_frame(pf_odom* h, double pose_out[7]) {
         set_error("local map exceeded max_map_points = %d", h->mcap);
         return PF_ERR_CAPACITY;
     }
-    if (h->h_sh->err & 14) {
-        set_error("map update failed (bits %d: 2 = map_resolution below 0.2 m, 4 = more than %d centroids left their voxel)", h->h_sh->err & 6, kMergeExcCap);
+    if (h->h_sh->err & 30) {
+        set_error("map update failed (bits %d: 2 = map_resolution below 0.2 m, 4 = more than %d centroids left their voxel, 8 / 16 = internal)",
+                  h->h_sh->err & 30, kMergeExcCap);
         return PF_ERR_CAPACITY;
     }
     if (pose_out) memcpy(pose_out, h->h_sh->pose, sizeof(double) * 7);
     if (h->inited) {
-        h->map_ub[0] = h->h_sh->n_map[0]; h->map_ub[1] = h->h_sh->n_map[1];
+        for (int k = 0; k < kKinds; ++k) h->map_ub[k] = h->h_sh->n_map[k];
         h->known_frame = h->frame - 1;
     }
     return PF_OK;
 }
 
-}  // namespace
-
-extern "C" int pf_odom_create(const pf_odom_params* p, int device, pf_odom** out) {
+int odom_create(const pf_odom_params* p, int device, bool bpf, pf_odom** out) {
     PF_REQUIRE(p && out, "null argument");
     PF_REQUIRE(p->map_resolution >= 0.2, "map_resolution %g: the streaming map update keeps 10-bit voxel coordinates inside the 200 m crop box (needs >= 0.2 m)",
                p->map_resolution);
@@ -430,6 +527,17 @@ extern "C" int pf_odom_create(const pf_odom_params* p, int device, pf_odom** out
     pf_odom* h = new pf_odom();
     h->device = device;
     h->prm = *p;
+    if (bpf) {      // beam, pillar: line residuals at map_resolution; facade: plane residuals at 2 x map_resolution (:658-660)
+        h->nk = 3;
+        h->type[0] = 0; h->type[1] = 0; h->type[2] = 1;
+        h->leaf_mul[0] = 1; h->leaf_mul[1] = 1; h->leaf_mul[2] = 2;
+        h->min_map[0] = 10; h->min_map[1] = 10; h->min_map[2] = 50;     // :720
+        h->npairs = 2;
+        h->pair[0][0] = 0; h->pair[0][1] = 2;
+        h->pair[1][0] = 1; h->pair[1][1] = kNull;
+    } else {
+        h->pair[0][0] = 0; h->pair[0][1] = 1;
+    }
     h->fcap = p->max_features > 0 ? p->max_features : 131072;
     h->mcap = p->max_map_points > 0 ? p->max_map_points : (2 << 20);
     if (h->mcap < h->fcap) h->mcap = h->fcap;   // the raw first-frame clouds become the maps (:217-222)
@@ -443,15 +551,20 @@ extern "C" int pf_odom_create(const pf_odom_params* p, int device, pf_odom** out
     return PF_OK;
 }
 
+}  // namespace
+
+extern "C" int pf_odom_create(const pf_odom_params* p, int device, pf_odom** out) { return odom_create(p, device, false, out); }
+extern "C" int pf_odom_bpf_create(const pf_odom_params* p, int device, pf_odom** out) { return odom_create(p, device, true, out); }
+
 extern "C" int pf_odom_destroy(pf_odom* h) {
     if (!h) return PF_OK;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     workspace_destroy(h->ws);
     map_merge_scratch_destroy(h->msc);
-    cudaFree(h->d_nfeat); cudaFree(h->d_nds); cudaFree(h->d_geom);
-    for (int k = 0; k < 2; ++k) {
-        cudaFree(h->d_feat[k]); cudaFree(h->d_ds[k]); cudaFree(h->d_map[0][k]); cudaFree(h->d_map[1][k]); cudaFree(h->d_nmap[k]);
+    cudaFree(h->d_nfeat); cudaFree(h->d_nds); cudaFree(h->d_geom); cudaFree(h->d_nmap[0]); cudaFree(h->d_nmap[1]);
+    for (int k = 0; k < kKinds; ++k) {
+        cudaFree(h->d_feat[k]); cudaFree(h->d_ds[k]); cudaFree(h->d_map[0][k]); cudaFree(h->d_map[1][k]);
         cudaFree(h->d_gpts[k]); cudaFree(h->d_cs[k]); cudaFree(h->d_ce[k]); cudaFree(h->d_head[k]); cudaFree(h->d_hits[k]);
         cudaFree(h->d_next[k]); cudaFree(h->d_nn[k]); cudaFree(h->d_flag[k]); cudaFree(h->d_g8[k]);
         cudaFree(h->d_wobs[k]); cudaFree(h->d_wspa[k]);
@@ -467,42 +580,66 @@ extern "C" int pf_odom_destroy(pf_odom* h) {
     return PF_OK;
 }
 
-extern "C" int pf_odom_init_map(pf_odom* h, const float* edge, int n_edge, const float* surf, int n_surf) {
+namespace {
+// host feature clouds -> device, then init / update
+int host_frame(pf_odom* h, int nk_expected, const float* const feat[], const int n[], bool init, double* pose_out) {
     PF_REQUIRE(h, "null handle");
+    PF_REQUIRE(h->nk == nk_expected, "this handle was created for %d feature kinds, the call passes %d", h->nk, nk_expected);
+    if (!init && !h->inited) { set_error("update before init_map"); return PF_ERR_STATE; }
     PF_CUDA(cudaSetDevice(h->device));
-    PF_CHECK(upload_features(h, edge, n_edge, surf, n_surf));
-    const float4* feat[2] = {h->d_feat[0], h->d_feat[1]};
-    const int* nf[2] = {h->d_nfeat, h->d_nfeat + 1};
-    PF_CHECK(enqueue_init(h, feat, nf, n_edge, n_surf));
-    return finish_frame(h, nullptr);
+    PF_CHECK(upload_features(h, feat, n));
+    const float4* df[kKinds];
+    const int* dn[kKinds];
+    int ub[kKinds];
+    for (int k = 0; k < kKinds; ++k) { df[k] = h->d_feat[k]; dn[k] = h->d_nfeat + k; ub[k] = k < h->nk ? n[k] : 0; }
+    if (init) { PF_CHECK(enqueue_init(h, df, dn, ub)); }
+    else { PF_CHECK(enqueue_update(h, df, dn, ub)); }
+    return finish_frame(h, pose_out);
+}
+}  // namespace
+
+extern "C" int pf_odom_init_map(pf_odom* h, const float* edge, int n_edge, const float* surf, int n_surf) {
+    const float* f[2] = {edge, surf};
+    const int n[2] = {n_edge, n_surf};
+    return host_frame(h, 2, f, n, true, nullptr);
 }
 
 extern "C" int pf_odom_update(pf_odom* h, const float* edge, int n_edge, const float* surf, int n_surf, double pose_out[7]) {
-    PF_REQUIRE(h, "null handle");
-    if (!h->inited) { set_error("pf_odom_update before pf_odom_init_map"); return PF_ERR_STATE; }
-    PF_CUDA(cudaSetDevice(h->device));
-    PF_CHECK(upload_features(h, edge, n_edge, surf, n_surf));
-    const float4* feat[2] = {h->d_feat[0], h->d_feat[1]};
-    const int* nf[2] = {h->d_nfeat, h->d_nfeat + 1};
-    PF_CHECK(enqueue_update(h, feat, nf, n_edge, n_surf));
-    return finish_frame(h, pose_out);
+    const float* f[2] = {edge, surf};
+    const int n[2] = {n_edge, n_surf};
+    return host_frame(h, 2, f, n, false, pose_out);
+}
+
+// Odom_BPF_EstimationClass::initMapWithPoints (:692-698) / updatePointsToMap (:706-760)
+extern "C" int pf_odom_bpf_init_map(pf_odom* h, const float* beam, int n_beam, const float* pillar, int n_pillar, const float* facade, int n_facade) {
+    const float* f[3] = {beam, pillar, facade};
+    const int n[3] = {n_beam, n_pillar, n_facade};
+    return host_frame(h, 3, f, n, true, nullptr);
+}
+
+extern "C" int pf_odom_bpf_update(pf_odom* h, const float* beam, int n_beam, const float* pillar, int n_pillar, const float* facade, int n_facade,
+                                  double pose_out[7]) {
+    const float* f[3] = {beam, pillar, facade};
+    const int n[3] = {n_beam, n_pillar, n_facade};
+    return host_frame(h, 3, f, n, false, pose_out);
 }
 
 static int process_extracted(pf_odom* h, pf_extract* ex, double pose_out[7], bool sync) {
     PF_REQUIRE(h && ex, "null handle");
+    PF_REQUIRE(h->nk == 2, "the fused extraction hand-off feeds the edge / surf odometry");
     PF_CUDA(cudaSetDevice(h->device));
-    const float4* feat[2];
-    const int* nf[2];
+    const float4* feat[kKinds] = {};
+    const int* nf[kKinds] = {};
+    int ub[kKinds] = {0, 0, 0, 0};
     cudaStream_t exs;
-    int ecap, scap;
-    pf_extract_device_outputs(ex, &feat[0], &nf[0], &feat[1], &nf[1], &exs, &ecap, &scap);
-    PF_REQUIRE(scap <= h->fcap, "scan of %d points exceeds max_features %d", scap, h->fcap);
+    pf_extract_device_outputs(ex, &feat[0], &nf[0], &feat[1], &nf[1], &exs, &ub[0], &ub[1]);
+    PF_REQUIRE(ub[1] <= h->fcap, "scan of %d points exceeds max_features %d", ub[1], h->fcap);
     PF_CUDA(cudaEventRecord(h->ev, exs));
     PF_CUDA(cudaStreamWaitEvent(h->stream, h->ev, 0));
     if (!h->inited) {
-        PF_CHECK(enqueue_init(h, feat, nf, ecap, scap));
+        PF_CHECK(enqueue_init(h, feat, nf, ub));
     } else {
-        PF_CHECK(enqueue_update(h, feat, nf, ecap, scap));
+        PF_CHECK(enqueue_update(h, feat, nf, ub));
     }
     // the extractor's output buffers are reused by the next frame: it must not start before this frame consumed them
     PF_CUDA(cudaEventRecord(h->ev_done, h->stream));
@@ -550,16 +687,16 @@ extern "C" int pf_odom_get_pose(pf_odom* h, double pose[7]) {
 }
 
 extern "C" int pf_odom_map_size(pf_odom* h, int which, int* n) {
-    PF_REQUIRE(h && n && (which == 0 || which == 1), "bad argument");
+    PF_REQUIRE(h && n && which >= 0 && which < h->nk, "bad argument");
     PF_CUDA(cudaSetDevice(h->device));
-    PF_CUDA(cudaMemcpyAsync(h->h_counts, h->d_nmap[h->cur], sizeof(int) * 2, cudaMemcpyDeviceToHost, h->stream));
+    PF_CUDA(cudaMemcpyAsync(h->h_counts, h->d_nmap[h->cur], sizeof(int) * kKinds, cudaMemcpyDeviceToHost, h->stream));
     PF_CUDA(cudaStreamSynchronize(h->stream));
     *n = h->h_counts[which];
     return PF_OK;
 }
 
 extern "C" int pf_odom_get_map_part(pf_odom* h, int which, pf_point* out, int cap, int* n) {
-    PF_REQUIRE(h && out && n && (which == 0 || which == 1), "bad argument");
+    PF_REQUIRE(h && out && n && which >= 0 && which < h->nk, "bad argument");
     int m = 0;
     PF_CHECK(pf_odom_map_size(h, which, &m));
     PF_REQUIRE(m <= cap, "map has %d points, buffer holds %d", m, cap);
@@ -568,16 +705,20 @@ extern "C" int pf_odom_get_map_part(pf_odom* h, int which, pf_point* out, int ca
     return PF_OK;
 }
 
-// getMap (:210-215): surf map, then corner map
+// getMap: ES (:210-215) surf map, then corner map; BPF (:683-689) beam, pillar, facade
 extern "C" int pf_odom_get_map(pf_odom* h, pf_point* out, int cap, int* n) {
     PF_REQUIRE(h && out && n, "bad argument");
-    int ns = 0, ne = 0;
-    PF_CHECK(pf_odom_map_size(h, 1, &ns));
-    PF_CHECK(pf_odom_map_size(h, 0, &ne));
-    PF_REQUIRE(ns + ne <= cap, "map has %d points, buffer holds %d", ns + ne, cap);
-    if (ns) PF_CUDA(cudaMemcpy(out, h->d_map[h->cur][1], sizeof(Pt) * ns, cudaMemcpyDeviceToHost));
-    if (ne) PF_CUDA(cudaMemcpy(out + ns, h->d_map[h->cur][0], sizeof(Pt) * ne, cudaMemcpyDeviceToHost));
-    *n = ns + ne;
+    const int order_es[2] = {1, 0}, order_bpf[3] = {0, 1, 2};
+    const int* order = h->nk == 2 ? order_es : order_bpf;
+    int total = 0, sz[3] = {0, 0, 0};
+    for (int i = 0; i < h->nk; ++i) { PF_CHECK(pf_odom_map_size(h, order[i], &sz[i])); total += sz[i]; }
+    PF_REQUIRE(total <= cap, "map has %d points, buffer holds %d", total, cap);
+    int off = 0;
+    for (int i = 0; i < h->nk; ++i) {
+        if (sz[i]) PF_CUDA(cudaMemcpy(out + off, h->d_map[h->cur][order[i]], sizeof(Pt) * sz[i], cudaMemcpyDeviceToHost));
+        off += sz[i];
+    }
+    *n = total;
     return PF_OK;
 }
 
@@ -593,15 +734,18 @@ extern "C" int pf_odom_get_iter_poses(pf_odom* h, double* poses, int cap, int* n
     return PF_OK;
 }
 
+// ES: the two kinds; BPF: n_edge_ds / map_edge describe the beam cloud, n_surf_ds / map_surf the facade cloud, residual counts are
+// line-type (beam + pillar) and plane-type totals
 extern "C" int pf_odom_get_stats(pf_odom* h, pf_odom_stats* s) {
     PF_REQUIRE(h && s, "bad argument");
     PF_CUDA(cudaSetDevice(h->device));
-    PF_CUDA(cudaMemcpyAsync(h->h_counts, h->d_nds, sizeof(int) * 2, cudaMemcpyDeviceToHost, h->stream));
-    PF_CUDA(cudaMemcpyAsync(h->h_counts + 2, h->d_nmap[h->cur], sizeof(int) * 2, cudaMemcpyDeviceToHost, h->stream));
+    PF_CUDA(cudaMemcpyAsync(h->h_counts, h->d_nds, sizeof(int) * kKinds, cudaMemcpyDeviceToHost, h->stream));
+    PF_CUDA(cudaMemcpyAsync(h->h_counts + kKinds, h->d_nmap[h->cur], sizeof(int) * kKinds, cudaMemcpyDeviceToHost, h->stream));
     PF_CUDA(cudaMemcpyAsync(h->h_state, h->d_state, sizeof(LmState), cudaMemcpyDeviceToHost, h->stream));
     PF_CUDA(cudaStreamSynchronize(h->stream));
-    s->n_edge_ds = h->h_counts[0]; s->n_surf_ds = h->h_counts[1];
-    s->map_edge = h->h_counts[2]; s->map_surf = h->h_counts[3];
+    const int plane = h->nk == 2 ? 1 : 2;
+    s->n_edge_ds = h->h_counts[0]; s->n_surf_ds = h->h_counts[plane];
+    s->map_edge = h->h_counts[kKinds + 0]; s->map_surf = h->h_counts[kKinds + plane];
     s->n_edge_res = h->h_state->n_edge_res; s->n_surf_res = h->h_state->n_surf_res;
     s->passes = h->last_passes;
     s->lm_iterations = h->h_state->iter;

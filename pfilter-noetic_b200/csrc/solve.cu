@@ -248,9 +248,9 @@ __global__ void __cluster_dims__(kLmCluster, 1, 1) __launch_bounds__(kLmThreads)
     __shared__ double s_sum[32];           // cluster totals
     __shared__ LmState s_state;            // every CTA keeps the whole solver state
     __shared__ int s_n, s_scan[NW + 1];
-    __shared__ double s_mm[8];             // weightType != 0: min / max of observe and sparsity per kind
+    __shared__ double s_mm[4 * kLmMaxSrc]; // weightType != 0: min / max of observe and sparsity per source
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-    if (P.weight_type != 0 && tid < 8) s_mm[tid] = __longlong_as_double((long long)P.w_minmax[tid]);
+    if (P.weight_type != 0 && tid < 4 * P.nsrc) s_mm[tid] = __longlong_as_double((long long)P.src[tid >> 2].w_minmax[tid & 3]);
 
     {
         const unsigned* src = reinterpret_cast<const unsigned*>(P.state);
@@ -268,8 +268,7 @@ __global__ void __cluster_dims__(kLmCluster, 1, 1) __launch_bounds__(kLmThreads)
     }
     // compaction of this CTA's slices, order preserving (chunks of kLmThreads entries: ballot + warp counts)
     int overflow = 0;
-#pragma unroll
-    for (int kind = 0; kind < 2; ++kind) {
+    for (int kind = 0; kind < P.nsrc; ++kind) {
         const ResidualSrc& R = P.src[kind];
         const int n = R.n ? *R.n : 0;
         const int per = (n + kLmCluster - 1) / kLmCluster;
@@ -285,7 +284,7 @@ __global__ void __cluster_dims__(kLmCluster, 1, 1) __launch_bounds__(kLmThreads)
             for (int k = 0; k < NW; ++k) { const int c = s_scan[k]; if (k < w) off += c; tot += c; }
             if (v) {
                 const int pos = off + __popc(m & lanemask_lt());
-                if (pos < list_cap) s_list[pos] = (kind << 30) | i; else overflow = 1;
+                if (pos < list_cap) s_list[pos] = (int)(((unsigned)kind << 30) | (unsigned)i); else overflow = 1;
             }
             __syncthreads();
             if (tid == 0) s_n += tot;
@@ -293,7 +292,7 @@ __global__ void __cluster_dims__(kLmCluster, 1, 1) __launch_bounds__(kLmThreads)
         }
     }
     const int n_list = min(s_n, list_cap);
-    const int my_edges = [&] { int c = 0; for (int k = tid; k < n_list; k += kLmThreads) c += (s_list[k] >> 30) == 0 ? 1 : 0; return c; }();
+    const int my_edges = [&] { int c = 0; for (int k = tid; k < n_list; k += kLmThreads) c += P.src[(unsigned)s_list[k] >> 30].type == 0 ? 1 : 0; return c; }();
     (void)overflow;     // cannot happen: list_cap covers the whole slice (host side)
     const double* part_of[kLmCluster];
 #pragma unroll
@@ -310,12 +309,14 @@ __global__ void __cluster_dims__(kLmCluster, 1, 1) __launch_bounds__(kLmThreads)
 #pragma unroll
         for (int k = 0; k < kAcc; ++k) acc[k] = 0.0;
         for (int k = tid; k < n_list; k += kLmThreads) {
-            const int e = s_list[k], kind = e >> 30, i = e & 0x3fffffff;
-            const ResidualSrc& R = P.src[kind];
+            const unsigned e = (unsigned)s_list[k];
+            const int src = (int)(e >> 30), i = (int)(e & 0x3fffffffu);
+            const ResidualSrc& R = P.src[src];
+            const int kind = R.type;
             D3 p;
             if (R.p_override) p = d3(R.p_override[3 * i], R.p_override[3 * i + 1], R.p_override[3 * i + 2]);
             else { const Pt q = R.queries[i]; p = d3((double)q.x, (double)q.y, (double)q.z); }
-            const double weight = P.weight_type != 0 ? residual_weight(P.weight_type, (double)R.w_obs[i], R.w_spa[i], s_mm + 4 * kind) : 0.0;
+            const double weight = P.weight_type != 0 ? residual_weight(P.weight_type, (double)R.w_obs[i], R.w_spa[i], s_mm + 4 * src) : 0.0;
             eval_one(kind, p, R.geom + 8 * (size_t)i, Rm, tv, weight, acc);
         }
         // warp reduction, fixed tree (skipped by warps that evaluated nothing: their partial is exactly zero)
@@ -369,11 +370,13 @@ __global__ void __cluster_dims__(kLmCluster, 1, 1) __launch_bounds__(kLmThreads)
     cluster.sync();                            // peers must not exit while others may still read their shared memory
 }
 
-int lm_solve(cudaStream_t stream, const LmParams& P, const double* pose_src, int first_pass, uint64_t* launches, int ub_edge, int ub_surf) {
+int lm_solve(cudaStream_t stream, const LmParams& P, const double* pose_src, int first_pass, uint64_t* launches, const int* ub) {
     // shared-memory list: the largest slice a CTA can own
-    const int list_cap = (ub_edge + kLmCluster - 1) / kLmCluster + (ub_surf + kLmCluster - 1) / kLmCluster + 8;
+    int list_cap = 8;
+    for (int k = 0; k < P.nsrc; ++k) list_cap += (ub[k] + kLmCluster - 1) / kLmCluster;
     const size_t smem = sizeof(int) * (size_t)list_cap;
-    PF_REQUIRE(smem <= 160 * 1024, "lm_solve: %d + %d residual candidates exceed the solver's shared-memory list", ub_edge, ub_surf);
+    PF_REQUIRE(P.nsrc >= 1 && P.nsrc <= kLmMaxSrc, "lm_solve: %d residual sources", P.nsrc);
+    PF_REQUIRE(smem <= 160 * 1024, "lm_solve: %d residual candidates per CTA exceed the solver's shared-memory list", list_cap);
     static size_t smem_set = 0;
     if (smem > smem_set) {
         PF_CUDA(cudaFuncSetAttribute(k_lm_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem > 48 * 1024 ? smem : 48 * 1024)));
@@ -436,14 +439,14 @@ int solve_tap_setup(SolveTap& t, int device, const double pose[7], const double*
             PF_CUDA(cudaMemcpyAsync(t.d_p[k], hp[k].data(), sizeof(double) * 3 * n[k], cudaMemcpyHostToDevice, t.stream));
             PF_CUDA(cudaMemcpyAsync(t.d_geom[k], hg[k].data(), sizeof(double) * 8 * n[k], cudaMemcpyHostToDevice, t.stream));
         }
-        P.src[k] = ResidualSrc{nullptr, t.d_p[k], t.d_flag[k], t.d_geom[k], t.d_n + k, nullptr, nullptr};
+        P.src[k] = ResidualSrc{k, nullptr, t.d_p[k], t.d_flag[k], t.d_geom[k], t.d_n + k, nullptr, nullptr, nullptr};
     }
     PF_CUDA(cudaMalloc(&t.d_state, sizeof(LmState)));
     PF_CUDA(cudaMemsetAsync(t.d_state, 0, sizeof(LmState), t.stream));
     PF_CUDA(cudaMemcpyAsync(t.d_state->x, pose, sizeof(double) * 7, cudaMemcpyHostToDevice, t.stream));
     P.state = t.d_state;
     P.iter_poses = nullptr;
-    P.weight_type = 0; P.w_minmax = nullptr;
+    P.weight_type = 0; P.nsrc = 2;
     PF_CUDA(cudaStreamSynchronize(t.stream));   // the staging vectors go out of scope
     return PF_OK;
 }
@@ -456,7 +459,7 @@ extern "C" int pf_eval_normal_eq(int device, const double pose[7], const double*
     LmParams P{};
     PF_CHECK(solve_tap_setup(t, device, pose, edge9, n_edge, surf7, n_surf, P));
     P.eval_only = 1;
-    PF_CHECK(lm_solve(t.stream, P, nullptr, 1, nullptr, n_edge, n_surf));
+    { const int ub[2] = {n_edge, n_surf}; PF_CHECK(lm_solve(t.stream, P, nullptr, 1, nullptr, ub)); }
     LmState S;
     PF_CUDA(cudaMemcpyAsync(&S, t.d_state, sizeof(S), cudaMemcpyDeviceToHost, t.stream));
     PF_CUDA(cudaStreamSynchronize(t.stream));
@@ -473,7 +476,7 @@ extern "C" int pf_lm_solve(int device, double pose_io[7], const double* edge9, i
     LmParams P{};
     PF_CHECK(solve_tap_setup(t, device, pose_io, edge9, n_edge, surf7, n_surf, P));
     P.eval_only = 0;
-    PF_CHECK(lm_solve(t.stream, P, nullptr, 1, nullptr, n_edge, n_surf));
+    { const int ub[2] = {n_edge, n_surf}; PF_CHECK(lm_solve(t.stream, P, nullptr, 1, nullptr, ub)); }
     LmState S;
     PF_CUDA(cudaMemcpyAsync(&S, t.d_state, sizeof(S), cudaMemcpyDeviceToHost, t.stream));
     PF_CUDA(cudaStreamSynchronize(t.stream));

@@ -6,7 +6,10 @@
 
 namespace pf {
 
+constexpr int kLmMaxSrc = 3;  // ES path: edge, surf; BPF path: beam, pillar, facade
+
 struct ResidualSrc {          // one feature kind
+    int type;                 // 0 = point-to-line residual (edge / beam / pillar), 1 = point-to-plane (surf / facade)
     const Pt* queries;        // sensor-frame points (float), used when p_override == null
     const double* p_override; // [3 n] points in double (stage taps)
     const uint8_t* flag;      // 2 = residual block present
@@ -14,6 +17,7 @@ struct ResidualSrc {          // one feature kind
     const int* n;             // device count
     const float* w_obs;       // weightType != 0: observe value of the residual block
     const double* w_spa;      // weightType != 0: point sparsity of the residual block
+    const unsigned long long* w_minmax;   // weightType != 0: [4] min / max of observe, min / max of sparsity of this kind (match.cuh)
 };
 
 struct LmState {
@@ -36,12 +40,12 @@ struct LmState {
 };
 
 struct LmParams {
-    ResidualSrc src[2];       // 0 edge, 1 surf
+    ResidualSrc src[kLmMaxSrc];   // in the order the reference adds the residual blocks
+    int nsrc;
     LmState* state;
     double* iter_poses;       // [16][7] pose after every outer iteration (may be null)
     int eval_only;            // stage tap: evaluate at state->x and stop
     int weight_type;          // 0, 1, 2, 12: residual weights (src/odomEstimationClass.cpp:389-423, src/lidarOptimization.cpp:25-28, :62-63)
-    const unsigned long long* w_minmax;   // [2][4] min / max of observe and sparsity per kind (see match.cuh)
 };
 
 constexpr int kLmCluster = 8;    // CTAs of the solver cluster (8 SMs, distributed shared memory reduction)
@@ -49,7 +53,7 @@ constexpr int kLmThreads = 256;  // 2048 threads; 255 registers per thread keep 
 
 // One launch = one complete solve: at most 1 + 4 evaluations (max_num_iterations = 4) and the trust-region state machine.
 // pose_src: device pose to start from (null: keep state->x); first_pass resets the outer-iteration counter.
-// ub_edge / ub_surf: upper bounds of the two query counts (size the shared-memory list of residual blocks).
-int lm_solve(cudaStream_t stream, const LmParams& P, const double* pose_src, int first_pass, uint64_t* launches, int ub_edge, int ub_surf);
+// ub[s]: upper bound of the query count of source s (sizes the shared-memory list of residual blocks).
+int lm_solve(cudaStream_t stream, const LmParams& P, const double* pose_src, int first_pass, uint64_t* launches, const int* ub);   // ub[nsrc]
 
 }  // namespace pf

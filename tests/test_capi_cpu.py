@@ -51,7 +51,7 @@ def test_cpp_class_wrappers_compile():
     hdr = os.path.join(ROOT, "include", "pfilter_b200")
     if not os.path.isdir(hdr):
         pytest.skip("C++ wrappers not present")
-    src = "#include \"pfilter_b200/laserProcessingClass.h\"\n#include \"pfilter_b200/odomEstimationClass.h\"\n#include \"pfilter_b200/laserMappingClass.h\"\nint main(){return 0;}\n"
+    src = "#include \"pfilter_b200/laserProcessingClass.h\"\n#include \"pfilter_b200/odomEstimationClass.h\"\n#include \"pfilter_b200/laserMappingClass.h\"\nint main(){ Odom_BPF_EstimationClass* b = nullptr; (void)b; return 0;}\n"
     r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), "-x", "c++", "-"], input=src, text=True,
                        stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
     assert r.returncode == 0, r.stdout
