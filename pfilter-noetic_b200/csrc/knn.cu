@@ -67,45 +67,94 @@ __global__ void k_grid_geom(GridBuild G) {
     }
 }
 
-__global__ void __launch_bounds__(256) k_grid_keys_clear(GridBuild G, uint32_t* __restrict__ keys) {
+// The cell sort is a counting sort: zero the per-cell counters, count (one atomic per point), exclusive scan over the cells
+// (single pass, chained look-back), scatter (one atomic per point on the cell's cursor).  The order of the points inside a
+// cell is whatever the atomics produce; the search does not depend on it (exact distances, ties broken by the carried index).
+__global__ void __launch_bounds__(256) k_grid_clear(GridBuild G) {
+    const int kind = blockIdx.y;
+    const int* geom = G.geom[kind];
+    const long long cells = (long long)geom[3] * geom[4] * geom[5];
+    int* cs = G.cell_start[kind];
+    const int stride = gridDim.x * blockDim.x, t0 = blockIdx.x * blockDim.x + threadIdx.x;
+    for (long long c = t0; c < cells; c += stride) cs[c] = 0;
+}
+
+__global__ void __launch_bounds__(256) k_grid_count(GridBuild G, uint32_t* __restrict__ keys) {
     const int kind = blockIdx.y;
     const int n = *G.n_map[kind];
     const int base = kind == 0 ? 0 : *G.n_map[0];
     const int* geom = G.geom[kind];
     const int ox = geom[0], oy = geom[1], oz = geom[2], dx = geom[3], dy = geom[4], dz = geom[5];
-    const long long cells = (long long)dx * dy * dz;
+    if ((long long)dx * dy * dz <= 0) return;
     const Pt* m = G.map[kind];
-    const int stride = gridDim.x * blockDim.x, t0 = blockIdx.x * blockDim.x + threadIdx.x;
-    for (int i = t0; i < n; i += stride) {
-        Pt p = m[i];
-        unsigned key = 0xffffffffu;
-        if (cells > 0) {
-            const int cx = (int)floorf(p.x) - ox, cy = (int)floorf(p.y) - oy, cz = (int)floorf(p.z) - oz;
-            key = (unsigned)(cx + (cy + cz * dy) * dx) | ((unsigned)kind << 23);
-        }
-        keys[base + i] = key;
-    }
     int* cs = G.cell_start[kind];
-    int* ce = G.cell_end[kind];
-    for (long long c = t0; c < cells; c += stride) { cs[c] = 0; ce[c] = 0; }
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const Pt p = m[i];
+        const int cx = (int)floorf(p.x) - ox, cy = (int)floorf(p.y) - oy, cz = (int)floorf(p.z) - oz;
+        const unsigned cell = (unsigned)(cx + (cy + cz * dy) * dx);
+        keys[base + i] = cell;
+        atomicAdd(&cs[cell], 1);
+    }
 }
 
-__global__ void __launch_bounds__(256) k_grid_fill(GridBuild G, const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals) {
+constexpr int kGridScanTile = 2048;     // cells per tile of the scan (8 per thread)
+__global__ void __launch_bounds__(256) k_grid_scan(GridBuild G, unsigned long long* status, int status_stride, unsigned* ctrl) {
+    const int kind = blockIdx.y;
+    const int* geom = G.geom[kind];
+    const long long cells = (long long)geom[3] * geom[4] * geom[5];
+    const int ntiles = (int)((cells + kGridScanTile - 1) / kGridScanTile);
+    int* cs = G.cell_start[kind];
+    int* ce = G.cell_end[kind];
+    __shared__ int s_tile;
+    __shared__ int s_tmp[9];
+    __shared__ unsigned s_look[kScanSmemWords];
+    const int tid = threadIdx.x;
+    while (true) {
+        __syncthreads();
+        if (tid == 0) s_tile = (int)atomicAdd(&ctrl[9 + kind], 1u);
+        __syncthreads();
+        const int tile = s_tile;
+        if (tile >= ntiles) return;
+        const long long c0 = (long long)tile * kGridScanTile + 8 * tid;
+        int v[8];
+        if (c0 + 8 <= cells) {
+            const int4 a = *reinterpret_cast<const int4*>(cs + c0), b = *reinterpret_cast<const int4*>(cs + c0 + 4);
+            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] = c0 + k < cells ? cs[c0 + k] : 0;
+        }
+        int sum = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { const int t = v[k]; v[k] = sum; sum += t; }
+        int total;
+        const int excl = block_scan_excl_256(sum, s_tmp, &total);
+        const unsigned tag = (ctrl[0] << 3) | 5u;
+        const unsigned gbase = chained_scan_exclusive(status + (size_t)kind * status_stride, tag, tile, (unsigned)total, s_look);
+        const int off = (int)gbase + excl;
+        if (c0 + 8 <= cells) {
+            const int4 a = make_int4(off + v[0], off + v[1], off + v[2], off + v[3]), b = make_int4(off + v[4], off + v[5], off + v[6], off + v[7]);
+            *reinterpret_cast<int4*>(cs + c0) = a; *reinterpret_cast<int4*>(cs + c0 + 4) = b;
+            *reinterpret_cast<int4*>(ce + c0) = a; *reinterpret_cast<int4*>(ce + c0 + 4) = b;     // cursor of the scatter, ends up as the cell's end
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                if (c0 + k < cells) { cs[c0 + k] = off + v[k]; ce[c0 + k] = off + v[k]; }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_grid_scatter(GridBuild G, const uint32_t* __restrict__ keys) {
     const int kind = blockIdx.y;
     const int n = *G.n_map[kind];
-    const int n0 = *G.n_map[0];
-    const int start = kind == 0 ? 0 : n0;     // both maps are sorted jointly: map 0 first (bit 23 clear)
-    const Pt* m = G.map[kind];
+    const int base = kind == 0 ? 0 : *G.n_map[0];
     if (G.geom[kind][3] == 0) return;
+    const Pt* m = G.map[kind];
+    int* ce = G.cell_end[kind];
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const int p = start + i;
-        const unsigned key = keys[p];
-        const int orig = (int)vals[p] - start;
-        const Pt v = m[orig];
-        G.pts[kind][i] = make_float4(v.x, v.y, v.z, __int_as_float(orig));
-        const unsigned cell = key & ((1u << 23) - 1u);
-        if (i == 0 || keys[p - 1] != key) G.cell_start[kind][cell] = i;
-        if (i == n - 1 || keys[p + 1] != key) G.cell_end[kind][cell] = i + 1;
+        const Pt v = m[i];
+        const int pos = atomicAdd(&ce[keys[base + i]], 1);
+        G.pts[kind][pos] = make_float4(v.x, v.y, v.z, __int_as_float(i));
     }
 }
 
@@ -114,18 +163,18 @@ int build_grids(Workspace& ws, const GridBuild& G_in, int slot, int cap0, int ca
     G.state = ws.ctrl + kSlotBase + slot * kSlotWords;
     const int cap = cap0 + cap1;
     PF_REQUIRE(cap <= ws.cap, "build_grids: %d points exceed workspace capacity %d", cap, ws.cap);
+    PF_REQUIRE(ws.status_stride >= kGridCellCap / kGridScanTile + 8, "build_grids: workspace look-back array too small");
     const int capmax = cap0 > cap1 ? cap0 : cap1;
     int nblk = div_up(capmax, 256 * 4);
     if (nblk > 4 * kSMs) nblk = 4 * kSMs;
     if (nblk < 1) nblk = 1;
     k_grid_bounds<<<dim3(nblk, 2), 256, 0, ws.stream>>>(G);
     k_grid_geom<<<2, 32, 0, ws.stream>>>(G);
-    k_grid_keys_clear<<<dim3(4 * kSMs, 2), 256, 0, ws.stream>>>(G, ws.keys[0]);
-    ws.launches += 3;
-    int rb = 0;
-    PF_CHECK(radix_sort(ws, reinterpret_cast<const int*>(G.state) + 14, cap, 3, true, &rb));
-    k_grid_fill<<<dim3(nblk, 2), 256, 0, ws.stream>>>(G, ws.keys[rb], ws.vals[rb]);
-    ws.launches += 1;
+    k_grid_clear<<<dim3(4 * kSMs, 2), 256, 0, ws.stream>>>(G);
+    k_grid_count<<<dim3(nblk, 2), 256, 0, ws.stream>>>(G, ws.keys[0]);
+    k_grid_scan<<<dim3(4 * kSMs, 2), 256, 0, ws.stream>>>(G, ws.scan_status, ws.status_stride, ws.ctrl);
+    k_grid_scatter<<<dim3(nblk, 2), 256, 0, ws.stream>>>(G, ws.keys[0]);
+    ws.launches += 6;
     PF_CUDA(cudaGetLastError());
     return PF_OK;
 }

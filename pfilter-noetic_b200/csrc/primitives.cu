@@ -248,6 +248,7 @@ int workspace_create(Workspace& ws, int cap, cudaStream_t stream) {
     PF_CUDA(cudaMalloc(&ws.hist, sizeof(uint32_t) * kRadix * ws.nb_cap));
     PF_CUDA(cudaMalloc(&ws.totals, sizeof(uint32_t) * kRadix));
     ws.status_stride = ws.nb_cap * 8 + 8;
+    if (ws.status_stride < kMinStatusStride) ws.status_stride = kMinStatusStride;
     PF_CUDA(cudaMalloc(&ws.scan_status, sizeof(unsigned long long) * 4 * ws.status_stride));
     PF_CUDA(cudaMemset(ws.scan_status, 0, sizeof(unsigned long long) * 4 * ws.status_stride));
     PF_CUDA(cudaMalloc(&ws.ctrl, sizeof(unsigned) * kCtrlWords));

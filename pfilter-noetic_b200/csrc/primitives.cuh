@@ -11,6 +11,7 @@ constexpr int kSortItems = 8;
 constexpr int kSortTile = kSortThreads * kSortItems;   // 2048 keys per block
 constexpr int kRadixBits = 8;
 constexpr int kRadix = 1 << kRadixBits;
+constexpr int kMinStatusStride = (1 << 23) / 2048 + 8;   // look-back words for a scan over the 2^23 cells of a search grid (knn.cu)
 constexpr int kSmallSort = 8192;   // inputs up to this size are sorted by one CTA (k_sort_small), larger ones cooperatively
 
 // control words (device): [0] epoch (bumped once per pipeline step), [1..31] tickets of the chained scans,
