@@ -15,6 +15,11 @@
 
 namespace pf {
 
+// A warp takes kAssocBatch consecutive queries: the 5-NN search of each one is warp-cooperative (one after the other), then
+// lane g fits the geometry of query g.  The fp64 line / plane fit is ~3000 dependent instructions; run redundantly by all 32
+// lanes of a warp per query it made the kernel bound by fp64 issue (ncu: 37 us for 7.6 k queries); packed one query per lane it
+// costs a fraction of that pipe time per query.
+constexpr int kAssocBatch = 4;
 __global__ void __launch_bounds__(256) k_assoc_match(AssocParams P) {
     const int kind = blockIdx.y;
     const AssocCloud& c = P.c[kind];
@@ -23,69 +28,87 @@ __global__ void __launch_bounds__(256) k_assoc_match(AssocParams P) {
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
     if (P.weight_type != 0 && blockIdx.x == 0 && threadIdx.x < 4)     // min / max slots of this pass (read by k_assoc_persist, which follows)
         P.w_minmax[4 * kind + threadIdx.x] = (threadIdx.x & 1) ? 0ull : ~0ull;
-    for (int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; q < nq; q += nwarps) {
     const bool guard = P.guard == nullptr || *P.guard != 0;   // :247
-    unsigned flag = 0;
-    if (guard) {
-        const Pt qp = c.queries[q];
-        const D3 pw = pose_apply(P.pose, d3((double)qp.x, (double)qp.y, (double)qp.z));
-        int idx[5];
-        float d2[5];
-        if (knn5_warp(c.grid, (float)pw.x, (float)pw.y, (float)pw.z, idx, d2)) {   // :299-300 / :447-451
-            D3 nb[5];
+    for (int q0 = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * kAssocBatch; q0 < nq; q0 += nwarps * kAssocBatch) {
+        int my_idx[5] = {-1, -1, -1, -1, -1};
+        bool my_found = false;
+        if (guard) {
+#pragma unroll 1
+            for (int g = 0; g < kAssocBatch; ++g) {
+                const int q = q0 + g;
+                if (q >= nq) break;
+                const Pt qp = c.queries[q];
+                const D3 pw = pose_apply(P.pose, d3((double)qp.x, (double)qp.y, (double)qp.z));
+                int idx[5];
+                float d2[5];
+                const bool found = knn5_warp(c.grid, (float)pw.x, (float)pw.y, (float)pw.z, idx, d2);   // :299-300 / :447-451
+                if ((int)lane == g) {
+                    my_found = found;
 #pragma unroll
-            for (int j = 0; j < 5; ++j) {
-                const Pt m = c.map[idx[j]];
-                nb[j] = d3((double)m.x, (double)m.y, (double)m.z);
-            }
-            double g8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-            bool valid;
-            if (kind == 0) {
-                D3 ctr = d3(0, 0, 0);
-#pragma unroll
-                for (int j = 0; j < 5; ++j) ctr = ctr + nb[j];
-                ctr = d3(ctr.x / 5.0, ctr.y / 5.0, ctr.z / 5.0);
-                double c00 = 0, c01 = 0, c02 = 0, c11 = 0, c12 = 0, c22 = 0;
-#pragma unroll
-                for (int j = 0; j < 5; ++j) {
-                    const D3 d = nb[j] - ctr;
-                    c00 += d.x * d.x; c01 += d.x * d.y; c02 += d.x * d.z;
-                    c11 += d.y * d.y; c12 += d.y * d.z; c22 += d.z * d.z;
+                    for (int j = 0; j < 5; ++j) my_idx[j] = idx[j];
                 }
-                double w[3];
-                D3 v;
-                eig3_sym(c00, c01, c02, c11, c12, c22, w, v);
-                valid = w[2] > 3 * w[1];                                   // :326
-                const D3 a = (0.1 * v) + ctr, b = (-0.1 * v) + ctr;        // :330-331
-                g8[0] = a.x; g8[1] = a.y; g8[2] = a.z; g8[3] = b.x; g8[4] = b.y; g8[5] = b.z;
-            } else {
-                double A[3][5], rhs[5], n[3];
-#pragma unroll
-                for (int j = 0; j < 5; ++j) { A[0][j] = nb[j].x; A[1][j] = nb[j].y; A[2][j] = nb[j].z; rhs[j] = -1.0; }
-                plane_lsq_5x3(A, rhs, n);                                  // :461
-                const double nn = sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
-                const double negOA = 1 / nn;                               // :462
-                n[0] = n[0] / nn; n[1] = n[1] / nn; n[2] = n[2] / nn;      // :463
-                valid = true;
-#pragma unroll
-                for (int j = 0; j < 5; ++j)
-                    if (fabs(n[0] * nb[j].x + n[1] * nb[j].y + n[2] * nb[j].z + negOA) > 0.2) valid = false;   // :466-476 (NaN -> stays valid, as in the reference)
-                g8[0] = n[0]; g8[1] = n[1]; g8[2] = n[2];
-                g8[3] = (double)(float)negOA;   // surfInfo::negative_OA_dot_norm is a float (include/odomEstimationClass.h:93-94)
-            }
-            if (valid) {
-                flag = 1;
-                if (lane < 5) {
-                    const int m = idx[lane], hit = 5 * q + (int)lane;
-                    c.nn_idx[hit] = m;
-                    c.next[hit] = atomicExch(&c.head[m], hit);
-                    atomicAdd(&c.hits[m], 1);
-                }
-                if (lane < 8) c.geom[8 * (size_t)q + lane] = g8[lane];
             }
         }
-    }
-    if (lane == 0) c.flag[q] = (uint8_t)flag;
+        const int q = q0 + (int)lane;
+        if ((int)lane < kAssocBatch && q < nq) {
+            unsigned flag = 0;
+            if (my_found) {
+                D3 nb[5];
+#pragma unroll
+                for (int j = 0; j < 5; ++j) {
+                    const Pt m = c.map[my_idx[j]];
+                    nb[j] = d3((double)m.x, (double)m.y, (double)m.z);
+                }
+                double g8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                bool valid;
+                if (kind == 0) {
+                    D3 ctr = d3(0, 0, 0);
+#pragma unroll
+                    for (int j = 0; j < 5; ++j) ctr = ctr + nb[j];
+                    ctr = d3(ctr.x / 5.0, ctr.y / 5.0, ctr.z / 5.0);
+                    double c00 = 0, c01 = 0, c02 = 0, c11 = 0, c12 = 0, c22 = 0;
+#pragma unroll
+                    for (int j = 0; j < 5; ++j) {
+                        const D3 d = nb[j] - ctr;
+                        c00 += d.x * d.x; c01 += d.x * d.y; c02 += d.x * d.z;
+                        c11 += d.y * d.y; c12 += d.y * d.z; c22 += d.z * d.z;
+                    }
+                    double w[3];
+                    D3 v;
+                    eig3_sym(c00, c01, c02, c11, c12, c22, w, v);
+                    valid = w[2] > 3 * w[1];                                   // :326
+                    const D3 a = (0.1 * v) + ctr, b = (-0.1 * v) + ctr;        // :330-331
+                    g8[0] = a.x; g8[1] = a.y; g8[2] = a.z; g8[3] = b.x; g8[4] = b.y; g8[5] = b.z;
+                } else {
+                    double A[3][5], rhs[5], n[3];
+#pragma unroll
+                    for (int j = 0; j < 5; ++j) { A[0][j] = nb[j].x; A[1][j] = nb[j].y; A[2][j] = nb[j].z; rhs[j] = -1.0; }
+                    plane_lsq_5x3(A, rhs, n);                                  // :461
+                    const double nn = sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+                    const double negOA = 1 / nn;                               // :462
+                    n[0] = n[0] / nn; n[1] = n[1] / nn; n[2] = n[2] / nn;      // :463
+                    valid = true;
+#pragma unroll
+                    for (int j = 0; j < 5; ++j)
+                        if (fabs(n[0] * nb[j].x + n[1] * nb[j].y + n[2] * nb[j].z + negOA) > 0.2) valid = false;   // :466-476 (NaN -> stays valid, as in the reference)
+                    g8[0] = n[0]; g8[1] = n[1]; g8[2] = n[2];
+                    g8[3] = (double)(float)negOA;   // surfInfo::negative_OA_dot_norm is a float (include/odomEstimationClass.h:93-94)
+                }
+                if (valid) {
+                    flag = 1;
+#pragma unroll
+                    for (int j = 0; j < 5; ++j) {
+                        const int m = my_idx[j], hit = 5 * q + j;
+                        c.nn_idx[hit] = m;
+                        c.next[hit] = atomicExch(&c.head[m], hit);
+                        atomicAdd(&c.hits[m], 1);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) c.geom[8 * (size_t)q + j] = g8[j];
+                }
+            }
+            c.flag[q] = (uint8_t)flag;
+        }
     }
 }
 
@@ -155,7 +178,7 @@ __global__ void __launch_bounds__(128) k_assoc_persist(AssocParams P) {
 int associate_pass(cudaStream_t stream, const AssocParams& P, int qcap0, int qcap1, uint64_t* launches) {
     const int qcap = qcap0 > qcap1 ? qcap0 : qcap1;
     if (qcap <= 0) return PF_OK;
-    int gm = div_up(qcap, 8), gp = div_up(qcap, 128);
+    int gm = div_up(qcap, 8 * kAssocBatch), gp = div_up(qcap, 128);
     if (gm > 8 * kSMs) gm = 8 * kSMs;
     if (gp > 4 * kSMs) gp = 4 * kSMs;
     k_assoc_match<<<dim3(gm, 2), 256, 0, stream>>>(P);
