@@ -232,6 +232,33 @@ def smoke_odometry(p, O):
             assert od.status == 0
             dq, dt = np.abs(od.pose7[:4] - rp[:4]).max(), np.abs(od.pose7[4:] - rp[4:]).max()
             assert dq < 1e-4 and dt < 2e-3, f"frame {f}: pose differs from the oracle (dq {dq:.2e}, dt {dt:.2e})"
+    # global map (LaserMappingClass) and the BPF odometry class on the same data
+    mp = LaserMappingClass(max_map_points=1 << 20, max_points=131072)
+    mp.init(0.4)
+    om = O.Mapping(0.4)
+    for f in range(2):
+        s = synth.scan(p, f)
+        rt = capi.pose_to_rt(synth.pose(p, f))
+        mp.updateCurrentPointsToMap(s, rt.reshape(3, 4))
+        om.update(s, rt)
+    gm, rm = mp.getMap(), om.get_map()
+    assert mp.status == 0 and len(gm) == len(rm) and np.array_equal(np.sort(gm.view(np.uint32), axis=0), np.sort(rm.view(np.uint32), axis=0)), \
+        "global map differs from the oracle"
+    bpf = Odom_BPF_EstimationClass(max_map_points=262144)
+    bpf.init(lid, 0.4, 0, 0.4, 75, 0.0)
+    rb = O.OdomBPF(0.4, 0, 0.4, 75)
+    for f in range(2):
+        s = synth.scan(p, f)
+        r = O.extract(s, num_lines=p.sensor_lines, order=1)
+        e, u = s[r["edge_idx"]], s[r["surf_idx"]]
+        if f == 0:
+            bpf.initMapWithPoints(e[0::2], e[1::2], u)
+            rb.init_map(e[0::2], e[1::2], u)
+        else:
+            bpf.updatePointsToMap(e[0::2], e[1::2], u)
+            rp = rb.update(e[0::2], e[1::2], u)
+            assert bpf.status == 0 and np.abs(bpf.pose7 - rp).max() < 2e-3, "BPF pose differs from the oracle"
+    print(f"smoke: global map ok ({len(gm)} pts), BPF odometry ok")
     st = od.odometry.stats()
     print(f"smoke: odometry ok (3 frames, {od.odometry.launches} kernel launches, map {st['map_edge']}+{st['map_surf']} pts, "
           f"t = {np.round(od.pose7[4:], 3)})")
