@@ -317,7 +317,9 @@ __global__ void __launch_bounds__(kExtractThreads, 4) k_ring_extract(ExtractPara
     if (tid == 0) s_work = (int)atomicAdd(&P.ctrl[0], 1u);
     if (tid < kSectors) s_ccnt[tid] = 0;
     __syncthreads();
-    const int s = s_work / P.num_lines, r = s_work % P.num_lines;
+    // ring-major over the batch: ring r of a scan starts a whole wave of CTAs after its rings 0..r-1, so by the time it looks
+    // back for their counts they have long been published (scan-major order made ring 63 wait for 63 siblings started with it)
+    const int s = s_work % P.batch, r = s_work / P.batch;
     const unsigned epoch = *reinterpret_cast<volatile unsigned int*>(&P.ctrl[1]);
     const int n = P.n[s];
     const uint8_t* rid = P.ringid + (size_t)s * P.stride;
