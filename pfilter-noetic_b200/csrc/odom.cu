@@ -92,7 +92,7 @@ struct AppendParams {
     int write_pose;   // first pair of the frame: publish the pose
     OdomShared* sh; const LmState* S;
     int map_cap;      // capacity of the map buffers (points)
-    double* pose_hist; int hist_slot;
+    double* pose_hist;   // [kPoseHist][7]; slot = (frame of this update) % kPoseHist, the frame counter lives in OdomShared
 };
 
 // odom <- (q_w_curr, t_w_curr) (:278-280) and addPointsToMap's append loop (:592-604)
@@ -109,7 +109,8 @@ __global__ void __launch_bounds__(256) k_append(AppendParams A) {
         if (kind == 0 && A.write_pose) {
             quat_to_mat(s_pose, A.sh->odom.R);
             for (int i = 0; i < 3; ++i) A.sh->odom.t[i] = s_pose[4 + i];
-            for (int i = 0; i < 7; ++i) { A.sh->pose[i] = s_pose[i]; A.pose_hist[7 * A.hist_slot + i] = s_pose[i]; }
+            const int hist_slot = (int)((A.sh->frame + 1) % kPoseHist);      // this update is frame (last finished + 1)
+            for (int i = 0; i < 7; ++i) { A.sh->pose[i] = s_pose[i]; A.pose_hist[7 * hist_slot + i] = s_pose[i]; }
         }
     }
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -139,14 +140,14 @@ __global__ void __launch_bounds__(256) k_init_map(InitParams I) {
     }
 }
 
-__global__ void k_check_map_cap(const int* n_map0, const int* n_map1, int slot0, int slot1, int cap, OdomShared* sh, long long frame,
+__global__ void k_check_map_cap(const int* n_map0, const int* n_map1, int slot0, int slot1, int cap, OdomShared* sh, int last_pair,
                                 const unsigned* merge_err) {
     if (threadIdx.x != 0) return;
     if (*n_map0 > cap || *n_map1 > cap) atomicOr(&sh->err, 1);
     if (*merge_err) atomicOr(&sh->err, (int)(*merge_err & 30u));
     sh->n_map[slot0] = *n_map0;
     sh->n_map[slot1] = *n_map1;
-    sh->frame = frame;
+    if (last_pair) sh->frame += 1;     // the frame this block now describes
 }
 
 }  // namespace pf
@@ -211,6 +212,14 @@ struct pf_odom {
     int ring_add[kRing][kKinds] = {};
     long long ring_head = 0;             // frames recorded in the ring
     long long known_frame = -1;          // newest frame whose exact map sizes have been folded into map_ub
+    // steady-state replay: the launch sequence of one update (optimization_count == 2) captured as a CUDA graph per map buffer
+    bool use_graph = true;               // PF_ODOM_GRAPH=0 disables
+    cudaGraphExec_t graph_exec[2] = {nullptr, nullptr};
+    const float4* graph_feat[2][kKinds] = {};
+    const int* graph_nfeat[2][kKinds] = {};
+    int graph_ub[2][kKinds] = {};        // feature upper bounds the graph was sized for
+    int graph_mub[2][kKinds] = {};       // map upper bounds the graph was sized for
+    uint64_t graph_launches[2] = {0, 0};
     // optional phase timing (PF_ODOM_TIMING=1): CUDA events at the phase boundaries of the last update
     bool timing = false;
     cudaEvent_t tev[8] = {};
@@ -272,6 +281,7 @@ int odom_alloc(pf_odom* h) {
     PF_CUDA(cudaMallocHost(&h->h_iter, sizeof(double) * 16 * 7));
     PF_CUDA(cudaMallocHost(&h->h_ring, sizeof(OdomShared) * pf_odom::kRing));
     h->timing = getenv("PF_ODOM_TIMING") != nullptr;
+    { const char* g = getenv("PF_ODOM_GRAPH"); h->use_graph = !(g && g[0] == '0') && !h->timing; }
     if (h->timing) for (int i = 0; i < 8; ++i) PF_CUDA(cudaEventCreate(&h->tev[i]));
     for (int i = 0; i < pf_odom::kRing; ++i) PF_CUDA(cudaEventCreateWithFlags(&h->ring_ev[i], cudaEventDisableTiming));
     k_odom_reset<<<1, 32, 0, h->stream>>>(h->d_sh, h->d_state);
@@ -352,23 +362,10 @@ int enqueue_init(pf_odom* h, const float4* const feat[kKinds], const int* const 
     return PF_OK;
 }
 
-int enqueue_update(pf_odom* h, const float4* const feat_in[kKinds], const int* const n_feat_in[kKinds], const int ub_in[kKinds]) {
-    if (h->optimization_count > 2) h->optimization_count--;   // :232-233
-    ring_refresh(h);
-    const float4* feat[kKinds];
-    const int* n_feat[kKinds];
-    int ub[kKinds], mub[kKinds];
-    for (int k = 0; k < kKinds; ++k) {
-        const bool live = k < h->nk;
-        feat[k] = live ? feat_in[k] : h->d_feat[kNull];
-        n_feat[k] = live ? n_feat_in[k] : h->d_nfeat + kNull;
-        ub[k] = live ? ub_in[k] : 0;
-        if (ub[k] > h->fcap) ub[k] = h->fcap;
-        if (live && ub[k] < 1) ub[k] = 1;
-        mub[k] = live ? (h->map_ub[k] > 1 ? h->map_ub[k] : 1) : 0;
-    }
-    const int passes = h->optimization_count;
-    h->last_passes = passes;
+// The launch sequence of one update, enqueued on h->stream (directly, or into a stream capture).  ub / mub: upper bounds of the
+// feature and map counts (launch geometry only: every kernel is grid-stride or persistent and reads the exact device counts).
+int record_update(pf_odom* h, const float4* const feat[kKinds], const int* const n_feat[kKinds], const int ub[kKinds], const int mub[kKinds],
+                  int passes, bool sorted_known, int app[kKinds]) {
     Workspace& ws = h->ws;
     const int cur = h->cur, nxt = cur ^ 1;
     auto mark = [&](int i) { if (h->timing) cudaEventRecord(h->tev[i], h->stream); };
@@ -443,7 +440,7 @@ int enqueue_update(pf_odom* h, const float4* const feat_in[kKinds], const int* c
     mark(4);
     // append + map maintenance
     const float mres = (float)h->prm.map_resolution;   // rgbds(tmp, map_resolution [* 2]) with the float member map_resolution (:625-626)
-    int app[kKinds] = {0, 0, 0, 0};
+    for (int k = 0; k < kKinds; ++k) app[k] = 0;
     for (int p = 0; p < h->npairs; ++p) {
         AppendParams P{};
         for (int j = 0; j < 2; ++j) {
@@ -452,7 +449,7 @@ int enqueue_update(pf_odom* h, const float4* const feat_in[kKinds], const int* c
         }
         P.write_pose = p == 0;
         P.sh = h->d_sh; P.S = h->d_state; P.map_cap = h->bufcap;
-        P.pose_hist = h->d_pose_hist; P.hist_slot = (int)(h->frame % kPoseHist);
+        P.pose_hist = h->d_pose_hist;
         k_append<<<dim3(kSMs, 2), 256, 0, h->stream>>>(P);
         ws.launches += 1;
     }
@@ -473,23 +470,90 @@ int enqueue_update(pf_odom* h, const float4* const feat_in[kKinds], const int* c
             const int k = h->pair[p][j];
             app[k] = mub[k] + ub[k] < h->bufcap ? mub[k] + ub[k] : h->bufcap;
             // unsorted part: everything on the first update (raw first-frame maps), later last update's exceptions + this frame's points
-            capb[j] = h->sorted_known ? (kMergeExcCap + ub[k] < app[k] ? kMergeExcCap + ub[k] : app[k]) : app[k];
+            capb[j] = sorted_known ? (kMergeExcCap + ub[k] < app[k] ? kMergeExcCap + ub[k] : app[k]) : app[k];
             if (k == kNull) capb[j] = 0;
             capa[j] = mub[k];
         }
         PF_CHECK(map_merge(ws, M, capb[0], capb[1], capa[0], capa[1]));
-        k_check_map_cap<<<1, 32, 0, h->stream>>>(h->d_nmap[nxt] + ka, h->d_nmap[nxt] + kb, ka, kb, h->mcap, h->d_sh, h->frame, map_merge_error_word(ws));
+        k_check_map_cap<<<1, 32, 0, h->stream>>>(h->d_nmap[nxt] + ka, h->d_nmap[nxt] + kb, ka, kb, h->mcap, h->d_sh, p == h->npairs - 1 ? 1 : 0, map_merge_error_word(ws));
         ws.launches += 1;
     }
-    h->sorted_known = true;
     PF_CUDA(cudaGetLastError());
-    h->cur = nxt;
     mark(5);
+    return PF_OK;
+}
+
+int enqueue_update(pf_odom* h, const float4* const feat_in[kKinds], const int* const n_feat_in[kKinds], const int ub_in[kKinds]) {
+    if (h->optimization_count > 2) h->optimization_count--;   // :232-233
+    ring_refresh(h);
+    const float4* feat[kKinds];
+    const int* n_feat[kKinds];
+    int ub[kKinds], mub[kKinds], app[kKinds];
+    for (int k = 0; k < kKinds; ++k) {
+        const bool live = k < h->nk;
+        feat[k] = live ? feat_in[k] : h->d_feat[kNull];
+        n_feat[k] = live ? n_feat_in[k] : h->d_nfeat + kNull;
+        ub[k] = live ? ub_in[k] : 0;
+        if (ub[k] > h->fcap) ub[k] = h->fcap;
+        if (live && ub[k] < 1) ub[k] = 1;
+        mub[k] = live ? (h->map_ub[k] > 1 ? h->map_ub[k] : 1) : 0;
+    }
+    const int passes = h->optimization_count;
+    h->last_passes = passes;
+    const int cur = h->cur;
+    bool replayed = false;
+    if (h->use_graph && passes == 2 && h->sorted_known) {
+        // steady state: replay the captured launch sequence of this map buffer; (re)capture when the inputs moved or outgrew its sizing
+        bool fits = h->graph_exec[cur] != nullptr;
+        for (int k = 0; k < kKinds && fits; ++k)
+            fits = h->graph_feat[cur][k] == feat[k] && h->graph_nfeat[cur][k] == n_feat[k] && ub[k] <= h->graph_ub[cur][k] && mub[k] <= h->graph_mub[cur][k];
+        if (!fits) {
+            int gub[kKinds], gmub[kKinds];
+            for (int k = 0; k < kKinds; ++k) {
+                const bool live = k < h->nk;
+                gub[k] = live ? (ub[k] + ub[k] / 4 + 1024 < h->fcap ? ub[k] + ub[k] / 4 + 1024 : h->fcap) : 0;   // headroom: scans differ in size
+                const long long want = 2ll * mub[k] + 32768;
+                gmub[k] = live ? (int)(want < h->bufcap ? want : h->bufcap) : 0;
+            }
+            if (h->graph_exec[cur]) { cudaGraphExecDestroy(h->graph_exec[cur]); h->graph_exec[cur] = nullptr; }
+            cudaGraph_t graph = nullptr;
+            const uint64_t l0 = h->ws.launches;
+            bool ok = cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+            if (ok) {
+                const int rc = record_update(h, feat, n_feat, gub, gmub, passes, true, app);
+                ok = cudaStreamEndCapture(h->stream, &graph) == cudaSuccess && rc == PF_OK && graph != nullptr;
+            }
+            if (ok) ok = cudaGraphInstantiate(&h->graph_exec[cur], graph, 0) == cudaSuccess;
+            if (graph) cudaGraphDestroy(graph);
+            h->graph_launches[cur] = h->ws.launches - l0;
+            h->ws.launches = l0;
+            if (!ok) {          // capture not possible on this driver: run the plain launch sequence from now on
+                cudaGetLastError();
+                h->graph_exec[cur] = nullptr;
+                h->use_graph = false;
+            } else {
+                for (int k = 0; k < kKinds; ++k) {
+                    h->graph_feat[cur][k] = feat[k]; h->graph_nfeat[cur][k] = n_feat[k];
+                    h->graph_ub[cur][k] = gub[k]; h->graph_mub[cur][k] = gmub[k];
+                }
+            }
+        }
+        if (h->graph_exec[cur]) {
+            PF_CUDA(cudaGraphLaunch(h->graph_exec[cur], h->stream));
+            h->ws.launches += h->graph_launches[cur];
+            for (int k = 0; k < kKinds; ++k) app[k] = mub[k] + ub[k] < h->bufcap ? mub[k] + ub[k] : h->bufcap;
+            replayed = true;
+        }
+    }
+    if (!replayed) PF_CHECK(record_update(h, feat, n_feat, ub, mub, passes, h->sorted_known, app));
+    h->sorted_known = true;
+    h->cur = cur ^ 1;
     for (int k = 0; k < kKinds; ++k) h->map_ub[k] = app[k];     // the update never grows a map beyond old + appended
     PF_CHECK(ring_record(h, ub));
     h->frame += 1;
     return PF_OK;
 }
+
 
 int finish_frame(pf_odom* h, double pose_out[7]) {
     PF_CUDA(cudaMemcpyAsync(h->h_sh, h->d_sh, sizeof(OdomShared), cudaMemcpyDeviceToHost, h->stream));
@@ -560,6 +624,7 @@ extern "C" int pf_odom_destroy(pf_odom* h) {
     if (!h) return PF_OK;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    for (int b = 0; b < 2; ++b) if (h->graph_exec[b]) cudaGraphExecDestroy(h->graph_exec[b]);
     workspace_destroy(h->ws);
     map_merge_scratch_destroy(h->msc);
     cudaFree(h->d_nfeat); cudaFree(h->d_nds); cudaFree(h->d_geom); cudaFree(h->d_nmap[0]); cudaFree(h->d_nmap[1]);
