@@ -579,9 +579,18 @@ struct pf_extract {
     int* h_counts = nullptr;       // [3 * max_batch]: n, n_edge, n_surf
     unsigned int* h_ctrl = nullptr;
     uint64_t launches = 0;
-    // result of the last single-scan run (device resident hand-off to the odometry)
+    // result of the last single-scan run (device resident hand-off to the odometry).  Single-scan outputs are double
+    // buffered (slot toggles per scan) so that the extraction of the next frame can run while the odometry still reads this one.
     int last_valid = 0;
     int last_n = 0;
+    int slot = 0;
+    float4* d_edge1 = nullptr;       // slot 1 (slot 0 = d_edge / d_surf / d_n_edge / d_n_surf, shared with the batched path)
+    float4* d_surf1 = nullptr;
+    int* d_cnt1 = nullptr;           // [2] n_edge, n_surf of slot 1
+    float4* out_edge() const { return slot ? d_edge1 : d_edge; }
+    float4* out_surf() const { return slot ? d_surf1 : d_surf; }
+    int* out_n_edge() const { return slot ? d_cnt1 : d_n_edge; }
+    int* out_n_surf() const { return slot ? d_cnt1 + 1 : d_n_surf; }
 };
 
 namespace pf {
@@ -701,6 +710,9 @@ extern "C" int pf_extract_create(const pf_lidar_params* lidar, const pf_extract_
     PF_CUDA(cudaMalloc(&h->d_edge, (size_t)h->max_batch * h->edge_stride * 16));
     PF_CUDA(cudaMalloc(&h->d_surf, np * 16));
     PF_CUDA(cudaMalloc(&h->d_n, sizeof(int) * h->max_batch));
+    PF_CUDA(cudaMalloc(&h->d_edge1, (size_t)h->edge_stride * 16));
+    PF_CUDA(cudaMalloc(&h->d_surf1, (size_t)h->stride * 16));
+    PF_CUDA(cudaMalloc(&h->d_cnt1, sizeof(int) * 2));
     PF_CUDA(cudaMalloc(&h->d_n_edge, sizeof(int) * h->max_batch));
     PF_CUDA(cudaMalloc(&h->d_n_surf, sizeof(int) * h->max_batch));
     PF_CUDA(cudaMalloc(&h->d_done, sizeof(unsigned long long) * h->max_batch * kMaxLines));
@@ -719,6 +731,7 @@ extern "C" int pf_extract_destroy(pf_extract* h) {
     cudaStreamSynchronize(h->stream);
     cudaFree(h->d_pts); cudaFree(h->d_ringid); cudaFree(h->d_ring_tiles); cudaFree(h->d_tile_pure); cudaFree(h->d_label); cudaFree(h->d_edge);
     cudaFree(h->d_surf); cudaFree(h->d_n); cudaFree(h->d_n_edge); cudaFree(h->d_n_surf); cudaFree(h->d_done);
+    cudaFree(h->d_edge1); cudaFree(h->d_surf1); cudaFree(h->d_cnt1);
     cudaFree(h->d_ctrl);
     cudaFreeHost(h->h_counts); cudaFreeHost(h->h_ctrl);
     cudaStreamDestroy(h->stream);
@@ -764,8 +777,9 @@ int pf_extract_enqueue_single(pf_extract* h, const float* xyzi, int n, int devic
     } else if (n > 0) {
         PF_CUDA(cudaMemcpyAsync(h->d_pts, xyzi, (size_t)n * 16, cudaMemcpyHostToDevice, h->stream));
     }
-    PF_CHECK(extract_launch(h, src ? src : h->d_pts, h->d_n, 1, h->stride, h->d_edge, h->d_n_edge, h->edge_stride, h->d_surf,
-                            h->d_n_surf, want_label ? h->d_label : nullptr));
+    h->slot ^= 1;
+    PF_CHECK(extract_launch(h, src ? src : h->d_pts, h->d_n, 1, h->stride, h->out_edge(), h->out_n_edge(), h->edge_stride, h->out_surf(),
+                            h->out_n_surf(), want_label ? h->d_label : nullptr));
     h->last_valid = 1;
     h->last_n = n;
     return PF_OK;
@@ -773,8 +787,9 @@ int pf_extract_enqueue_single(pf_extract* h, const float* xyzi, int n, int devic
 
 // accessors for the device-resident hand-off (odom.cu)
 void pf_extract_device_outputs(pf_extract* h, const float4** edge, const int** n_edge, const float4** surf, const int** n_surf,
-                               cudaStream_t* stream, int* edge_cap, int* surf_cap) {
-    *edge = h->d_edge; *n_edge = h->d_n_edge; *surf = h->d_surf; *n_surf = h->d_n_surf; *stream = h->stream;
+                               cudaStream_t* stream, int* edge_cap, int* surf_cap, int* slot) {
+    *edge = h->out_edge(); *n_edge = h->out_n_edge(); *surf = h->out_surf(); *n_surf = h->out_n_surf(); *stream = h->stream;
+    *slot = h->slot;
     *edge_cap = h->edge_stride < h->last_n ? h->edge_stride : h->last_n; *surf_cap = h->last_n;   // upper bounds of the device counts
 }
 
@@ -821,13 +836,13 @@ extern "C" int pf_extract_run(pf_extract* h, const float* xyzi, int n, float* ed
     PF_REQUIRE(h && edge && n_edge && surf && n_surf, "null argument");
     PF_CHECK(pf_extract_enqueue_single(h, xyzi, n, 0, label != nullptr));
     int* hc = h->h_counts + h->max_batch;
-    PF_CUDA(cudaMemcpyAsync(hc, h->d_n_edge, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-    PF_CUDA(cudaMemcpyAsync(hc + 1, h->d_n_surf, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    PF_CUDA(cudaMemcpyAsync(hc, h->out_n_edge(), sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    PF_CUDA(cudaMemcpyAsync(hc + 1, h->out_n_surf(), sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     PF_CHECK(extract_check_ctrl(h));
     *n_edge = hc[0];
     *n_surf = hc[1];
-    if (*n_edge > 0) PF_CUDA(cudaMemcpyAsync(edge, h->d_edge, (size_t)*n_edge * 16, cudaMemcpyDeviceToHost, h->stream));
-    if (*n_surf > 0) PF_CUDA(cudaMemcpyAsync(surf, h->d_surf, (size_t)*n_surf * 16, cudaMemcpyDeviceToHost, h->stream));
+    if (*n_edge > 0) PF_CUDA(cudaMemcpyAsync(edge, h->out_edge(), (size_t)*n_edge * 16, cudaMemcpyDeviceToHost, h->stream));
+    if (*n_surf > 0) PF_CUDA(cudaMemcpyAsync(surf, h->out_surf(), (size_t)*n_surf * 16, cudaMemcpyDeviceToHost, h->stream));
     if (label && n > 0) PF_CUDA(cudaMemcpyAsync(label, h->d_label, (size_t)n, cudaMemcpyDeviceToHost, h->stream));
     PF_CUDA(cudaStreamSynchronize(h->stream));
     return PF_OK;

@@ -156,13 +156,14 @@ using namespace pf;
 
 // accessors implemented in extract.cu
 void pf_extract_device_outputs(pf_extract* h, const float4** edge, const int** n_edge, const float4** surf, const int** n_surf,
-                               cudaStream_t* stream, int* edge_cap, int* surf_cap);
+                               cudaStream_t* stream, int* edge_cap, int* surf_cap, int* slot);
 int pf_extract_enqueue_single(pf_extract* h, const float* xyzi, int n, int device_input, int want_label);
 
 struct pf_odom {
     int device = 0;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev = nullptr, ev_done = nullptr;
+    cudaEvent_t ev = nullptr, ev_done[2] = {nullptr, nullptr};   // ev_done[slot]: the odometry has consumed the extractor's output slot
+    bool ev_done_set[2] = {false, false};
     pf_odom_params prm{};
     int fcap = 0, mcap = 0, bufcap = 0;
     // feature kinds and the pairs they are processed in
@@ -608,7 +609,7 @@ int odom_create(const pf_odom_params* p, int device, bool bpf, pf_odom** out) {
     h->bufcap = h->mcap + h->fcap;
     PF_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     PF_CUDA(cudaEventCreateWithFlags(&h->ev, cudaEventDisableTiming));
-    PF_CUDA(cudaEventCreateWithFlags(&h->ev_done, cudaEventDisableTiming));
+    for (int b = 0; b < 2; ++b) PF_CUDA(cudaEventCreateWithFlags(&h->ev_done[b], cudaEventDisableTiming));
     int rc = odom_alloc(h);
     if (rc != PF_OK) { pf_odom_destroy(h); return rc; }
     *out = h;
@@ -639,7 +640,7 @@ extern "C" int pf_odom_destroy(pf_odom* h) {
     cudaFreeHost(h->h_sh); cudaFreeHost(h->h_state); cudaFreeHost(h->h_counts); cudaFreeHost(h->h_iter); cudaFreeHost(h->h_ring);
     for (int i = 0; i < pf_odom::kRing; ++i) if (h->ring_ev[i]) cudaEventDestroy(h->ring_ev[i]);
     if (h->ev) cudaEventDestroy(h->ev);
-    if (h->ev_done) cudaEventDestroy(h->ev_done);
+    for (int b = 0; b < 2; ++b) if (h->ev_done[b]) cudaEventDestroy(h->ev_done[b]);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return PF_OK;
@@ -697,7 +698,8 @@ static int process_extracted(pf_odom* h, pf_extract* ex, double pose_out[7], boo
     const int* nf[kKinds] = {};
     int ub[kKinds] = {0, 0, 0, 0};
     cudaStream_t exs;
-    pf_extract_device_outputs(ex, &feat[0], &nf[0], &feat[1], &nf[1], &exs, &ub[0], &ub[1]);
+    int slot = 0;
+    pf_extract_device_outputs(ex, &feat[0], &nf[0], &feat[1], &nf[1], &exs, &ub[0], &ub[1], &slot);
     PF_REQUIRE(ub[1] <= h->fcap, "scan of %d points exceeds max_features %d", ub[1], h->fcap);
     PF_CUDA(cudaEventRecord(h->ev, exs));
     PF_CUDA(cudaStreamWaitEvent(h->stream, h->ev, 0));
@@ -706,9 +708,11 @@ static int process_extracted(pf_odom* h, pf_extract* ex, double pose_out[7], boo
     } else {
         PF_CHECK(enqueue_update(h, feat, nf, ub));
     }
-    // the extractor's output buffers are reused by the next frame: it must not start before this frame consumed them
-    PF_CUDA(cudaEventRecord(h->ev_done, h->stream));
-    PF_CUDA(cudaStreamWaitEvent(exs, h->ev_done, 0));
+    // The extractor's outputs are double buffered: the next extraction writes the OTHER slot, so it may run while this update
+    // still reads this one; it only has to wait for the update that read that other slot (the previous frame).
+    PF_CUDA(cudaEventRecord(h->ev_done[slot], h->stream));
+    h->ev_done_set[slot] = true;
+    if (h->ev_done_set[slot ^ 1]) PF_CUDA(cudaStreamWaitEvent(exs, h->ev_done[slot ^ 1], 0));
     return sync ? finish_frame(h, pose_out) : PF_OK;
 }
 
