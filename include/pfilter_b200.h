@@ -166,6 +166,14 @@ int pf_frame_process(pf_extract* ex, pf_odom* od, const float* xyzi, int n, doub
  * synchronisation (frames can be queued back to back; errors surface at pf_odom_sync). */
 int pf_frame_process_device(pf_extract* ex, pf_odom* od, const void* d_xyzi, int n, double* pose_out);
 int pf_odom_sync(pf_odom* h);
+int pf_odom_result_bytes(void);   /* bytes read back from the device per frame (pose, map sizes, error bits) */
+/* Pipelined whole frame from a HOST scan: submit enqueues H2D + extraction + odometry and returns at once with the frame's id
+ * (0 = the init frame); wait blocks until that frame is done and returns its pose.  Submitting frame k+1 before waiting for
+ * frame k overlaps the upload / extraction of the next scan with the odometry of the current one (the reference overlaps them
+ * by running its nodes as separate processes).  xyzi must stay valid -- and should be pinned (pf_host_alloc) -- until the
+ * frame has been waited for; at most 32 frames may be outstanding. */
+int pf_frame_submit(pf_extract* ex, pf_odom* od, const float* xyzi, int n, long long* frame_id);
+int pf_frame_wait(pf_odom* od, long long frame_id, double pose_out[7]);
 /* poses of updates first_frame .. first_frame+count-1 (frame 0 is the init frame; history depth 4096 frames) */
 int pf_odom_get_pose_history(pf_odom* h, long long first_frame, int count, double* poses);
 

@@ -432,6 +432,20 @@ class Mapping:
         return {"n_sorted": ns.value, "dropped": dr.value, "launches": la.value}
 
 
+def frame_submit(extractor, odometry, xyzi):
+    """pf_frame_submit: asynchronous; returns the frame id.  `xyzi` must stay alive (pinned) until frame_wait(frame id)."""
+    a = as_points(xyzi)
+    fid = C.c_longlong()
+    check(lib().pf_frame_submit(extractor.h, odometry.h, _vp(a), len(a), C.byref(fid)))
+    return fid.value
+
+
+def frame_wait(odometry, frame_id):
+    pose = np.zeros(7)
+    check(lib().pf_frame_wait(odometry.h, C.c_longlong(frame_id), _vp(pose)))
+    return pose
+
+
 def frame_process(extractor, odometry, xyzi):
     """pf_frame_process: H2D scan -> extract -> (init | update) -> pose."""
     a = as_points(xyzi)

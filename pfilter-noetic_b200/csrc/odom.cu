@@ -732,6 +732,39 @@ extern "C" int pf_frame_process_device(pf_extract* ex, pf_odom* od, const void* 
     return process_extracted(od, ex, pose_out, pose_out != nullptr);
 }
 
+// Pipelined form of pf_frame_process: submit returns as soon as the frame is enqueued (H2D copy, extraction, odometry), wait
+// blocks until that frame is done and hands out its pose.  A caller that submits frame k+1 before waiting for frame k overlaps the
+// upload and the extraction of the next scan with the odometry of the current one -- what the reference gets from running its
+// nodes as separate processes.  The scan buffer must stay valid (and should be pinned) until the frame has been waited for.
+extern "C" int pf_frame_submit(pf_extract* ex, pf_odom* od, const float* xyzi, int n, long long* frame_id) {
+    PF_REQUIRE(ex && od, "null handle");
+    PF_CHECK(pf_extract_enqueue_single(ex, xyzi, n, 0, 0));
+    PF_CHECK(process_extracted(od, ex, nullptr, false));
+    if (frame_id) *frame_id = od->frame - 1;
+    return PF_OK;
+}
+
+extern "C" int pf_frame_wait(pf_odom* h, long long frame_id, double pose_out[7]) {
+    PF_REQUIRE(h && pose_out, "null argument");
+    PF_CUDA(cudaSetDevice(h->device));
+    const long long lo = h->ring_head > pf_odom::kRing ? h->ring_head - pf_odom::kRing : 0;
+    for (long long i = h->ring_head - 1; i >= lo; --i) {
+        const int slot = (int)(i % pf_odom::kRing);
+        if (h->ring_frame[slot] != frame_id) continue;
+        PF_CUDA(cudaEventSynchronize(h->ring_ev[slot]));
+        const OdomShared& sh = h->h_ring[slot];
+        if (sh.err & 1) { set_error("local map exceeded max_map_points = %d", h->mcap); return PF_ERR_CAPACITY; }
+        if (sh.err & 30) { set_error("map update failed (bits %d)", sh.err & 30); return PF_ERR_CAPACITY; }
+        memcpy(pose_out, sh.pose, sizeof(double) * 7);
+        return PF_OK;
+    }
+    set_error("frame %lld is not among the last %d submitted frames", frame_id, pf_odom::kRing);
+    return PF_ERR_STATE;
+}
+
+// bytes the library reads back from the device per frame (the pose block: pose, map sizes, error bits)
+extern "C" int pf_odom_result_bytes(void) { return (int)sizeof(OdomShared); }
+
 extern "C" int pf_odom_sync(pf_odom* h) {
     PF_REQUIRE(h, "null handle");
     PF_CUDA(cudaSetDevice(h->device));

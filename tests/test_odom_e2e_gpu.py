@@ -102,3 +102,22 @@ def test_graph_replay_is_bit_identical_to_plain_launches(pfb, capi, monkeypatch)
     assert p1.tobytes() == p0.tobytes()
     assert m1[0].tobytes() == m0[0].tobytes() and m1[1].tobytes() == m0[1].tobytes()
     assert l1 == l0            # replayed kernels are counted like launched ones
+
+
+def test_pipelined_submit_wait_equals_synchronous_calls(pfb, capi):
+    p = pfb.synth.config("cfg2")
+    scans = [pfb.synth.scan(p, f) for f in range(16)]
+    ex, od = capi.Extractor(num_lines=64, max_points=131072), capi.Odometry(0.4, 0, 0.4, 75, max_map_points=262144)
+    sync = np.array([capi.frame_process(ex, od, s) for s in scans])
+    ex.close(); od.close()
+    ex, od = capi.Extractor(num_lines=64, max_points=131072), capi.Odometry(0.4, 0, 0.4, 75, max_map_points=262144)
+    ids = [capi.frame_submit(ex, od, s) for s in scans[:3]]          # three frames in flight
+    out = []
+    for k in range(3, len(scans)):
+        ids.append(capi.frame_submit(ex, od, scans[k]))
+        out.append(capi.frame_wait(od, ids[k - 3]))
+    out += [capi.frame_wait(od, i) for i in ids[-3:]]
+    assert ids == list(range(len(scans)))
+    assert np.array(out).tobytes() == sync.tobytes()
+    with pytest.raises(capi.PfError):
+        capi.frame_wait(od, 10_000)
