@@ -88,25 +88,6 @@ __device__ __forceinline__ void put_exception(const MapMergeParams& P, int cloud
     if ((int)slot < P.s.exc_cap) P.s.exc[(size_t)cloud * P.s.exc_cap + slot] = o;
 }
 
-// first index i in [0, n) with a[i] >= key; all 32 lanes of the warp call it with the same arguments (32-ary search)
-__device__ __forceinline__ int warp_lower_bound(const int* a, int n, int key) {
-    const int lane = (int)lane_id();
-    int lo = 0, hi = n;
-    while (hi - lo > 32) {
-        const int step = (hi - lo + 31) / 32;
-        const int idx = lo + (lane + 1) * step - 1;
-        const bool less = idx < hi && a[idx] < key;
-        const int c = __popc(__ballot_sync(0xffffffffu, less));
-        const int first_ge = lo + (c + 1) * step - 1;      // probe c is the first one that is not < key (if it exists)
-        const int nlo = lo + c * step;
-        hi = (c < 32 && first_ge < hi) ? first_ge : hi;
-        lo = nlo < hi ? nlo : hi;
-    }
-    const int idx = lo + lane;
-    const bool less = idx < hi && a[idx] < key;
-    return lo + __popc(__ballot_sync(0xffffffffu, less));
-}
-
 __global__ void __launch_bounds__(256) k_mm_keys(MapMergeParams P, uint32_t* __restrict__ keys) {
     const int cloud = blockIdx.y;
     const MapMergeCloud& c = P.c[cloud];
@@ -300,18 +281,25 @@ __global__ void __launch_bounds__(256) k_mm_count(MapMergeParams P) {
     const int tid = threadIdx.x;
     int cta_part = 0;
     const unsigned long long keep_in_l2 = l2_policy_evict_last();
-    for (int t = R.lo; t < R.hi; ++t) {
+    auto load_tile = [&](int t, Pt (&q)[4]) {
         const int base = t * kMergeTile;
-        int v = 0;
-        Pt p[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const int i = base + k * 256 + tid;        // coalesced: the count does not care which thread sees which point
-            p[k] = Pt{3.0e38f, 0.f, 0.f, 0u};     // far outside any crop box
-            if (i < mA) *reinterpret_cast<float4*>(&p[k]) = ld_f4_l2hint(c.buf + i, keep_in_l2);
+            q[k] = Pt{3.0e38f, 0.f, 0.f, 0u};         // far outside any crop box
+            if (i < mA) *reinterpret_cast<float4*>(&q[k]) = ld_f4_l2hint(c.buf + i, keep_in_l2);
         }
+    };
+    Pt p[4];
+    if (R.lo < R.hi) load_tile(R.lo, p);
+    for (int t = R.lo; t < R.hi; ++t) {
+        Pt nxt[4];
+        if (t + 1 < R.hi) load_tile(t + 1, nxt);       // the next tile's loads are in flight while this one is counted
+        int v = 0;
 #pragma unroll
         for (int k = 0; k < 4; ++k) v += (in_box(box, p[k]) && single_point_kept(P, p[k].rgba)) ? 1 : 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) p[k] = nxt[k];
         const int mLo = tm[t], mHi = tm[t + 1];
         for (int h = mLo + tid; h < mHi; h += 256) v += P.s.m_delta[lbase + h];
         if (tid == 0) v += ti[t + 1] - ti[t];
