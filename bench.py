@@ -324,6 +324,7 @@ def run_ours(args):
     capi.check(lib.pf_odom_get_pose_history(od.h, C.c_longlong(1), K - 1, hist.ctypes.data_as(C.c_void_p)))
     poses_dev = np.concatenate([np.array([[0, 0, 0, 1, 0, 0, 0.0]]), hist])
     stats = od.stats()
+    stats["graph_captures"] = od.graph_captures
     ex.close(); od.close()
 
     # ---- e2e (synchronous): one pf_frame_process per frame from pinned host memory ---------------------------------

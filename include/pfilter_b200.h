@@ -142,6 +142,9 @@ void* pf_odom_stream(pf_odom* h);
  * build, ms[2] optimisation passes up to the last association, ms[3] the last pass's 5 LM evaluations, ms[4] append + map update */
 int pf_odom_get_phase_ms(pf_odom* h, float ms[5]);
 int pf_odom_kernel_launches(pf_odom* h, uint64_t* launches);
+/* From the frame at which optimization_count has settled at 2, the launch sequence of an update is replayed as a CUDA graph (one
+ * per map ping-pong buffer; PF_ODOM_GRAPH=0 turns this off).  *n = number of captures so far. */
+int pf_odom_graph_captures(pf_odom* h, int* n);
 
 /* ------------------------------------------------------------------------------------------------
  * Odom_BPF_EstimationClass (include/odomEstimationClass.h:169-205, src/odomEstimationClass.cpp:649-1306): the reference's

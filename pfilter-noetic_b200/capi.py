@@ -349,6 +349,12 @@ class Odometry:
         check(lib().pf_odom_kernel_launches(self.h, C.byref(v)))
         return v.value
 
+    @property
+    def graph_captures(self):
+        v = C.c_int()
+        check(lib().pf_odom_graph_captures(self.h, C.byref(v)))
+        return v.value
+
 
 class OdometryBPF(Odometry):
     """Handle of pf_odom_bpf_* (replaces Odom_BPF_EstimationClass): beam / pillar / facade feature kinds."""

@@ -221,6 +221,8 @@ struct pf_odom {
     int graph_ub[2][kKinds] = {};        // feature upper bounds the graph was sized for
     int graph_mub[2][kKinds] = {};       // map upper bounds the graph was sized for
     uint64_t graph_launches[2] = {0, 0};
+    int graph_captures = 0;
+    int map_exact[kKinds] = {};          // last exactly known map sizes (read-backs); map_ub may run ahead of them when frames are queued
     // optional phase timing (PF_ODOM_TIMING=1): CUDA events at the phase boundaries of the last update
     bool timing = false;
     cudaEvent_t tev[8] = {};
@@ -327,7 +329,7 @@ void ring_refresh(pf_odom* h) {
             const int sj = (int)(j % pf_odom::kRing);
             for (int k = 0; k < kKinds; ++k) ub[k] += h->ring_add[sj][k];
         }
-        for (int k = 0; k < kKinds; ++k) h->map_ub[k] = ub[k] < h->bufcap ? ub[k] : h->bufcap;
+        for (int k = 0; k < kKinds; ++k) { h->map_ub[k] = ub[k] < h->bufcap ? ub[k] : h->bufcap; h->map_exact[k] = h->h_ring[slot].n_map[k]; }
         h->known_frame = h->ring_frame[slot];
         break;
     }
@@ -504,16 +506,19 @@ int enqueue_update(pf_odom* h, const float4* const feat_in[kKinds], const int* c
     const int cur = h->cur;
     bool replayed = false;
     if (h->use_graph && passes == 2 && h->sorted_known) {
-        // steady state: replay the captured launch sequence of this map buffer; (re)capture when the inputs moved or outgrew its sizing
+        // steady state: replay the captured launch sequence of this map buffer; (re)capture when the inputs moved or outgrew its
+        // sizing.  The sizing only sets grid dimensions (the kernels are grid-stride and read exact device counts), so the test uses
+        // the last exactly known map sizes, not the host's running upper bound, which runs ahead while frames are queued.
         bool fits = h->graph_exec[cur] != nullptr;
         for (int k = 0; k < kKinds && fits; ++k)
-            fits = h->graph_feat[cur][k] == feat[k] && h->graph_nfeat[cur][k] == n_feat[k] && ub[k] <= h->graph_ub[cur][k] && mub[k] <= h->graph_mub[cur][k];
+            fits = h->graph_feat[cur][k] == feat[k] && h->graph_nfeat[cur][k] == n_feat[k] && ub[k] <= h->graph_ub[cur][k] &&
+                   h->map_exact[k] <= h->graph_mub[cur][k];
         if (!fits) {
             int gub[kKinds], gmub[kKinds];
             for (int k = 0; k < kKinds; ++k) {
                 const bool live = k < h->nk;
                 gub[k] = live ? (ub[k] + ub[k] / 4 + 1024 < h->fcap ? ub[k] + ub[k] / 4 + 1024 : h->fcap) : 0;   // headroom: scans differ in size
-                const long long want = 2ll * mub[k] + 32768;
+                const long long want = 2ll * h->map_exact[k] + 65536;
                 gmub[k] = live ? (int)(want < h->bufcap ? want : h->bufcap) : 0;
             }
             if (h->graph_exec[cur]) { cudaGraphExecDestroy(h->graph_exec[cur]); h->graph_exec[cur] = nullptr; }
@@ -528,6 +533,7 @@ int enqueue_update(pf_odom* h, const float4* const feat_in[kKinds], const int* c
             if (graph) cudaGraphDestroy(graph);
             h->graph_launches[cur] = h->ws.launches - l0;
             h->ws.launches = l0;
+            h->graph_captures += 1;
             if (!ok) {          // capture not possible on this driver: run the plain launch sequence from now on
                 cudaGetLastError();
                 h->graph_exec[cur] = nullptr;
@@ -570,7 +576,7 @@ int finish_frame(pf_odom* h, double pose_out[7]) {
     }
     if (pose_out) memcpy(pose_out, h->h_sh->pose, sizeof(double) * 7);
     if (h->inited) {
-        for (int k = 0; k < kKinds; ++k) h->map_ub[k] = h->h_sh->n_map[k];
+        for (int k = 0; k < kKinds; ++k) { h->map_ub[k] = h->h_sh->n_map[k]; h->map_exact[k] = h->h_sh->n_map[k]; }
         h->known_frame = h->frame - 1;
     }
     return PF_OK;
@@ -865,6 +871,13 @@ extern "C" int pf_odom_get_phase_ms(pf_odom* h, float ms[5]) {
 }
 
 extern "C" void* pf_odom_stream(pf_odom* h) { return h ? (void*)h->stream : nullptr; }
+
+// how many times the steady-state update has been captured as a CUDA graph so far (0: graphs off or not yet in steady state)
+extern "C" int pf_odom_graph_captures(pf_odom* h, int* n) {
+    PF_REQUIRE(h && n, "null argument");
+    *n = h->graph_captures;
+    return PF_OK;
+}
 
 extern "C" int pf_odom_kernel_launches(pf_odom* h, uint64_t* launches) {
     PF_REQUIRE(h && launches, "null argument");
