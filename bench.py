@@ -256,7 +256,25 @@ def extra_kernel_legs(capi, dev_index):
           "valid_fraction": valid, "algorithmic_gbs": 136.0 * nq / (ms_query * 1e-3) / 1e9,
           "traffic": _traffic().get("k4", {}).get("bytes_per_launch"), "l2_hit_pct": _traffic().get("k4", {}).get("knn", {}).get("l2_hit_pct"),
           "grid_build_gbs": 36.0 * len(m0) / (ms_build * 1e-3) / 1e9}
-    return {"k9_map_merge": k9, "k4_knn": k4}
+    # K10: global map (LaserMappingClass) grown to ~8 M points, then steady-state updates with one frame's worth of points;
+    # wall clock around pf_mapping_update + the wait for it (H2D of the frame's points included)
+    mp = capi.Mapping(0.4, max_map_points=10_000_000, max_points=262144, device=dev_index)
+    rt = np.eye(4)[:3].reshape(12)
+    while mp.size() < 8_000_000:
+        mp.update(((rng.random((262144, 4), dtype=np.float32) - 0.5) * np.array([240, 240, 60, 1], np.float32)).astype(np.float32), rt)
+    n0 = mp.size()
+    fpts = ((rng.random((80000, 4), dtype=np.float32) - 0.5) * np.array([120, 120, 10, 1], np.float32)).astype(np.float32)
+    ts = []
+    for k in range(8):
+        t0 = time.perf_counter()
+        mp.update(fpts + np.float32(0.01 * k), rt)
+        n1 = mp.size()
+        ts.append(time.perf_counter() - t0)
+    ms = 1e3 * float(np.median(ts[2:]))
+    k10 = {"kernel": "k_mp_* (K10 global map update: transform + 50 m cell binning + VoxelGrid merge, streaming)", "map_points": n0,
+           "new_points": len(fpts), "ms_per_update_wall": ms, "algorithmic_gbs": 40.0 * n0 / (ms * 1e-3) / 1e9, "bytes_per_map_point": 40}
+    mp.close()
+    return {"k9_map_merge": k9, "k4_knn": k4, "k10_global_map": k10}
 
 
 def run_ours(args):

@@ -10,10 +10,13 @@
 //                written behind the map in input order
 //   k_mp_keys    31-bit key (cell inside the 5x5x5 block : 7 | voxel inside the cell : 3 x 8) of every unsorted point
 //   radix_sort   stable -> canonical summation order (ascending input index)
-//   k_mp_heads   one thread per voxel run of the sorted new points: binary search in the sorted map; runs that meet a map
-//                point are "matched", the others are reduced to finished voxels ("inserts")
-//   k_mp_merge   ONE streaming pass over the map: cells outside the block pass through, block cells merge their matched
-//                runs (VoxelGrid centroid of x, y, z, intensity) and take the inserts in key order
+//   k_mp_heads   one thread per voxel run of the sorted new points: binary search in the sorted map; a run that meets a map
+//                point is finished right there (VoxelGrid centroid of map point + run: x, y, z, intensity) and becomes that
+//                point's replacement, the others are reduced to finished voxels ("inserts")
+//   k_mp_tiles   per tile of 1024 map points: its replacements / inserts and how many points it will emit (no pass over the map
+//                is needed for that: every map point survives unless its replacement left the voxel) + per-CTA sums
+//   k_mp_write   ONE streaming pass over the map, no inter-CTA dependency (output offsets = prefix of the tile counts): cells
+//                outside the block pass through, replacements are substituted, inserts placed in key order
 //   k_mp_finish  appends "exceptions" (centroids that float rounding pushed out of their voxel) behind the sorted part
 // A point keeps the cell it was first binned into (the reference never re-bins: the cloud a centroid lives in is its cell),
 // hence the 4-byte cell id beside every point: 20 B read + 20 B written per map point per update, O(map) streaming instead
@@ -29,6 +32,7 @@ constexpr unsigned kBadKey = 0xffffffffu;
 constexpr unsigned kNoCell = 0xffffffffu;
 constexpr int kBlock = 5;            // 2 * LASER_CELL_RANGE + 1 cells per axis (include/laserMappingClass.h:29-30)
 constexpr int kExcCap = 4096;
+constexpr int kMpMaxGrid = 8 * kSMs;   // CTAs of the write pass
 
 struct MapperParams {
     float4* buf;  unsigned* cbuf;     // current map: points + cell ids, [0, n_sorted) sorted | exceptions | this frame's points
@@ -37,8 +41,11 @@ struct MapperParams {
     unsigned long long* dropped;      // device: points that fell outside the 5x5x5 block (the reference's out-of-range access)
     float inv_leaf;
     int bx, by, bz;                   // lowest cell of the block around the pose
-    int *m_ra, *m_start, *m_len, *i_ra;
+    int *m_ra, *m_keep, *i_ra;        // replacements: map index, kept (0 = the centroid left its voxel -> exception)
+    float4* m_pt;                     // replacement points
     float4* i_pt;  unsigned* i_cell;
+    int *tile_m, *tile_i, *tile_agg, *cta_sum;   // per 1024-point tile: first replacement / insert, points emitted; per CTA of the write pass
+    int tile_cap, write_grid;
     float4* exc;   unsigned* exc_cell;
     unsigned* state;                  // [0] nB [2] nvalid [4] n matched [6] n inserts [10] n exceptions
 };
@@ -189,20 +196,20 @@ __global__ void __launch_bounds__(256) k_mp_heads(MapperParams P, const uint32_t
                     const unsigned ca = P.cbuf[rA];
                     matched = ca == cell && vox24(P.buf[rA], ca, P.inv_leaf) == v24;
                 }
-                if (!matched) {
-                    Acc4 acc;
-                    for (int q = e; q < e2; ++q) acc_add(acc, bpts[vals[q]]);
-                    o = acc_mean(acc);
-                    if (acc.n > 1 && vox24(o, cell, P.inv_leaf) != v24) put_exception(P, o, cell);
-                    else ins = true;
-                }
+                Acc4 acc;
+                if (matched) acc_add(acc, P.buf[rA]);        // the map point leads the voxel's sum
+                for (int q = e; q < e2; ++q) acc_add(acc, bpts[vals[q]]);
+                o = acc_mean(acc);
+                bool keep = true;
+                if (acc.n > 1 && vox24(o, cell, P.inv_leaf) != v24) { put_exception(P, o, cell); keep = false; }
+                if (matched) len = keep ? 1 : 0; else ins = keep;
             }
         }
         const unsigned tag = (ctrl[0] << 3);
         int total_m, total_i;
         const int lm = block_scan_excl_256(matched ? 1 : 0, s_tmp, &total_m);
         const unsigned excl_m = chained_scan_exclusive(status, tag | 2u, tile, (unsigned)total_m, s_look);
-        if (matched) { const int idx = (int)excl_m + lm; P.m_ra[idx] = rA; P.m_start[idx] = e; P.m_len[idx] = len; }
+        if (matched) { const int idx = (int)excl_m + lm; P.m_ra[idx] = rA; P.m_pt[idx] = o; P.m_keep[idx] = len; }
         const int li = block_scan_excl_256(ins ? 1 : 0, s_tmp, &total_i);
         const unsigned excl_i = chained_scan_exclusive(status + status_stride, tag | 3u, tile, (unsigned)total_i, s_look);
         if (ins) { const int idx = (int)excl_i + li; P.i_ra[idx] = rA; P.i_pt[idx] = o; P.i_cell[idx] = cell; }
@@ -213,120 +220,125 @@ __global__ void __launch_bounds__(256) k_mp_heads(MapperParams P, const uint32_t
     }
 }
 
-// first index i in [0, n) with a[i] >= key (whole warp, same arguments)
-__device__ __forceinline__ int warp_lower_bound_i(const int* a, int n, int key) {
-    const int lane = (int)lane_id();
-    int lo = 0, hi = n;
-    while (hi - lo > 32) {
-        const int step = (hi - lo + 31) / 32;
-        const int idx = lo + (lane + 1) * step - 1;
-        const bool less = idx < hi && a[idx] < key;
-        const int c = __popc(__ballot_sync(0xffffffffu, less));
-        const int first_ge = lo + (c + 1) * step - 1;
-        const int nlo = lo + c * step;
-        hi = (c < 32 && first_ge < hi) ? first_ge : hi;
-        lo = nlo < hi ? nlo : hi;
-    }
-    const int idx = lo + lane;
-    const bool less = idx < hi && a[idx] < key;
-    return lo + __popc(__ballot_sync(0xffffffffu, less));
+__device__ __forceinline__ int lower_bound_i(const int* __restrict__ a, int lo, int hi, int key) {
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (a[mid] < key) lo = mid + 1; else hi = mid; }
+    return lo;
 }
 
-__global__ void __launch_bounds__(256) k_mp_merge(MapperParams P, const uint32_t* __restrict__ vals, unsigned long long* status, unsigned* ctrl) {
-    __shared__ int s_link[kMpTile];
-    __shared__ int s_cnt[kMpTile + 1];
-    __shared__ int s_first[kMpTile + 1];
-    __shared__ int s_pre[kMpTile + 1];
-    __shared__ int s_rng[4];
-    __shared__ int s_tile;
-    __shared__ int s_tmp[9];
-    __shared__ unsigned s_look[kScanSmemWords];
+// static partition of the map tiles over the CTAs of the write pass
+__device__ __forceinline__ void tile_range(int mA, int grid, int b, int& lo, int& hi, int& ntiles) {
+    ntiles = mA / kMpTile + 1;      // the last tile also takes the inserts behind the last map point
+    const int per = (ntiles + grid - 1) / grid;
+    lo = min(ntiles, b * per);
+    hi = min(ntiles, lo + per);
+}
+
+__global__ void __launch_bounds__(256) k_mp_tiles(MapperParams P) {
     const int mA = P.counts[0];
-    const int ntiles = mA / kMpTile + 1;     // the last tile also takes the inserts behind the last map point
+    const int ntiles = mA / kMpTile + 1;
     const int nm = (int)P.state[4], ni = (int)P.state[6];
-    const float4* bpts = P.buf + mA;
-    const int tid = threadIdx.x;
-    while (true) {
-        __syncthreads();
-        if (tid == 0) s_tile = (int)atomicAdd(&ctrl[2], 1u);
-        __syncthreads();
-        const int tile = s_tile;
-        if (tile >= ntiles) return;
-        const int base = tile * kMpTile;
-        const bool last = tile == ntiles - 1;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) { s_link[tid + 256 * k] = 0; s_cnt[tid + 256 * k] = 0; s_first[tid + 256 * k] = 0x7fffffff; }
-        if (tid == 0) { s_cnt[kMpTile] = 0; s_first[kMpTile] = 0x7fffffff; }
-        if (tid < 32) {
-            const int a = warp_lower_bound_i(P.m_ra, nm, base);
-            const int b = last ? nm : warp_lower_bound_i(P.m_ra, nm, base + kMpTile);
-            if (tid == 0) { s_rng[0] = a; s_rng[1] = b; }
-        } else if (tid < 64) {
-            const int a = warp_lower_bound_i(P.i_ra, ni, base);
-            const int b = last ? ni : warp_lower_bound_i(P.i_ra, ni, base + kMpTile);
-            if (tid == 32) { s_rng[2] = a; s_rng[3] = b; }
-        }
-        __syncthreads();
-        const int mLo = s_rng[0], mHi = s_rng[1], iLo = s_rng[2], iHi = s_rng[3];
-        for (int h = mLo + tid; h < mHi; h += 256) s_link[P.m_ra[h] - base] = h + 1;
-        for (int e = iLo + tid; e < iHi; e += 256) {
-            const int s = P.i_ra[e] - base;
-            atomicAdd(&s_cnt[s], 1);
-            atomicMin(&s_first[s], e);
-        }
-        __syncthreads();
-        float4 o[4];
-        unsigned oc[4];
-        bool keep[4];
+    if (ntiles + 1 > P.tile_cap) { if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(&P.counts[4], 4); return; }
+    const int per = (ntiles + P.write_grid - 1) / P.write_grid;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t <= ntiles; t += gridDim.x * blockDim.x) {
+        int a = nm, b = ni;
+        if (t < ntiles) { a = lower_bound_i(P.m_ra, 0, nm, t * kMpTile); b = lower_bound_i(P.i_ra, 0, ni, t * kMpTile); }
+        P.tile_m[t] = a; P.tile_i[t] = b;
+    }
+    // emitted points per tile: its own map points, minus the replacements that turned into exceptions, plus its inserts
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < ntiles; t += gridDim.x * blockDim.x) {
+        const int base = t * kMpTile;
+        const int a0 = lower_bound_i(P.m_ra, 0, nm, base), a1 = t + 1 < ntiles ? lower_bound_i(P.m_ra, 0, nm, base + kMpTile) : nm;
+        const int b0 = lower_bound_i(P.i_ra, 0, ni, base), b1 = t + 1 < ntiles ? lower_bound_i(P.i_ra, 0, ni, base + kMpTile) : ni;
+        int emit = min(kMpTile, max(0, mA - base)) + (b1 - b0);
+        for (int h = a0; h < a1; ++h) emit -= P.m_keep[h] ? 0 : 1;
+        P.tile_agg[t] = emit;
+        atomicAdd(&P.cta_sum[t / per], emit);
+    }
+}
+
+// The streaming pass: same structure as k_mm_write (merge.cu): a thread owns the slots tid, tid + 256, ... of a tile (coalesced
+// loads and stores), kept-prefix from 32 ballot words, replacements / inserts found by binary search in their sorted lists.
+__global__ void __launch_bounds__(256, 6) k_mp_write(MapperParams P) {
+    __shared__ unsigned s_mask[2][32];
+    __shared__ int s_segpre[2][33];
+    __shared__ int s_tmp[9];
+    const int mA = P.counts[0];
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int ni_all = (int)P.state[6];
+    if (mA == 0) {       // empty map: everything is an insert, already in key order
+        for (int e = blockIdx.x * 256 + tid; e < ni_all; e += gridDim.x * 256) { P.out[e] = P.i_pt[e]; P.cell_out[e] = P.i_cell[e]; }
+        if (blockIdx.x == 0 && tid == 0) P.counts[3] = ni_all;
+        return;
+    }
+    int lo, hi, ntiles;
+    tile_range(mA, (int)gridDim.x, (int)blockIdx.x, lo, hi, ntiles);
+    if (lo >= hi) return;
+    int running;
+    {
         int v = 0;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int slot = 4 * tid + k, i = base + slot;
-            keep[k] = false;
-            if (i < mA) {
-                const float4 p = P.buf[i];
-                const unsigned cell = P.cbuf[i];
-                o[k] = p; oc[k] = cell; keep[k] = true;
-                const int l = s_link[slot];
-                if (l) {     // this map point's voxel receives new points (its cell is inside the block by construction)
-                    Acc4 acc;
-                    acc_add(acc, p);
-                    const int st = P.m_start[l - 1], ln = P.m_len[l - 1];
-                    for (int q = 0; q < ln; ++q) acc_add(acc, bpts[vals[st + q]]);
-                    const float4 r = acc_mean(acc);
-                    if (vox24(r, cell, P.inv_leaf) != vox24(p, cell, P.inv_leaf)) { put_exception(P, r, cell); keep[k] = false; }
-                    o[k] = r;
-                }
-            }
-            v += (keep[k] ? 1 : 0) + s_cnt[slot];
-        }
-        if (tid == 255) v += s_cnt[kMpTile];
+        for (int b = tid; b <= (int)blockIdx.x; b += 256) v += P.cta_sum[b];
         int total;
-        const int t_excl = block_scan_excl_256(v, s_tmp, &total);
-        {
-            int run = t_excl;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                s_pre[4 * tid + k] = run;
-                run += s_cnt[4 * tid + k] + (keep[k] ? 1 : 0);
-            }
-            if (tid == 255) s_pre[kMpTile] = run;
-        }
-        const unsigned tag = (ctrl[0] << 3) | 4u;
-        const unsigned gbase = chained_scan_exclusive(status, tag, tile, (unsigned)total, s_look);
+        block_scan_excl_256(v, s_tmp, &total);
+        running = total;
+    }
+    if (hi == ntiles && tid == 0) P.counts[3] = running;
+    for (int tile = hi - 1, par = 0; tile >= lo; --tile, par ^= 1) {
+        const int emit = P.tile_agg[tile];
+        const int gbase = running - emit;
+        running = gbase;
+        const int base = tile * kMpTile;
+        float4 p[4];
+        unsigned pc[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            if (keep[k]) {
-                const int d = (int)gbase + s_pre[4 * tid + k] + s_cnt[4 * tid + k];
-                P.out[d] = o[k]; P.cell_out[d] = oc[k];
+            const int i = base + k * 256 + tid;
+            p[k] = make_float4(0.f, 0.f, 0.f, 0.f); pc[k] = 0u;
+            if (i < mA) { p[k] = ld_stream_f4(P.buf + i); pc[k] = P.cbuf[i]; }
+        }
+        const int mLo = P.tile_m[tile], mHi = P.tile_m[tile + 1], iLo = P.tile_i[tile], iHi = P.tile_i[tile + 1];
+        unsigned mask[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int i = base + k * 256 + tid;
+            bool keep = i < mA;
+            if (keep && mHi > mLo) {
+                const int h = lower_bound_i(P.m_ra, mLo, mHi, i);
+                if (h < mHi && P.m_ra[h] == i) { p[k] = P.m_pt[h]; keep = P.m_keep[h] != 0; }    // finished in k_mp_heads
+            }
+            mask[k] = __ballot_sync(0xffffffffu, keep);
+            if (lane == 0) s_mask[par][k * 8 + w] = mask[k];
+        }
+        __syncthreads();
+        if (w == 0) {
+            const int cnt = __popc(s_mask[par][lane]);
+            int x = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int y = __shfl_up_sync(0xffffffffu, x, o);
+                if (lane >= o) x += y;
+            }
+            s_segpre[par][lane] = x - cnt;
+            if (lane == 31) s_segpre[par][32] = x;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (mask[k] >> lane & 1u) {
+                const int i = base + k * 256 + tid;
+                int pos = gbase + s_segpre[par][k * 8 + w] + __popc(mask[k] & lanemask_lt());
+                if (iHi > iLo) pos += lower_bound_i(P.i_ra, iLo, iHi, i + 1) - iLo;      // inserts in front of this point
+                st_stream_f4(P.out + pos, p[k]);
+                P.cell_out[pos] = pc[k];
             }
         }
+        const int kept = s_segpre[par][32];
         for (int e = iLo + tid; e < iHi; e += 256) {
-            const int s = P.i_ra[e] - base;
-            const int d = (int)gbase + s_pre[s] + (e - s_first[s]);
-            P.out[d] = P.i_pt[e]; P.cell_out[d] = P.i_cell[e];
+            const int s = P.i_ra[e] - base;      // the insert goes in front of slot s; s >= 1024: behind the last map point
+            const int before = s >= kMpTile ? kept : s_segpre[par][s >> 5] + __popc(s_mask[par][s >> 5] & ((1u << (s & 31)) - 1u));
+            P.out[gbase + before + (e - iLo)] = P.i_pt[e];
+            P.cell_out[gbase + before + (e - iLo)] = P.i_cell[e];
         }
-        if (last && tid == 0) P.counts[3] = (int)gbase + total;
+        if (tid == 0 && kept + (iHi - iLo) != emit) atomicOr(&P.counts[4], 8);     // count and write must agree
     }
 }
 
@@ -360,8 +372,10 @@ struct pf_mapping {
     float4* d_in = nullptr;
     int* d_counts = nullptr;
     unsigned long long* d_dropped = nullptr;
-    int *d_mra = nullptr, *d_mstart = nullptr, *d_mlen = nullptr, *d_ira = nullptr;
-    float4 *d_ipt = nullptr, *d_exc = nullptr;
+    int *d_mra = nullptr, *d_mkeep = nullptr, *d_ira = nullptr;
+    float4 *d_mpt = nullptr, *d_ipt = nullptr, *d_exc = nullptr;
+    int *d_tile = nullptr, *d_cta = nullptr;     // [3][tile_cap] tile_m, tile_i, tile_agg; [kMpMaxGrid] per-CTA sums
+    int tile_cap = 0;
     unsigned *d_icell = nullptr, *d_exccell = nullptr;
     int* h_counts = nullptr;              // pinned read-back of the device counts after the last update
     unsigned long long* h_dropped = nullptr;
@@ -378,6 +392,7 @@ int mapping_settle(pf_mapping* h) {   // wait for the last update's counts
         h->pending = false;
         if (h->h_counts[4] & 1) { set_error("global map exceeded max_map_points = %d", h->mcap); return PF_ERR_CAPACITY; }
         if (h->h_counts[4] & 2) { set_error("more than %d centroids left their voxel in one update", kExcCap); return PF_ERR_CAPACITY; }
+        if (h->h_counts[4] & 12) { set_error("global map update: internal error (bits %d)", h->h_counts[4] & 12); return PF_ERR_CUDA; }
         h->map_ub = h->h_counts[1];
         h->sorted_ub = h->h_counts[0];
     }
@@ -419,8 +434,11 @@ extern "C" int pf_mapping_create(double map_resolution, int max_map_points, int 
         const int counts[8] = {0, 0, 0, 0, 0, h->bufcap, h->mcap, 0};
         PF_CUDA(cudaMemcpy(h->d_counts, counts, sizeof(counts), cudaMemcpyHostToDevice));
         PF_CUDA(cudaMalloc(&h->d_mra, sizeof(int) * capb));
-        PF_CUDA(cudaMalloc(&h->d_mstart, sizeof(int) * capb));
-        PF_CUDA(cudaMalloc(&h->d_mlen, sizeof(int) * capb));
+        PF_CUDA(cudaMalloc(&h->d_mkeep, sizeof(int) * capb));
+        PF_CUDA(cudaMalloc(&h->d_mpt, sizeof(float4) * capb));
+        h->tile_cap = h->bufcap / kMpTile + 3;
+        PF_CUDA(cudaMalloc(&h->d_tile, sizeof(int) * 3 * (size_t)h->tile_cap));
+        PF_CUDA(cudaMalloc(&h->d_cta, sizeof(int) * kMpMaxGrid));
         PF_CUDA(cudaMalloc(&h->d_ira, sizeof(int) * capb));
         PF_CUDA(cudaMalloc(&h->d_ipt, sizeof(float4) * capb));
         PF_CUDA(cudaMalloc(&h->d_icell, sizeof(unsigned) * capb));
@@ -445,7 +463,8 @@ extern "C" int pf_mapping_destroy(pf_mapping* h) {
     workspace_destroy(h->ws);
     for (int b = 0; b < 2; ++b) { cudaFree(h->d_map[b]); cudaFree(h->d_cell[b]); }
     cudaFree(h->d_in); cudaFree(h->d_counts); cudaFree(h->d_dropped);
-    cudaFree(h->d_mra); cudaFree(h->d_mstart); cudaFree(h->d_mlen); cudaFree(h->d_ira); cudaFree(h->d_ipt); cudaFree(h->d_icell);
+    cudaFree(h->d_mra); cudaFree(h->d_mkeep); cudaFree(h->d_mpt); cudaFree(h->d_ira); cudaFree(h->d_ipt); cudaFree(h->d_icell);
+    cudaFree(h->d_tile); cudaFree(h->d_cta);
     cudaFree(h->d_exc); cudaFree(h->d_exccell);
     cudaFreeHost(h->h_counts); cudaFreeHost(h->h_dropped);
     if (h->ev) cudaEventDestroy(h->ev);
@@ -473,7 +492,9 @@ static int mapping_update(pf_mapping* h, const float* xyzi, int n, const double 
     P.counts = h->d_counts; P.dropped = h->d_dropped;
     P.inv_leaf = 1.0f / h->leaf;       // inverse_leaf_size_ = 1 / leaf_size_ (float)
     P.bx = cell_of(rt[3]) - 2; P.by = cell_of(rt[7]) - 2; P.bz = cell_of(rt[11]) - 2;   // :154-156, block of checkPoints :110-149
-    P.m_ra = h->d_mra; P.m_start = h->d_mstart; P.m_len = h->d_mlen; P.i_ra = h->d_ira; P.i_pt = h->d_ipt; P.i_cell = h->d_icell;
+    P.m_ra = h->d_mra; P.m_keep = h->d_mkeep; P.m_pt = h->d_mpt; P.i_ra = h->d_ira; P.i_pt = h->d_ipt; P.i_cell = h->d_icell;
+    P.tile_m = h->d_tile; P.tile_i = h->d_tile + h->tile_cap; P.tile_agg = h->d_tile + 2 * h->tile_cap; P.cta_sum = h->d_cta;
+    P.tile_cap = h->tile_cap;
     P.exc = h->d_exc; P.exc_cell = h->d_exccell;
     P.state = ws.ctrl + kSlotBase;
     Mat34 T;
@@ -493,11 +514,16 @@ static int mapping_update(pf_mapping* h, const float* xyzi, int n, const double 
     int tiles = div_up(capB, 256);
     if (tiles > 6 * kSMs) tiles = 6 * kSMs;
     k_mp_heads<<<tiles, 256, 0, h->stream>>>(P, ws.keys[rb], ws.vals[rb], ws.scan_status, ws.status_stride, ws.ctrl);
-    int mtiles = h->map_ub / kMpTile + 1;
-    if (mtiles > 4 * kSMs) mtiles = 4 * kSMs;
-    k_mp_merge<<<mtiles, 256, 0, h->stream>>>(P, ws.vals[rb], ws.scan_status, ws.ctrl);
+    int wgrid = h->map_ub / kMpTile + 1;
+    if (wgrid > kMpMaxGrid) wgrid = kMpMaxGrid;
+    P.write_grid = wgrid;
+    PF_CUDA(cudaMemsetAsync(h->d_cta, 0, sizeof(int) * kMpMaxGrid, h->stream));
+    int tblk = div_up(h->map_ub / kMpTile + 2, 256);
+    if (tblk > 2 * kSMs) tblk = 2 * kSMs;
+    k_mp_tiles<<<tblk, 256, 0, h->stream>>>(P);
+    k_mp_write<<<wgrid, 256, 0, h->stream>>>(P);
     k_mp_finish<<<1, 256, 0, h->stream>>>(P);
-    ws.launches += 3;
+    ws.launches += 4;
     PF_CUDA(cudaGetLastError());
     h->cur ^= 1;
     PF_CUDA(cudaMemcpyAsync(h->h_counts, h->d_counts, sizeof(int) * 8, cudaMemcpyDeviceToHost, h->stream));
