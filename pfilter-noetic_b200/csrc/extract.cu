@@ -80,9 +80,8 @@ __device__ __noinline__ int ring_id_exact(float x, float y, float z, int num_lin
 // fp32 evaluation of the same decision; returns -1 when the point is too close to a decision boundary to call.
 // atan(t) = t P(t^2) on |t| <= 0.75 (least-squares fit, |error| < 6e-6 deg); the bin position u is then known to
 // better than 1e-4, and anything within kEps of an integer / a gate goes to the exact path.
-__device__ __forceinline__ int ring_id_fast(float dist, float z, int num_lines) {
+__device__ __forceinline__ int ring_id_fast_t(float t, int num_lines) {
     constexpr float kEps = 1e-3f;
-    const float t = __fdividef(z, dist);
     if (!(fabsf(t) <= 0.75f)) return -1;
     const float u2 = __fmul_rn(t, t);
     float p = 0x1.2dafa8p-6f;
@@ -118,13 +117,16 @@ __device__ __forceinline__ int ring_id_fast(float dist, float z, int num_lines) 
     return id < num_lines ? id : 255;
 }
 
+// fp32 fast path on top of one MUFU.RSQ: dist = s * rsqrt(s) and z / dist = z * rsqrt(s) are good to ~3 ulp, i.e. the bin position is
+// still known to ~1e-4 (ring_id_fast calls everything within 1e-3 of a decision "unsure"); the range gate is pulled in by 1e-6
+// relative so that the approximate distance can never decide a point the reference's (double)sqrtf comparison would not.
 __device__ __forceinline__ int ring_id_dev(float x, float y, float z, int num_lines, double min_d, double max_d, float gate_lo,
                                            float gate_hi) {
-    const float s = __fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y));
-    const float dist = __fsqrt_rn(s);
+    const float s = __fmaf_rn(x, x, __fmul_rn(y, y));
+    const float r = rsqrtf(s);
+    const float dist = __fmul_rn(s, r);
     int id = -1;
-    // the range gate compares (double)dist with the double limits: decided in fp32 away from the limits
-    if (dist > gate_lo && dist < gate_hi && isfinite(z)) id = ring_id_fast(dist, z, num_lines);
+    if (dist > gate_lo && dist < gate_hi && fabsf(z) < 3.0e38f) id = ring_id_fast_t(__fmul_rn(z, r), num_lines);
     if (id < 0) {
         if (!(isfinite(x) && isfinite(y) && isfinite(z))) return 255;   // x86 int(NaN) = INT_MIN: the reference drops these
         id = ring_id_exact(x, y, z, num_lines, min_d, max_d);
@@ -140,6 +142,7 @@ __global__ void __launch_bounds__(kTile) k_ring_classify(ExtractParams P, float 
     }
     const int n = P.n[s];
     if (tile * kTile >= n) return;
+    __shared__ int s_wring[kTile / 32];
     __shared__ unsigned s_lo[kTile / 32], s_hi[kTile / 32], s_drop[kTile / 32];
     const int i = tile * kTile + tid;
     const size_t g = (size_t)s * P.stride + i;
@@ -150,27 +153,41 @@ __global__ void __launch_bounds__(kTile) k_ring_classify(ExtractParams P, float 
         if (P.label) P.label[g] = 0;
     }
     P.ringid[g] = (uint8_t)ring;
-    // rings present in this tile -> per (scan, ring) tile range; a full tile of one ring is "pure" (copied without ballots)
+    // rings present in this tile -> per (scan, ring) tile range; a full tile of one ring is "pure" (copied without ballots).
+    // Common case first (ring-major input: 3 tiles out of 4 hold a single ring): one match per warp, one atomic pair per tile.
+    int same;
+    __match_all_sync(0xffffffffu, ring, &same);
+    if ((tid & 31) == 0) s_wring[tid >> 5] = same ? ring : 256;
+    __syncthreads();
+    const int r0 = s_wring[0];
+    bool pure = r0 < kMaxLines;
+#pragma unroll
+    for (int w = 1; w < kTile / 32; ++w) pure = pure && s_wring[w] == r0;
+    if (pure) {      // uniform over the CTA
+        if (tid == 0) {
+            int2* rt = P.ring_tiles + (size_t)s * kMaxLines + r0;
+            atomicMin(&rt->x, tile);
+            atomicMax(&rt->y, tile);
+            P.tile_pure[(size_t)s * P.tiles + tile] = (uint8_t)r0;
+        }
+        return;
+    }
     const unsigned bit = 1u << (ring & 31);
     const unsigned lo = __reduce_or_sync(0xffffffffu, ring < 32 ? bit : 0u);
     const unsigned hi = __reduce_or_sync(0xffffffffu, (ring >= 32 && ring < 64) ? bit : 0u);
-    const unsigned drop = __ballot_sync(0xffffffffu, ring >= 64);
-    if ((tid & 31) == 0) { s_lo[tid >> 5] = lo; s_hi[tid >> 5] = hi; s_drop[tid >> 5] = drop; }
+    if ((tid & 31) == 0) { s_lo[tid >> 5] = lo; s_hi[tid >> 5] = hi; }
     __syncthreads();
     if (tid < kMaxLines) {
-        unsigned m = 0u, ml = 0u, mh = 0u, d = 0u;
+        unsigned ml = 0u, mh = 0u;
 #pragma unroll
-        for (int w = 0; w < kTile / 32; ++w) { ml |= s_lo[w]; mh |= s_hi[w]; d |= s_drop[w]; }
-        m = tid < 32 ? ml : mh;
+        for (int w = 0; w < kTile / 32; ++w) { ml |= s_lo[w]; mh |= s_hi[w]; }
+        const unsigned m = tid < 32 ? ml : mh;
         if (m >> (tid & 31) & 1u) {
             int2* rt = P.ring_tiles + (size_t)s * kMaxLines + tid;
             atomicMin(&rt->x, tile);
             atomicMax(&rt->y, tile);
         }
-        if (tid == 0) {
-            const bool pure = d == 0u && __popc(ml) + __popc(mh) == 1;
-            P.tile_pure[(size_t)s * P.tiles + tile] = pure ? (uint8_t)(ml ? __ffs(ml) - 1 : 31 + __ffs(mh)) : (uint8_t)255;
-        }
+        if (tid == 0) P.tile_pure[(size_t)s * P.tiles + tile] = (uint8_t)255;
     }
 }
 
@@ -687,6 +704,9 @@ extern "C" int pf_extract_create(const pf_lidar_params* lidar, const pf_extract_
     if (!((double)h->gate_lo > lidar->min_distance)) h->gate_lo = nextafterf(h->gate_lo, INFINITY);
     h->gate_hi = (float)lidar->max_distance;
     if (!((double)h->gate_hi < lidar->max_distance)) h->gate_hi = nextafterf(h->gate_hi, -INFINITY);
+    // the fast path sees the distance only to a few ulp (rsqrt): pull both limits in by 1e-6 relative
+    h->gate_lo = h->gate_lo * (1.0f + 1e-6f) + 1e-30f;
+    h->gate_hi = h->gate_hi * (1.0f - 1e-6f);
     // scans per launch pair.  Measured on B200 (128 scans of 114 k points): one pair for the whole batch is fastest (0.444 ms
     // vs 0.605 ms in L2-sized groups of 21): the kernels are bound by instruction issue, not by DRAM, so the second read of the
     // points missing L2 costs less than the extra launches and partial waves of small groups.  PF_EXTRACT_GROUP overrides.
