@@ -30,6 +30,27 @@ def _voxel_key(p, leaf):
     return (k[0] + (1 << 20)) << 42 | (k[1] + (1 << 20)) << 21 | (k[2] + (1 << 20))
 
 
+def _split_sorted(m, leaf):
+    """(strictly key-ascending part, rest) of an oracle map: a centroid that float rounding pushed out of its voxel (likely when
+    points sit exactly on voxel faces) breaks the order and must travel with the unsorted input, as pf_odom_update does."""
+    import bisect
+    keys = _voxel_key(m, leaf)
+    tails, tail_idx, prev = [], [], np.full(len(m), -1)
+    for i, k in enumerate(keys):                       # longest strictly increasing subsequence
+        j = bisect.bisect_left(tails, k)
+        if j == len(tails):
+            tails.append(k); tail_idx.append(i)
+        else:
+            tails[j] = k; tail_idx[j] = i
+        prev[i] = tail_idx[j - 1] if j else -1
+    keep = np.zeros(len(m), bool)
+    i = tail_idx[-1] if tail_idx else -1
+    while i >= 0:
+        keep[i] = True
+        i = prev[i]
+    return m[keep], m[~keep]
+
+
 def _check(capi, oracle, sorted_map, extra, center, leaf, prm):
     out, ns = capi.map_merge(sorted_map, extra, center, leaf, *prm)
     ref = oracle.map_update(np.concatenate([sorted_map, extra]), center, leaf, *prm)
@@ -98,3 +119,43 @@ def test_merge_large_map_streams(capi, oracle):
     m0 = oracle.map_update(raw, (0, 0, 0), 0.4, 0, 1.0, 200)
     add = _cloud(capi, rng, 20000, (100, 100, 10))
     _check(capi, oracle, m0, add, (0.2, 0.1, 0.0), 0.4, (0, 1.0, 200))
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_merge_adversarial_small_inputs(capi, oracle, seed):
+    """Points on voxel faces, on the crop-box faces, duplicates, one crowded voxel, negative coordinates, tiny maps."""
+    rng = np.random.default_rng(100 + seed)
+    leaf = [0.4, 0.8][seed % 2]
+    prm = [(0, 0.4, 75), (2, 0.9, 10), (0, 0.0, 0)][seed % 3]
+    center = (rng.uniform(-3, 3), rng.uniform(-3, 3), rng.uniform(-1, 1))
+    lo = np.float32(center[0] - 100)
+    n = int(rng.integers(1, 4000))
+    grid = np.round(rng.uniform(-120, 120, (n, 3)) / leaf) * leaf                 # exactly on voxel faces (as far as floats allow)
+    xyz = np.where(rng.random((n, 1)) < 0.5, grid, rng.uniform(-120, 120, (n, 3))).astype(np.float32)
+    xyz[: n // 10] = xyz[0]                                                        # a crowded voxel of duplicates
+    xyz[n // 10: n // 8, 0] = lo                                                   # on the lower crop face (kept: inclusive)
+    xyz[n // 8: n // 6, 0] = np.nextafter(lo, np.float32(-1e9))                    # just outside
+    raw = capi.make_points(xyz, r=rng.integers(0, 256, n), g=rng.integers(0, 256, n), b=0, a=255)
+    m0 = oracle.map_update(raw, center, leaf, *prm)
+    k = int(rng.integers(0, 3000))
+    m0_xyz = np.stack([m0["x"], m0["y"], m0["z"]], axis=1) if len(m0) else np.zeros((1, 3), np.float32)
+    exy = np.where(rng.random((k, 1)) < 0.5, m0_xyz[rng.integers(0, len(m0_xyz), k)],     # land exactly on existing centroids
+                   rng.uniform(-110, 110, (k, 3))).astype(np.float32)
+    extra = capi.make_points(exy, r=rng.integers(0, 8, k), g=rng.integers(0, 256, k), b=0, a=255)
+    center1 = (center[0] + 0.7, center[1] - 0.2, center[2])
+    m0s, exc = _split_sorted(m0, leaf)
+    assert len(exc) <= 4
+    _check(capi, oracle, m0s, np.concatenate([exc, extra]), center1, leaf, prm)
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_voxel_downsample_adversarial(capi, oracle, seed):
+    rng = np.random.default_rng(200 + seed)
+    leaf = [0.4, 0.8][seed % 2]
+    n = int(rng.integers(1, 6000))
+    grid = np.round(rng.uniform(-60, 60, (n, 3)) / leaf) * leaf
+    xyz = np.where(rng.random((n, 1)) < 0.6, grid, rng.uniform(-60, 60, (n, 3))).astype(np.float32)
+    xyz[: n // 5] = xyz[0]                                   # hundreds of duplicates in one voxel (long ordered sum)
+    pts = capi.make_points(xyz)
+    a, b = capi.voxel_downsample(pts, leaf), oracle.voxel_downsample(pts, leaf)
+    assert len(a) == len(b) and a.tobytes() == b.tobytes()
