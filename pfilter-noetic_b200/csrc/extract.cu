@@ -3,23 +3,25 @@
 // Replaces LaserProcessingClass::featureExtraction / featureExtractionFromSector
 // (/root/reference/src/laserProcessingClass.cpp:10-96, :99-209).  Arithmetic spec: SURVEY.md appendix A.1.
 //
-// Two kernels per batch of scans:
-//   k_ring_classify : one thread per point, coalesced float4 loads; ring id (elevation angle, :25-61) -> 1 byte.  The
-//                     angle is first evaluated in fp32 (polynomial atan); only points whose bin position lies within
-//                     1e-3 of a decision boundary take the reference's exact double-precision atan path, so the ring
-//                     ids are the reference's.  Per (scan, ring) the first / last 256-point tile holding the ring.
-//   k_ring_extract  : one CTA (6 warps) per (scan, ring).  Stable gather of the ring's points (:62) from its tile
-//                     range into shared memory; 11-tap float curvature (:73-80) from a 17-point register window per
-//                     lane; "short step" link bits for the neighbour suppression (:128-145); then one warp per sector
-//                     (:81-92): candidates (curvature > 0.1, :114) are compacted into registers as
-//                     (23-bit monotone key | 9-bit index) words and the greedy descending walk of :110-148 becomes at
-//                     most 21 rounds of { redux.max, range kill }; two candidates in the same key bucket are resolved
-//                     with the exact double curvature (ties: higher index first, = the descending walk over an
-//                     ascending sort with lower index first).  surf = unflagged (:198-205).  Output offsets of the
-//                     rings of a scan are chained through a decoupled look-back on (epoch, counts) words, so the
-//                     compacted edge/surf clouds are written once, straight from shared memory.
+// Three kernels per batch of scans:
+//   k_ring_classify  : one warp per 256-point tile, coalesced float4 loads; ring id (elevation angle, :25-61) -> 1 byte.  The
+//                      angle is first evaluated in fp32 (polynomial atan); only points whose bin position lies within
+//                      2.5e-4 of a decision boundary take the reference's exact double-precision atan path, so the ring
+//                      ids are the reference's.  Per (scan, ring) the first / last tile holding the ring; per tile whether
+//                      it holds one ring only ("pure": the ring-major order LiDAR drivers emit makes most tiles pure).
+//   k_ring_index     : one warp per (scan, ring): ring position at which each tile of the ring's range starts, ring size.
+//   k_sector_extract : one WARP per (scan, ring, sector) (:81-92), persistent, work by ticket, no CTA barrier.  Stable gather of
+//                      the sector's points (+5 either side, :62) into the warp's slice of shared memory; 11-tap float
+//                      curvature (:73-80) from a 20-point register window per lane; "short step" link bits for the
+//                      neighbour suppression (:128-145); candidates (curvature > 0.1, :114) are compacted into registers as
+//                      (23-bit monotone key | 9-bit index) words and the greedy descending walk of :110-148 becomes at
+//                      most 21 rounds of { redux.max, flag-range update, range kill }; two candidates in the same key
+//                      bucket are resolved with the exact double curvature (ties: higher index first, = the descending
+//                      walk over an ascending sort with lower index first).  surf = unflagged (:198-205).  Output offsets
+//                      are chained through (epoch, counts) words per sector and per ring, so the compacted edge / surf
+//                      clouds are written once, straight from shared memory.
 // HBM traffic per point: 16 B read + 16 B written (+ ring id / label bytes); the second read of the points by
-// k_ring_extract hits L2.
+// k_sector_extract hits L2 when the batch fits there.
 #include <math.h>
 
 #include <vector>
@@ -28,31 +30,34 @@
 
 namespace pf {
 
-constexpr int kTile = 256;          // points per classify tile
-constexpr int kExtractThreads = 192;
-constexpr int kExtractWarps = kExtractThreads / 32;
+constexpr int kTile = 256;          // points per classify tile (one warp)
+constexpr int kClassifyThreads = 256;
+constexpr int kSecWarps = 2;        // warps per CTA of k_sector_extract; every warp works on its own
 constexpr int kMaxLines = 64;
 constexpr int kEdgePerSector = 20;  // src/laserProcessingClass.cpp:121
 constexpr int kSectors = 6;         // :81
-constexpr int kWin = 5;             // curvature values per lane per pass (odd: conflict-free 16-byte shared loads)
+constexpr int kWin = 10;            // curvature positions per lane per pass
 constexpr int kMaxRingCap = 3040;   // sector length <= 512 (9-bit index in the candidate word)
-static_assert(kExtractWarps == kSectors, "one warp per sector");
+constexpr unsigned kFull = 0xffffffffu;
 
 struct ExtractParams {
     const float4* pts;        // [batch][stride]
     const int* n;             // [batch]
     uint8_t* ringid;          // [batch][stride]
-    int2* ring_tiles;         // [batch][64] first / last tile holding the ring (reset to {INT_MAX, -1} by the consumer)
+    int2* ring_tiles;         // [batch][64] first / last tile holding the ring (reset to {INT_MAX, -1} by k_ring_index)
     uint8_t* tile_pure;       // [batch][tiles] ring id when the tile is a full tile of one ring, else 255
+    int* tile_off;            // [batch][64][tiles + 1] ring positions at which the tiles of the ring's range start
+    int4* ring_info;          // [batch][64] {first tile, tiles in range, points of the ring, -}
     uint8_t* label;           // [batch][stride] or null
     float4* edge;             // [batch][edge_stride]
     float4* surf;             // [batch][stride]
     int* n_edge;              // [batch]
     int* n_surf;              // [batch]
-    unsigned long long* done; // [batch][64] look-back words
+    unsigned long long* done_sec;   // [batch][64 * 6] (epoch | edges | surfs) of a sector
+    unsigned long long* done_ring;  // [batch][64]     the same summed over the ring, published by its last sector
     unsigned int* ctrl;       // [0] ticket, [1] epoch, [2] error bits
     int stride, tiles, edge_stride, batch;
-    int num_lines, rcap, maxtl;
+    int num_lines, rcap, scap, warp_smem;
     double min_d, max_d;
 };
 
@@ -78,10 +83,12 @@ __device__ __noinline__ int ring_id_exact(float x, float y, float z, int num_lin
 }
 
 // fp32 evaluation of the same decision; returns -1 when the point is too close to a decision boundary to call.
-// atan(t) = t P(t^2) on |t| <= 0.75 (least-squares fit, |error| < 6e-6 deg); the bin position u is then known to
-// better than 1e-4, and anything within kEps of an integer / a gate goes to the exact path.
+// atan(t) = t P(t^2) on |t| <= 0.75 (least-squares fit, |error| < 6e-6 deg).  Error budget of the bin position u (bins are 1/3,
+// 1/2, 4/3 or 2 degrees wide): t is known to ~4e-7 relative (fma, MUFU.RSQ at 2 ulp, one product) = 1e-5 deg at 25 deg, the
+// polynomial adds 6e-6 deg and its evaluation ~5e-6 deg: < 7e-5 bins in the worst case (3 bins per degree); anything within
+// kEps = 2.5e-4 of an integer / a gate goes to the exact path.
 __device__ __forceinline__ int ring_id_fast_t(float t, int num_lines) {
-    constexpr float kEps = 1e-3f;
+    constexpr float kEps = 2.5e-4f;
     if (!(fabsf(t) <= 0.75f)) return -1;
     const float u2 = __fmul_rn(t, t);
     float p = 0x1.2dafa8p-6f;
@@ -117,9 +124,9 @@ __device__ __forceinline__ int ring_id_fast_t(float t, int num_lines) {
     return id < num_lines ? id : 255;
 }
 
-// fp32 fast path on top of one MUFU.RSQ: dist = s * rsqrt(s) and z / dist = z * rsqrt(s) are good to ~3 ulp, i.e. the bin position is
-// still known to ~1e-4 (ring_id_fast calls everything within 1e-3 of a decision "unsure"); the range gate is pulled in by 1e-6
-// relative so that the approximate distance can never decide a point the reference's (double)sqrtf comparison would not.
+// fp32 fast path on top of one MUFU.RSQ: dist = s * rsqrt(s) and z / dist = z * rsqrt(s) are good to ~3 ulp; the range gate is
+// pulled in by 1e-6 relative so that the approximate distance can never decide a point the reference's (double)sqrtf comparison
+// would not.
 __device__ __forceinline__ int ring_id_dev(float x, float y, float z, int num_lines, double min_d, double max_d, float gate_lo,
                                            float gate_hi) {
     const float s = __fmaf_rn(x, x, __fmul_rn(y, y));
@@ -134,97 +141,120 @@ __device__ __forceinline__ int ring_id_dev(float x, float y, float z, int num_li
     return id;
 }
 
-__global__ void __launch_bounds__(kTile) k_ring_classify(ExtractParams P, float gate_lo, float gate_hi) {
-    const int s = blockIdx.y, tile = blockIdx.x, tid = threadIdx.x;
-    if (blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) {
+// One warp per 256-point tile (8 coalesced 512-byte rows, all loads in flight before the first use): ring id byte per point,
+// and the tile summary (one ring only -> "pure"; else the set of rings present) from registers and warp votes alone.
+__global__ void __launch_bounds__(kClassifyThreads) k_ring_classify(ExtractParams P, float gate_lo, float gate_hi) {
+    const int s = blockIdx.y, lane = threadIdx.x & 31;
+    const int tile = blockIdx.x * (kClassifyThreads / 32) + (threadIdx.x >> 5);
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
         P.ctrl[0] = 0;                // ticket for the extract kernel that follows in stream order
         atomicAdd(&P.ctrl[1], 1u);    // new epoch invalidates all look-back words of earlier launches
     }
     const int n = P.n[s];
-    if (tile * kTile >= n) return;
-    __shared__ int s_wring[kTile / 32];
-    __shared__ unsigned s_lo[kTile / 32], s_hi[kTile / 32], s_drop[kTile / 32];
-    const int i = tile * kTile + tid;
-    const size_t g = (size_t)s * P.stride + i;
-    int ring = 255;
-    if (i < n) {
-        float4 p = ld_stream_f4(P.pts + g);
-        ring = ring_id_dev(p.x, p.y, p.z, P.num_lines, P.min_d, P.max_d, gate_lo, gate_hi);
-        if (P.label) P.label[g] = 0;
-    }
-    P.ringid[g] = (uint8_t)ring;
-    // rings present in this tile -> per (scan, ring) tile range; a full tile of one ring is "pure" (copied without ballots).
-    // Common case first (ring-major input: 3 tiles out of 4 hold a single ring): one match per warp, one atomic pair per tile.
-    int same;
-    __match_all_sync(0xffffffffu, ring, &same);
-    if ((tid & 31) == 0) s_wring[tid >> 5] = same ? ring : 256;
-    __syncthreads();
-    const int r0 = s_wring[0];
-    bool pure = r0 < kMaxLines;
+    if (tile >= P.tiles || tile * kTile >= n) return;
+    constexpr int R = kTile / 32;
+    const int i0 = tile * kTile + lane;
+    const size_t g = (size_t)s * P.stride + i0;
+    float4 p[R];
 #pragma unroll
-    for (int w = 1; w < kTile / 32; ++w) pure = pure && s_wring[w] == r0;
-    if (pure) {      // uniform over the CTA
-        if (tid == 0) {
-            int2* rt = P.ring_tiles + (size_t)s * kMaxLines + r0;
+    for (int k = 0; k < R; ++k)
+        if (i0 + 32 * k < n) p[k] = ld_stream_f4(P.pts + g + 32 * k);
+    int ring[R];
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+        ring[k] = 255;
+        if (i0 + 32 * k < n) {
+            ring[k] = ring_id_dev(p[k].x, p[k].y, p[k].z, P.num_lines, P.min_d, P.max_d, gate_lo, gate_hi);
+            if (P.label) P.label[g + 32 * k] = 0;
+        }
+        P.ringid[g + 32 * k] = (uint8_t)ring[k];
+    }
+    bool same = true;
+#pragma unroll
+    for (int k = 1; k < R; ++k) same = same && ring[k] == ring[0];
+    int all_lanes;
+    __match_all_sync(kFull, ring[0], &all_lanes);
+    const bool pure = __all_sync(kFull, same) && all_lanes && ring[0] < kMaxLines;
+    if (pure) {      // the common case with ring-major input
+        if (lane == 0) {
+            int2* rt = P.ring_tiles + (size_t)s * kMaxLines + ring[0];
             atomicMin(&rt->x, tile);
             atomicMax(&rt->y, tile);
-            P.tile_pure[(size_t)s * P.tiles + tile] = (uint8_t)r0;
+            P.tile_pure[(size_t)s * P.tiles + tile] = (uint8_t)ring[0];
         }
         return;
     }
-    const unsigned bit = 1u << (ring & 31);
-    const unsigned lo = __reduce_or_sync(0xffffffffu, ring < 32 ? bit : 0u);
-    const unsigned hi = __reduce_or_sync(0xffffffffu, (ring >= 32 && ring < 64) ? bit : 0u);
-    if ((tid & 31) == 0) { s_lo[tid >> 5] = lo; s_hi[tid >> 5] = hi; }
-    __syncthreads();
-    if (tid < kMaxLines) {
-        unsigned ml = 0u, mh = 0u;
+    unsigned lo = 0u, hi = 0u;
 #pragma unroll
-        for (int w = 0; w < kTile / 32; ++w) { ml |= s_lo[w]; mh |= s_hi[w]; }
-        const unsigned m = tid < 32 ? ml : mh;
-        if (m >> (tid & 31) & 1u) {
-            int2* rt = P.ring_tiles + (size_t)s * kMaxLines + tid;
-            atomicMin(&rt->x, tile);
-            atomicMax(&rt->y, tile);
-        }
-        if (tid == 0) P.tile_pure[(size_t)s * P.tiles + tile] = (uint8_t)255;
+    for (int k = 0; k < R; ++k) {
+        if (ring[k] < 32) lo |= 1u << ring[k];
+        else if (ring[k] < 64) hi |= 1u << (ring[k] - 32);
     }
+    lo = __reduce_or_sync(kFull, lo);
+    hi = __reduce_or_sync(kFull, hi);
+    int2* rt = P.ring_tiles + (size_t)s * kMaxLines;
+    if (lo >> lane & 1u) { atomicMin(&rt[lane].x, tile); atomicMax(&rt[lane].y, tile); }
+    if (hi >> lane & 1u) { atomicMin(&rt[32 + lane].x, tile); atomicMax(&rt[32 + lane].y, tile); }
+    if (lane == 0) P.tile_pure[(size_t)s * P.tiles + tile] = (uint8_t)255;
 }
 
 __global__ void k_set_int(int* p, int v) {
     if (threadIdx.x == 0) *p = v;
 }
 
-// exclusive scan of a[0..n) in shared memory by the whole CTA; returns the total
-__device__ int block_excl_scan(int* a, int n, int* warp_tmp /*[kExtractWarps]*/) {
-    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-    int carry = 0;
-    for (int base = 0; base < n; base += kExtractThreads) {
-        int i = base + tid;
-        int v = i < n ? a[i] : 0;
-        int x = v;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            int y = __shfl_up_sync(0xffffffffu, x, o);
-            if (lane >= o) x += y;
-        }
-        if (lane == 31) warp_tmp[w] = x;
-        __syncthreads();
-        int woff = 0, tot = 0;
-#pragma unroll
-        for (int k = 0; k < kExtractWarps; ++k) {
-            int t = warp_tmp[k];
-            if (k < w) woff += t;
-            tot += t;
-        }
-        if (i < n) a[i] = carry + woff + x - v;
-        carry += tot;
-        __syncthreads();
-    }
-    return carry;
+// bytes of x equal to the byte b (0..255)
+__device__ __forceinline__ int count_bytes_eq(unsigned x, unsigned b) {
+    x ^= b * 0x01010101u;
+    unsigned t = (x & 0x7f7f7f7fu) + 0x7f7f7f7fu;
+    t = ~(t | x | 0x7f7f7f7fu);     // 0x80 in every byte of x that is zero
+    return __popc(t);
 }
 
-// exact curvature of ring element j (:73-77): float sums left to right, squares and their sum in double
+// One warp per (scan, ring): ring position at which every tile of the ring's tile range starts (exclusive prefix of the
+// per-tile point counts) and the ring's size, so that any sector of the ring can be located without touching the others.
+__global__ void __launch_bounds__(256) k_ring_index(ExtractParams P) {
+    const int lane = threadIdx.x & 31;
+    const int item = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (item >= P.batch * P.num_lines) return;
+    const int s = item / P.num_lines, r = item - s * P.num_lines;
+    int2* rtp = P.ring_tiles + (size_t)s * kMaxLines + r;
+    const int2 rt = *rtp;
+    __syncwarp();
+    if (lane == 0) *rtp = make_int2(0x7fffffff, -1);     // hand the slot back for the next launch
+    const int tlo = rt.x;
+    const int ncand = rt.y >= rt.x ? rt.y - rt.x + 1 : 0;
+    const uint8_t* pure = P.tile_pure + (size_t)s * P.tiles;
+    const uint8_t* rid = P.ringid + (size_t)s * P.stride;
+    int* off = P.tile_off + ((size_t)s * kMaxLines + r) * (P.tiles + 1);
+    int carry = 0;
+    for (int c0 = 0; c0 < ncand; c0 += 32) {
+        const int c = c0 + lane;
+        const int pr = c < ncand ? pure[tlo + c] : 254;
+        int cnt = pr == r ? kTile : 0;
+        unsigned mixed = __ballot_sync(kFull, pr == 255);
+        while (mixed) {       // a tile with several rings (or dropped points): count this ring's bytes, 8 per lane
+            const int b = __ffs(mixed) - 1;
+            mixed &= mixed - 1u;
+            const uint2 v = *reinterpret_cast<const uint2*>(rid + (size_t)(tlo + c0 + b) * kTile + lane * 8);
+            const int m = __reduce_add_sync(kFull, count_bytes_eq(v.x, (unsigned)r) + count_bytes_eq(v.y, (unsigned)r));
+            if (lane == b) cnt = m;
+        }
+        int x = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int y = __shfl_up_sync(kFull, x, o);
+            if (lane >= o) x += y;
+        }
+        if (c < ncand) off[c] = carry + x - cnt;
+        carry += __shfl_sync(kFull, x, 31);
+    }
+    if (lane == 0) {
+        off[ncand] = carry;
+        P.ring_info[(size_t)s * kMaxLines + r] = make_int4(tlo, ncand, carry, 0);
+    }
+}
+
+// exact curvature of sector-local element j (:73-77): float sums left to right, squares and their sum in double
 __device__ __noinline__ double curvature_exact(const float4* sp, int j) {
     double sq[3];
 #pragma unroll
@@ -246,65 +276,89 @@ __device__ __noinline__ double curvature_exact(const float4* sp, int j) {
     return __dadd_rn(__dadd_rn(sq[0], sq[1]), sq[2]);
 }
 
-// Greedy edge pick of one sector [a, b) by one warp (:110-148); NPL candidate words per lane.  Returns the pick count.
-// A candidate word is (23-bit key << 9) | (index - a): the maximum word is the next element of the descending walk unless
-// another live candidate shares its key bucket; then the exact double values decide (ties: higher index first).
+// 16-byte asynchronous copy global -> shared (L2 only): the gather keeps every row of a sector in flight without staging registers
+__device__ __forceinline__ void cp_async_16(void* smem, const void* gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+
+// shifts that give 0 for amounts >= 32 (PTX semantics), also for "negative" amounts seen as large unsigned numbers
+__device__ __forceinline__ unsigned shl_clamp(unsigned v, unsigned s) {
+    unsigned r;
+    asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(s));
+    return r;
+}
+__device__ __forceinline__ unsigned shr_clamp(unsigned v, unsigned s) {
+    unsigned r;
+    asm("shr.u32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(s));
+    return r;
+}
+
+// Greedy edge pick of one sector by one warp (:110-148).  Positions are sector-relative (rel = ring position - sector start;
+// the point of rel sits at sp[rel + 5]).  A candidate word is (23-bit key << 9) | rel: the maximum word is the next element of
+// the descending walk unless another live candidate shares its key bucket; then the exact double values decide (ties: higher
+// index first).  NPL words per lane live in registers; every round is one redux.max, the flag update of the suppressed range
+// (lane w keeps the flag bits of rel 32 w .. 32 w + 31) and a range kill.  Returns the pick count (<= 21).
 template <int NPL>
-__device__ __forceinline__ int sector_pick(const float4* sp, const unsigned* scand, int C, const uint8_t* slinkb, uint8_t* sflag,
-                                           int* edge_ids, int a, int b, int lane) {
+__device__ __forceinline__ int sector_pick(unsigned* scand, int C, const unsigned* slink, uint16_t* srng, int Ls, int lane,
+                                           unsigned& flagw, int& myedge) {
     unsigned word[NPL];
 #pragma unroll
     for (int k = 0; k < NPL; ++k) word[k] = (k * 32 + lane < C) ? scand[k * 32 + lane] : 0u;
+    __syncwarp();      // srng overlays scand from here on
+    // suppressed range of every candidate, should it get picked (:128-145): forward while the steps rel -> rel+1 -> ... are
+    // short (at most 5), same backward, clipped to the sector
+#pragma unroll
+    for (int k = 0; k < NPL; ++k) {
+        if (word[k] != 0u) {
+            const int rel = (int)(word[k] & 511u);
+            // link bit q = step between local points q and q+1; the point of rel is local rel + 5: bits rel .. rel + 9
+            const unsigned steps = __funnelshift_r(slink[rel >> 5], slink[(rel >> 5) + 1], rel & 31) & 0x3ffu;
+            const int fwd = __ffs(~(steps >> 5) | 32u) - 1;
+            const int back = __clz(~steps & 31u) - 27;
+            const int lo = max(rel - back, 0), hi = min(rel + fwd, Ls - 1);
+            srng[rel] = (uint16_t)(lo | ((hi - lo) << 9));
+        }
+    }
     // lanes holding two words of one bucket (rare) force the exact comparison whenever their bucket is on top
     bool dup = false;
 #pragma unroll
     for (int k = 0; k < NPL; ++k)
 #pragma unroll
         for (int l = k + 1; l < NPL; ++l) dup |= (word[k] != 0u) && ((word[k] ^ word[l]) >> 9) == 0u;
+    const bool anydup = __any_sync(kFull, dup);
+    __syncwarp();
+    const int wbase = lane * 32;
     int cnt = 0;
     while (true) {
         unsigned m = word[0];
 #pragma unroll
         for (int k = 1; k < NPL; ++k) m = max(m, word[k]);
-        const unsigned M = __reduce_max_sync(0xffffffffu, m);
+        const unsigned M = __reduce_max_sync(kFull, m);
         if (M == 0u) break;
         const unsigned bucket = M >> 9;
-        const unsigned top = __ballot_sync(0xffffffffu, (m >> 9) == bucket);
-        int rel = (int)(M & 511u);
-        if ((top & (top - 1u)) != 0u || __any_sync(0xffffffffu, dup && (m >> 9) == bucket)) {
-            unsigned long long bk = 0ull;
-            int bi = -1;
+        const unsigned top = __ballot_sync(kFull, (m >> 9) == bucket);
+        const int rel = (int)(M & 511u);
+        if ((top & (top - 1u)) != 0u || (anydup && __any_sync(kFull, dup && (m >> 9) == bucket))) {
+            // two live candidates share the top bucket: hand the live words back and let the exact (slow) walk finish the sector
 #pragma unroll
-            for (int k = 0; k < NPL; ++k) {
-                if ((word[k] >> 9) == bucket) {
-                    const int r = (int)(word[k] & 511u);
-                    const unsigned long long v = (unsigned long long)__double_as_longlong(curvature_exact(sp, a + r));
-                    if (bi < 0 || v > bk || (v == bk && r > bi)) { bk = v; bi = r; }
-                }
-            }
-#pragma unroll
-            for (int o = 16; o >= 1; o >>= 1) {
-                const unsigned long long ok = __shfl_xor_sync(0xffffffffu, bk, o);
-                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-                if (oi >= 0 && (bi < 0 || ok > bk || (ok == bk && oi > bi))) { bk = ok; bi = oi; }
-            }
-            rel = bi;
+            for (int k = 0; k < NPL; ++k) scand[k * 32 + lane] = word[k];
+            __syncwarp();
+            return -1 - cnt;
         }
-        const int i = a + rel;
         cnt++;                                                                      // :118-119
         if (cnt > kEdgePerSector) {                                                 // :121-126 the 21st is picked, not emitted
-            if (lane == 0) sflag[i] = 1;
+            if ((rel >> 5) == lane) flagw |= 1u << (rel & 31);
             break;
         }
-        if (lane == 0) edge_ids[cnt - 1] = i;
-        // neighbour suppression (:128-145): forward while the steps i->i+1->... are short (at most 5), same backward.
-        // lanes 0..9 fetch the step bytes i-5 .. i+4
-        const unsigned steps = __ballot_sync(0xffffffffu, slinkb[i - 5 + min(lane, 9)] != 0) & 0x3ffu;
-        const int fwd = __ffs(~(steps >> 5) | 32u) - 1;
-        const int back = __clz(~steps & 31u) - 27;
-        const int lo = max(i - back, a), hi = min(i + fwd, b - 1);
-        if (lane <= hi - lo) sflag[lo + lane] = 1;
-        const unsigned rlo = (unsigned)(lo - a), span = (unsigned)(hi - lo);
+        if (lane == cnt - 1) myedge = rel;
+        const unsigned rs = srng[rel];
+        const unsigned rlo = rs & 511u, span = rs >> 9;
+        const unsigned m11 = (2u << span) - 1u;
+        const int sh = (int)rlo - wbase;
+        flagw |= shl_clamp(m11, (unsigned)sh) | shr_clamp(m11, (unsigned)(-sh));
 #pragma unroll
         for (int k = 0; k < NPL; ++k)
             if ((word[k] & 511u) - rlo <= span) word[k] = 0u;
@@ -312,258 +366,320 @@ __device__ __forceinline__ int sector_pick(const float4* sp, const unsigned* sca
     return cnt;
 }
 
-__global__ void __launch_bounds__(kExtractThreads, 4) k_ring_extract(ExtractParams P) {
+// more than 256 candidates in a sector: the words stay in shared memory (slow, never seen on LiDAR-like data)
+__device__ __noinline__ int sector_pick_large(const float4* sp, unsigned* scand, int C, const unsigned* slink, int Ls, int lane,
+                                              unsigned& flagw, int& myedge, int cnt) {
+    const int wbase = lane * 32;
+    while (true) {
+        unsigned m = 0u;
+        for (int j = lane; j < C; j += 32) m = max(m, scand[j]);
+        const unsigned M = __reduce_max_sync(kFull, m);
+        if (M == 0u) break;
+        const unsigned bucket = M >> 9;
+        // always the exact comparison inside the top bucket
+        unsigned long long bk = 0ull;
+        int bi = -1;
+        for (int j = lane; j < C; j += 32) {
+            const unsigned wd = scand[j];
+            if ((wd >> 9) == bucket) {
+                const int r = (int)(wd & 511u);
+                const unsigned long long v = (unsigned long long)__double_as_longlong(curvature_exact(sp, r + 5));
+                if (bi < 0 || v > bk || (v == bk && r > bi)) { bk = v; bi = r; }
+            }
+        }
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) {
+            const unsigned long long ok = __shfl_xor_sync(kFull, bk, o);
+            const int oi = __shfl_xor_sync(kFull, bi, o);
+            if (oi >= 0 && (bi < 0 || ok > bk || (ok == bk && oi > bi))) { bk = ok; bi = oi; }
+        }
+        const int rel = bi;
+        cnt++;
+        if (cnt > kEdgePerSector) {
+            if ((rel >> 5) == lane) flagw |= 1u << (rel & 31);
+            break;
+        }
+        if (lane == cnt - 1) myedge = rel;
+        const unsigned steps = __funnelshift_r(slink[rel >> 5], slink[(rel >> 5) + 1], rel & 31) & 0x3ffu;
+        const int fwd = __ffs(~(steps >> 5) | 32u) - 1;
+        const int back = __clz(~steps & 31u) - 27;
+        const unsigned rlo = (unsigned)max(rel - back, 0), span = (unsigned)min(rel + fwd, Ls - 1) - rlo;
+        const unsigned m11 = (2u << span) - 1u;
+        const int sh = (int)rlo - wbase;
+        flagw |= shl_clamp(m11, (unsigned)sh) | shr_clamp(m11, (unsigned)(-sh));
+        for (int j = lane; j < C; j += 32)
+            if ((scand[j] & 511u) - rlo <= span) scand[j] = 0u;
+        __syncwarp();
+    }
+    return cnt;
+}
+
+// One warp per sector, handed out by ticket ((ring, sector)-major over the batch, so the sectors a warp has to look back on
+// were started a whole wave earlier).  No CTA-wide barrier anywhere: gather the sector's points (+5 on either side) from the
+// ring's tiles into the warp's slice of shared memory; 11-tap float curvature in the reference's order from a 20-point
+// register window per lane (:73-80), squares in double; short-step link bits (:129-132, :138-141); candidates (> 0.1, :114)
+// compacted by ballot; greedy pick (sector_pick); surf = unflagged (:198-205).  Output offsets: every sector publishes
+// (epoch | edges | surfs), the last sector of a ring to finish publishes the ring's sum, and a sector's offset is the sum of
+// the earlier rings' words plus the earlier sectors of its own ring: the compacted clouds are written once, from shared memory.
+template <bool kLabel>
+__global__ void __launch_bounds__(kSecWarps * 32, 14) k_sector_extract(ExtractParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float4* sp = reinterpret_cast<float4*>(smem_raw);                       // [rcap + 16] ring points
-    unsigned* scand = reinterpret_cast<unsigned*>(sp + P.rcap + 16);        // [rcap] candidate words, one list per sector
-    int* tl_off = reinterpret_cast<int*>(scand + P.rcap);                   // [maxtl + 1]
-    uint8_t* sflag = reinterpret_cast<uint8_t*>(tl_off + P.maxtl + 1);      // [rcap] picked / suppressed
-    uint8_t* slinkb = sflag + P.rcap;                                       // [rcap + 16] short step q -> q+1
-    int* ssrc = reinterpret_cast<int*>(slinkb + P.rcap + 16);               // [rcap] source index (label output only)
+    const int lane = threadIdx.x & 31;
+    const int S = P.scap;
+    unsigned char* wsm = smem_raw + (size_t)(threadIdx.x >> 5) * P.warp_smem;
+    float4* sp = reinterpret_cast<float4*>(wsm);                         // [S + 16] sector points, local index q
+    unsigned* scand = reinterpret_cast<unsigned*>(sp + S + 16);          // [S] candidate words; once they sit in registers the
+    uint16_t* srng = reinterpret_cast<uint16_t*>(scand);                 //     same bytes hold the suppressed range per position
+    unsigned* slink = scand + S;                                         // [S / 32 + 2] link bits: bit q = short step q -> q+1
+    int* ssrc = reinterpret_cast<int*>(slink + S / 32 + 2);              // [S] source index (label output only)
 
-    __shared__ int s_work;
-    __shared__ int s_warp[kExtractWarps];
-    __shared__ int s_edge_ids[kSectors][kEdgePerSector];
-    __shared__ int s_ecnt[kSectors], s_scnt[kSectors], s_ccnt[kSectors];
-    __shared__ int s_eoff, s_soff;
-
-    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-    constexpr int NW = kExtractWarps;
-
-    // work item by ticket: CTAs that hold ticket t only ever wait on tickets < t, which are already running
-    if (tid == 0) s_work = (int)atomicAdd(&P.ctrl[0], 1u);
-    if (tid < kSectors) s_ccnt[tid] = 0;
-    __syncthreads();
-    // ring-major over the batch: ring r of a scan starts a whole wave of CTAs after its rings 0..r-1, so by the time it looks
-    // back for their counts they have long been published (scan-major order made ring 63 wait for 63 siblings started with it)
-    const int s = s_work % P.batch, r = s_work / P.batch;
     const unsigned epoch = *reinterpret_cast<volatile unsigned int*>(&P.ctrl[1]);
-    const int n = P.n[s];
-    const uint8_t* rid = P.ringid + (size_t)s * P.stride;
-    const float4* pts = P.pts + (size_t)s * P.stride;
-    const uint8_t* pure = P.tile_pure + (size_t)s * P.tiles;
-    const bool want_label = P.label != nullptr;
+    const int nsec = P.batch * P.num_lines * kSectors;       // < 2^23 (host): the float division below is exact
+    const float inv_batch = 1.0f / (float)P.batch;
+    const unsigned lt = lanemask_lt();
 
-    // A. tile range of this ring (from the classify kernel); hand the slot back for the next launch
-    int2* rtp = P.ring_tiles + (size_t)s * kMaxLines + r;
-    const int2 rt = *rtp;
-    __syncthreads();
-    if (tid == 0) *rtp = make_int2(0x7fffffff, -1);
-    const int tlo = rt.x;
-    int ncand = rt.y >= rt.x ? rt.y - rt.x + 1 : 0;
-    if (ncand > P.maxtl) ncand = P.maxtl;   // cannot happen (maxtl = tiles per scan)
-
-    // B. matches per tile (a pure tile holds 256 points of one ring)
-    for (int c = w; c < ncand; c += NW) {
-        const int tbase = (tlo + c) * kTile;
-        const int pr = pure[tlo + c];
-        int cnt = 0;
-        if (pr == r) {
-            cnt = min(kTile, n - tbase);
-        } else if (pr == 255) {
-#pragma unroll
-            for (int k = 0; k < kTile / 32; ++k) {
-                int i = tbase + k * 32 + lane;
-                int b = i < n ? rid[i] : 255;
-                cnt += __popc(__ballot_sync(0xffffffffu, b == r));
-            }
+    while (true) {
+        int ticket = 0;
+        if (lane == 0) ticket = (int)atomicAdd(&P.ctrl[0], 1u);
+        ticket = __shfl_sync(kFull, ticket, 0);
+        if (ticket >= nsec) break;
+        const int rk = __float2int_rd(((float)ticket + 0.5f) * inv_batch), s = ticket - rk * P.batch;
+        const int r = rk / kSectors, k = rk - r * kSectors;
+        const int4 info = P.ring_info[(size_t)s * kMaxLines + r];
+        const int tlo = info.x, ncand = info.y, nr = info.z;
+        bool active = nr >= 131;                                   // :67
+        if (nr > P.rcap) {
+            active = false;
+            if (lane == 0 && k == 0) atomicOr(&P.ctrl[2], 1u);     // ring larger than the configured capacity
         }
-        if (lane == 0) tl_off[c] = cnt;
-    }
-    __syncthreads();
-    const int nr = block_excl_scan(tl_off, ncand, s_warp);
-    bool active = nr >= 131;                                   // :67
-    if (nr > P.rcap) {
-        active = false;
-        if (tid == 0) atomicOr(&P.ctrl[2], 1u);                // ring larger than the shared-memory capacity
-    }
+        int ne = 0, Ls = 0, myedge = 0;
+        unsigned flagw = 0u;
+        if (active) {
+            const int total = nr - 10, L = total / kSectors;
+            const int lo = L * k, hi = (k == kSectors - 1) ? total - 1 : lo + L - 1;   // hi excluded (:83-88)
+            Ls = hi - lo;
+            const int n_loc = Ls + 10, p0 = lo, p1 = lo + n_loc;     // ring positions [p0, p1) = local [0, n_loc)
+            const float4* pts = P.pts + (size_t)s * P.stride;
+            const uint8_t* rid = P.ringid + (size_t)s * P.stride;
+            const uint8_t* pure = P.tile_pure + (size_t)s * P.tiles;
+            const int* off = P.tile_off + ((size_t)s * kMaxLines + r) * (P.tiles + 1);
 
-    int e_total = 0, s_total = 0;
-    if (active) {
-        // C. stable gather of the ring into shared memory
-        for (int c = w; c < ncand; c += NW) {
-            const int tbase = (tlo + c) * kTile;
-            const int pr = pure[tlo + c];
-            int pos = tl_off[c];
-            if (pr == r) {
-                const int cnt = min(kTile, n - tbase);
-                float4 v[kTile / 32];
-#pragma unroll
-                for (int k = 0; k < kTile / 32; ++k)
-                    if (k * 32 + lane < cnt) v[k] = __ldg(pts + tbase + k * 32 + lane);
-#pragma unroll
-                for (int k = 0; k < kTile / 32; ++k) {
-                    if (k * 32 + lane < cnt) {
-                        sp[pos + k * 32 + lane] = v[k];
-                        if (want_label) ssrc[pos + k * 32 + lane] = tbase + k * 32 + lane;
-                    }
-                }
-            } else if (pr == 255) {
-                unsigned m[kTile / 32];
-#pragma unroll
-                for (int k = 0; k < kTile / 32; ++k) {
-                    int i = tbase + k * 32 + lane;
-                    int b = i < n ? rid[i] : 255;
-                    m[k] = __ballot_sync(0xffffffffu, b == r);
-                }
-                float4 v[kTile / 32];
-#pragma unroll
-                for (int k = 0; k < kTile / 32; ++k)
-                    if (m[k] >> lane & 1u) v[k] = __ldg(pts + tbase + k * 32 + lane);
-#pragma unroll
-                for (int k = 0; k < kTile / 32; ++k) {
-                    if (m[k] >> lane & 1u) {
-                        int d = pos + __popc(m[k] & lanemask_lt());
-                        sp[d] = v[k];
-                        if (want_label) ssrc[d] = tbase + k * 32 + lane;
-                    }
-                    pos += __popc(m[k]);
-                }
+            // A. first tile of the ring's range that reaches ring position p0
+            int c = 0;
+            for (int cb = 0; cb < ncand; cb += 32) {
+                const int cc = cb + lane;
+                const unsigned le = __ballot_sync(kFull, cc < ncand && off[cc + 1] <= p0);
+                c += __popc(le);
+                if (le != kFull) break;
             }
-        }
-        // flags of the ring, cleared by words
-        for (int q = tid; q < (nr + 3) / 4; q += kExtractThreads) reinterpret_cast<unsigned*>(sflag)[q] = 0u;
-        __syncthreads();
-
-        // D. curvature (:73-80) and short-step bytes (:129-132, :138-141) from a register window: a lane owns kWin
-        //    consecutive ring positions per pass; candidates (value > 0.1, :114) go straight into their sector's list.
-        const int total = nr - 10, L = total / kSectors;
-        const float inv_l = 1.0f / (float)L;
-        for (int base = 5 + w * (32 * kWin); base < nr - 1; base += NW * 32 * kWin) {
-            const int j0 = base + lane * kWin;
-            if (j0 < nr - 1) {
-                float wx[kWin + 10], wy[kWin + 10], wz[kWin + 10];
-#pragma unroll
-                for (int k = 0; k < kWin + 10; ++k) {
-                    const float4 p = sp[j0 - 5 + k];
-                    wx[k] = p.x; wy[k] = p.y; wz[k] = p.z;
-                }
-                // short steps q -> q+1 for the own positions (and 0..4 by the lane that owns position 5): float differences,
-                // double squares, decided in fp32 unless within 1e-6 of the threshold 0.05
-                auto short_step = [&](int k) {   // window slots k, k+1
-                    const float dx = __fsub_rn(wx[k + 1], wx[k]), dy = __fsub_rn(wy[k + 1], wy[k]), dz = __fsub_rn(wz[k + 1], wz[k]);
-                    const float sf = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-                    if (sf < 0.04999995f) return true;
-                    if (sf > 0.05000005f) return false;
-                    const double ddx = dx, ddy = dy, ddz = dz;
-                    return !(__dadd_rn(__dadd_rn(__dmul_rn(ddx, ddx), __dmul_rn(ddy, ddy)), __dmul_rn(ddz, ddz)) > 0.05);
-                };
-#pragma unroll
-                for (int k = 0; k < kWin; ++k)
-                    if (j0 + k + 1 < nr) slinkb[j0 + k] = short_step(k + 5) ? 1 : 0;
-                if (j0 == 5) {
-#pragma unroll
-                    for (int k = 0; k < 5; ++k) slinkb[k] = short_step(k) ? 1 : 0;
-                }
-                int t = j0 - 5;
-                int sec = min(kSectors - 1, __float2int_rd(((float)t + 0.5f) * inv_l));
-                int bound = L * (sec + 1);
-#pragma unroll
-                for (int k = 0; k < kWin; ++k, ++t) {
-                    auto tap = [&](const float* a) {
-                        float u = __fadd_rn(a[k], a[k + 1]);
-                        u = __fadd_rn(u, a[k + 2]);
-                        u = __fadd_rn(u, a[k + 3]);
-                        u = __fadd_rn(u, a[k + 4]);
-                        u = __fsub_rn(u, __fmul_rn(10.0f, a[k + 5]));
-                        u = __fadd_rn(u, a[k + 6]);
-                        u = __fadd_rn(u, a[k + 7]);
-                        u = __fadd_rn(u, a[k + 8]);
-                        u = __fadd_rn(u, a[k + 9]);
-                        u = __fadd_rn(u, a[k + 10]);
-                        return (double)u;
-                    };
-                    if (sec < kSectors - 1 && t >= bound) { ++sec; bound += L; }
-                    // sector slice [L sec, hi) with hi = L (sec+1) - 1, or total - 1 for the last: hi itself is dropped (:83-88)
-                    const int hi = sec == kSectors - 1 ? total - 1 : bound - 1;
-                    if (t < hi) {
-                        const double dx = tap(wx), dy = tap(wy), dz = tap(wz);
-                        const double val = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
-                        if (val > 0.1) {
-                            // key monotone in the exact value (round towards zero), index relative to the sector start
-                            const unsigned key = __float_as_uint(__double2float_rz(val)) >> 8;
-                            const int pos = atomicAdd(&s_ccnt[sec], 1);
-                            scand[L * sec + 5 + pos] = (key << 9) | (unsigned)(t - L * sec);
+            // B. stable gather (:62)
+            for (; c < ncand; ++c) {
+                const int beg = off[c];
+                if (beg >= p1) break;
+                const int end = off[c + 1];
+                if (end == beg) continue;
+                const int tbase = (tlo + c) * kTile;
+                if (pure[tlo + c] == r) {
+                    const int ps = max(beg, p0), pe = min(end, p1);
+                    for (int pos = ps + lane; pos < pe; pos += 32) {
+                        cp_async_16(sp + (pos - p0), pts + tbase + (pos - beg));
+                        if (kLabel) ssrc[pos - p0] = tbase + (pos - beg);
+                    }
+                } else {
+                    int run = beg;
+                    for (int row = 0; row < kTile / 32 && run < p1; ++row) {
+                        const int i = tbase + row * 32 + lane;
+                        const bool mt = rid[i] == r;
+                        const unsigned mm = __ballot_sync(kFull, mt);
+                        const int pos = run + __popc(mm & lt);
+                        if (mt && pos >= p0 && pos < p1) {
+                            cp_async_16(sp + (pos - p0), pts + i);
+                            if (kLabel) ssrc[pos - p0] = i;
                         }
+                        run += __popc(mm);
                     }
                 }
             }
-        }
-        __syncthreads();
-
-        // E. one warp per sector (:81-92, :99-209)
-        {
-            const int lo = L * w, hi = (w == kSectors - 1) ? total - 1 : L * (w + 1) - 1;   // hi excluded (:83-88)
-            const int a = lo + 5, b = hi + 5;
-            const int C = s_ccnt[w];
-            int cnt;
-            const unsigned* sc = scand + a;
-            if (C <= 32) cnt = sector_pick<1>(sp, sc, C, slinkb, sflag, s_edge_ids[w], a, b, lane);
-            else if (C <= 64) cnt = sector_pick<2>(sp, sc, C, slinkb, sflag, s_edge_ids[w], a, b, lane);
-            else if (C <= 128) cnt = sector_pick<4>(sp, sc, C, slinkb, sflag, s_edge_ids[w], a, b, lane);
-            else if (C <= 256) cnt = sector_pick<8>(sp, sc, C, slinkb, sflag, s_edge_ids[w], a, b, lane);
-            else cnt = sector_pick<16>(sp, sc, C, slinkb, sflag, s_edge_ids[w], a, b, lane);
+            if (lane < S / 32 + 2) slink[lane] = 0u;
+            cp_async_wait_all();
             __syncwarp();
-            int nsurf = 0;
-            for (int base = a; base < b; base += 32) {
-                int i = base + lane;
-                nsurf += __popc(__ballot_sync(0xffffffffu, i < b && !sflag[i]));
-            }
-            if (lane == 0) { s_ecnt[w] = min(cnt, kEdgePerSector); s_scnt[w] = nsurf; }
-        }
-        __syncthreads();
-        for (int k = 0; k < kSectors; ++k) { e_total += s_ecnt[k]; s_total += s_scnt[k]; }
-    }
 
-    // F. publish this ring's counts, then look back over the earlier rings of the same scan
-    unsigned long long* done = P.done + (size_t)s * kMaxLines;
-    if (tid == 0)
-        st_release_u64(done + r, ((unsigned long long)epoch << 32) | ((unsigned long long)e_total << 20) | (unsigned long long)s_total);
-    if (w == 0) {
-        int e = 0, su = 0;
-        for (int q = lane; q < r; q += 32) {
-            unsigned long long v = ld_acquire_u64(done + q);
-            while ((unsigned)(v >> 32) != epoch) {
+            // C. curvature, link bits, candidates
+            int C = 0;
+            for (int qb = 5; qb < n_loc - 1; qb += 32 * kWin) {
+                const int q0 = qb + lane * kWin;
+                const bool act = q0 < n_loc - 1;
+                const int qa = act ? q0 : 5;
+                unsigned lm = 0u;
+                // two half windows of 15 points (5 positions each): keeps the register window at 45 floats
+#pragma unroll 1
+                for (int h = 0; h < 2; ++h) {
+                    constexpr int HW = kWin / 2;
+                    // packed fp32 pairs (add.f32x2 / mul.f32x2 / fma.rn.f32x2: IEEE round-to-nearest per half, so bit-identical to
+                    // the scalar operations): (x, y) and (z, intensity) as they come out of the 16-byte shared load
+                    float2 wxy[HW + 10], wzw[HW + 10];
+#pragma unroll
+                    for (int j = 0; j < HW + 10; ++j) {
+                        const float4 p = sp[qa - 5 + h * HW + j];
+                        wxy[j] = make_float2(p.x, p.y); wzw[j] = make_float2(p.z, p.w);
+                    }
+                    const float2 neg1 = make_float2(-1.0f, -1.0f);
+                    // short steps between window slots j, j+1: float differences, double squares (:129-132), decided in
+                    // fp32 unless within 1e-7 of the threshold 0.05
+                    auto short_step = [&](int j) {
+                        const float2 dxy = __ffma2_rn(wxy[j], neg1, wxy[j + 1]), dzw = __ffma2_rn(wzw[j], neg1, wzw[j + 1]);   // b - a
+                        const float2 sq = __fmul2_rn(dxy, dxy);
+                        const float sf = __fmaf_rn(dzw.x, dzw.x, __fadd_rn(sq.x, sq.y));
+                        if (fabsf(sf - 0.05f) > 1e-7f) return sf < 0.05f;
+                        const double ddx = dxy.x, ddy = dxy.y, ddz = dzw.x;
+                        return !(__dadd_rn(__dadd_rn(__dmul_rn(ddx, ddx), __dmul_rn(ddy, ddy)), __dmul_rn(ddz, ddz)) > 0.05);
+                    };
+                    const int qh = q0 + h * HW;
+#pragma unroll
+                    for (int j = 0; j < HW; ++j)
+                        if (short_step(j + 5) && qh + j + 1 < n_loc) lm |= 1u << (h * HW + j);
+                    if (qh == 5) {       // the first lane also owns the steps 0 .. 4 (kept above its own ten bits for now)
+#pragma unroll
+                        for (int j = 0; j < 5; ++j)
+                            if (short_step(j)) lm |= 1u << (kWin + j);
+                    }
+#pragma unroll
+                    for (int j = 0; j < HW; ++j) {
+                        auto tap = [&](const float2* a) {     // left to right, t - 10 p = t + (-10 p) (:73-75)
+                            float2 u = __fadd2_rn(a[j], a[j + 1]);
+                            u = __fadd2_rn(u, a[j + 2]);
+                            u = __fadd2_rn(u, a[j + 3]);
+                            u = __fadd2_rn(u, a[j + 4]);
+                            // scalar products: ptxas 12.9 contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 (one rounding)
+                            u = __fadd2_rn(u, make_float2(__fmul_rn(-10.0f, a[j + 5].x), __fmul_rn(-10.0f, a[j + 5].y)));
+                            u = __fadd2_rn(u, a[j + 6]);
+                            u = __fadd2_rn(u, a[j + 7]);
+                            u = __fadd2_rn(u, a[j + 8]);
+                            u = __fadd2_rn(u, a[j + 9]);
+                            u = __fadd2_rn(u, a[j + 10]);
+                            return u;
+                        };
+                        const float2 sxy = tap(wxy), szw = tap(wzw);
+                        const double dx = (double)sxy.x, dy = (double)sxy.y, dz = (double)szw.x;
+                        const double val = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+                        const int rel = qh + j - 5;
+                        const bool isc = act && rel < Ls && val > 0.1;
+                        const unsigned cm = __ballot_sync(kFull, isc);
+                        if (isc) {
+                            // key monotone in the exact value: exponent and 18 mantissa bits of the double above 2^-4 (saturating)
+                            const unsigned key = min(((unsigned)__double2hiint(val) - 0x3FB00000u) >> 2, 0x7FFFFFu);
+                            scand[C + __popc(cm & lt)] = (key << 9) | (unsigned)rel;
+                        }
+                        C += __popc(cm);
+                    }
+                }
+                if (act) {
+                    int q = q0;
+                    if (q0 == 5) {
+                        lm = ((lm & ((1u << kWin) - 1u)) << 5) | (lm >> kWin);
+                        q = 0;
+                    }
+                    if (lm != 0u) {
+                        atomicOr(&slink[q >> 5], lm << (q & 31));
+                        if ((q & 31) != 0 && (lm >> (32 - (q & 31))) != 0u) atomicOr(&slink[(q >> 5) + 1], lm >> (32 - (q & 31)));
+                    }
+                }
+            }
+            __syncwarp();
+
+            // D. greedy pick (:99-209)
+            int cnt, cw = C;
+            if (C <= 64) { cnt = sector_pick<2>(scand, C, slink, srng, Ls, lane, flagw, myedge); cw = 64; }
+            else if (C <= 128) { cnt = sector_pick<4>(scand, C, slink, srng, Ls, lane, flagw, myedge); cw = 128; }
+            else if (C <= 256) { cnt = sector_pick<8>(scand, C, slink, srng, Ls, lane, flagw, myedge); cw = 256; }
+            else cnt = -1;
+            if (cnt < 0) cnt = sector_pick_large(sp, scand, cw, slink, Ls, lane, flagw, myedge, -1 - cnt);
+            ne = min(cnt, kEdgePerSector);
+        }
+        // surf = unflagged (:198-205): lane w owns the bits of rel 32 w .. 32 w + 31; base = surf points before its word
+        const int remw = Ls - lane * 32;
+        const unsigned keep = ~flagw & (remw >= 32 ? kFull : (remw > 0 ? (1u << remw) - 1u : 0u));
+        int sbase = __popc(keep);
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int y = __shfl_up_sync(kFull, sbase, o);
+            if (lane >= o) sbase += y;
+        }
+        const int ns = __shfl_sync(kFull, sbase, 31);
+        sbase -= __popc(keep);
+
+        // E. publish this sector's counts (the word is its own message: relaxed accesses, no fence)
+        unsigned long long* dsec = P.done_sec + ((size_t)s * kMaxLines + r) * kSectors;
+        unsigned long long* dring = P.done_ring + (size_t)s * kMaxLines;
+        if (lane == 0)
+            st_relaxed_u64(dsec + k, ((unsigned long long)epoch << 32) | ((unsigned long long)ne << 20) | (unsigned long long)ns);
+        // F. look back.  Own ring first: its last sector has then seen all siblings and publishes the ring's word (before it
+        //    waits for anything else, so ring words never chain); then the earlier rings of the scan, one word per ring.
+        //    The polls are warp-uniform loops (every lane stays until all words have arrived): a per-lane spin leaves the warp
+        //    split for the rest of the iteration and every later instruction is issued once per fragment.
+        int e_in = 0, su_in = 0;
+        {
+            unsigned long long v = 0ull;
+            bool ok = lane >= k;
+            while (true) {
+                if (!ok) {
+                    v = ld_relaxed_u64(dsec + lane);
+                    ok = (unsigned)(v >> 32) == epoch;
+                }
+                if (__all_sync(kFull, ok)) break;
                 __nanosleep(200);
-                v = ld_acquire_u64(done + q);
             }
-            e += (int)((v >> 20) & 0xfffu);
-            su += (int)(v & 0xfffffu);
+            if (lane < k) {
+                e_in = (int)((v >> 20) & 0xfffu);
+                su_in = (int)(v & 0xfffffu);
+            }
         }
-        e = __reduce_add_sync(0xffffffffu, e);
-        su = __reduce_add_sync(0xffffffffu, su);
-        if (lane == 0) {
-            s_eoff = e; s_soff = su;
-            if (r == P.num_lines - 1) { P.n_edge[s] = e + e_total; P.n_surf[s] = su + s_total; }
+        e_in = __reduce_add_sync(kFull, e_in);
+        su_in = __reduce_add_sync(kFull, su_in);
+        if (k == kSectors - 1 && lane == 0)
+            st_relaxed_u64(dring + r, ((unsigned long long)epoch << 32) | ((unsigned long long)(e_in + ne) << 20) |
+                                          (unsigned long long)(su_in + ns));
+        int e = 0, su = 0;
+        {
+            unsigned long long v0 = 0ull, v1 = 0ull;      // r <= 63: at most two ring words per lane
+            bool ok0 = lane >= r, ok1 = lane + 32 >= r;
+            while (true) {
+                if (!ok0) {
+                    v0 = ld_relaxed_u64(dring + lane);
+                    ok0 = (unsigned)(v0 >> 32) == epoch;
+                }
+                if (!ok1) {
+                    v1 = ld_relaxed_u64(dring + lane + 32);
+                    ok1 = (unsigned)(v1 >> 32) == epoch;
+                }
+                if (__all_sync(kFull, ok0 && ok1)) break;
+                __nanosleep(200);
+            }
+            if (lane < r) { e += (int)((v0 >> 20) & 0xfffu); su += (int)(v0 & 0xfffffu); }
+            if (lane + 32 < r) { e += (int)((v1 >> 20) & 0xfffu); su += (int)(v1 & 0xfffffu); }
         }
-    }
-    __syncthreads();
-    if (!active) return;
+        e = __reduce_add_sync(kFull, e) + e_in;
+        su = __reduce_add_sync(kFull, su) + su_in;
+        if (r == P.num_lines - 1 && k == kSectors - 1 && lane == 0) { P.n_edge[s] = e + ne; P.n_surf[s] = su + ns; }
 
-    // G. write the compacted clouds straight from shared memory
-    {
-        const int total = nr - 10, L = total / kSectors;
-        const int lo = L * w, hi = (w == kSectors - 1) ? total - 1 : L * (w + 1) - 1;
-        const int a = lo + 5, b = hi + 5;
-        int eo = s_eoff, so = s_soff;
-        for (int k = 0; k < w; ++k) { eo += s_ecnt[k]; so += s_scnt[k]; }
-        uint8_t* label = want_label ? P.label + (size_t)s * P.stride : nullptr;
-        if (lane < s_ecnt[w]) {
-            int id = s_edge_ids[w][lane];
-            P.edge[(size_t)s * P.edge_stride + eo + lane] = sp[id];
-            if (label) label[ssrc[id]] = 1;
-        }
-        float4* surf = P.surf + (size_t)s * P.stride + so;
-        for (int base = a; base < b; base += 32) {
-            int i = base + lane;
-            bool f = i < b && !sflag[i];
-            unsigned m = __ballot_sync(0xffffffffu, f);
-            if (f) {
-                st_stream_f4(surf + __popc(m & lanemask_lt()), sp[i]);
-                if (label) label[ssrc[i]] = 2;
+        // G. write the compacted clouds straight from shared memory
+        if (active) {
+            uint8_t* label = kLabel ? P.label + (size_t)s * P.stride : nullptr;
+            if (lane < ne) {
+                P.edge[(size_t)s * P.edge_stride + e + lane] = sp[myedge + 5];
+                if (kLabel) label[ssrc[myedge + 5]] = 1;
             }
-            surf += __popc(m);
+            float4* surf = P.surf + (size_t)s * P.stride + su;
+            for (int row = 0; row * 32 < Ls; ++row) {
+                const unsigned kw = __shfl_sync(kFull, keep, row);
+                const int bw = __shfl_sync(kFull, sbase, row);
+                if (kw >> lane & 1u) {
+                    st_stream_f4(surf + bw + __popc(kw & lt), sp[row * 32 + lane + 5]);
+                    if (kLabel) label[ssrc[row * 32 + lane + 5]] = 2;
+                }
+            }
         }
+        __syncwarp();
     }
 }
 
@@ -576,21 +692,24 @@ struct pf_extract {
     int device = 0;
     cudaStream_t stream = nullptr;
     pf_lidar_params lidar{};
-    int stride = 0, tiles = 0, max_batch = 0, rcap = 0, maxtl = 0, edge_stride = 0;
-    size_t smem = 0;
+    int stride = 0, tiles = 0, max_batch = 0, rcap = 0, scap = 0, edge_stride = 0;
+    int warp_smem = 0, warp_smem_label = 0;   // bytes of shared memory per warp of k_sector_extract (without / with label output)
+    int ctas = 0, ctas_label = 0;             // resident CTAs of the persistent kernel on the whole device
     int group = 1;
     // device
     float4* d_pts = nullptr;
     uint8_t* d_ringid = nullptr;
     int2* d_ring_tiles = nullptr;
     uint8_t* d_tile_pure = nullptr;
+    int* d_tile_off = nullptr;
+    int4* d_ring_info = nullptr;
     float gate_lo = 0, gate_hi = 0;
-    size_t smem_label = 0;
     uint8_t* d_label = nullptr;
     float4* d_edge = nullptr;
     float4* d_surf = nullptr;
     int *d_n = nullptr, *d_n_edge = nullptr, *d_n_surf = nullptr;
-    unsigned long long* d_done = nullptr;
+    unsigned long long* d_done_sec = nullptr;
+    unsigned long long* d_done_ring = nullptr;
     unsigned int* d_ctrl = nullptr;
     // pinned host
     int* h_counts = nullptr;       // [3 * max_batch]: n, n_edge, n_surf
@@ -631,14 +750,25 @@ static int extract_launch(pf_extract* h, const float4* d_xyzi, const int* d_n, i
         P.surf = d_surf + (size_t)s0 * stride;
         P.n_edge = d_n_edge + s0;
         P.n_surf = d_n_surf + s0;
-        P.done = h->d_done + (size_t)s0 * kMaxLines;
+        P.tile_off = h->d_tile_off + (size_t)s0 * kMaxLines * (h->tiles + 1);
+        P.ring_info = h->d_ring_info + (size_t)s0 * kMaxLines;
+        P.done_sec = h->d_done_sec + (size_t)s0 * kMaxLines * kSectors;
+        P.done_ring = h->d_done_ring + (size_t)s0 * kMaxLines;
         P.ctrl = h->d_ctrl;
         P.stride = stride; P.tiles = tiles; P.edge_stride = edge_stride; P.batch = nb;
-        P.num_lines = h->lidar.num_lines; P.rcap = h->rcap; P.maxtl = h->maxtl;
+        P.num_lines = h->lidar.num_lines; P.rcap = h->rcap; P.scap = h->scap;
         P.min_d = h->lidar.min_distance; P.max_d = h->lidar.max_distance;
-        k_ring_classify<<<dim3(tiles, nb), kTile, 0, h->stream>>>(P, h->gate_lo, h->gate_hi);
-        k_ring_extract<<<nb * h->lidar.num_lines, kExtractThreads, d_label ? h->smem_label : h->smem, h->stream>>>(P);
-        h->launches += 2;
+        k_ring_classify<<<dim3(div_up(tiles, kClassifyThreads / 32), nb), kClassifyThreads, 0, h->stream>>>(P, h->gate_lo, h->gate_hi);
+        k_ring_index<<<div_up(nb * h->lidar.num_lines, 8), 256, 0, h->stream>>>(P);
+        const int want = div_up(nb * h->lidar.num_lines * kSectors, kSecWarps);
+        if (d_label) {
+            P.warp_smem = h->warp_smem_label;
+            k_sector_extract<true><<<want < h->ctas_label ? want : h->ctas_label, kSecWarps * 32, (size_t)kSecWarps * h->warp_smem_label, h->stream>>>(P);
+        } else {
+            P.warp_smem = h->warp_smem;
+            k_sector_extract<false><<<want < h->ctas ? want : h->ctas, kSecWarps * 32, (size_t)kSecWarps * h->warp_smem, h->stream>>>(P);
+        }
+        h->launches += 3;
     }
     PF_CUDA(cudaGetLastError());
     return PF_OK;
@@ -665,6 +795,7 @@ extern "C" int pf_extract_create(const pf_lidar_params* lidar, const pf_extract_
     PF_REQUIRE(lidar->num_lines == 16 || lidar->num_lines == 32 || lidar->num_lines == 64,
                "num_lines must be 16, 32 or 64 (src/laserProcessingClass.cpp:30-61), got %d", lidar->num_lines);
     PF_REQUIRE(cfg->max_points > 0 && cfg->max_batch > 0, "max_points and max_batch must be positive");
+    PF_REQUIRE(cfg->max_batch <= 16384, "max_batch %d > 16384", cfg->max_batch);   // sectors per launch stay below 2^23
     int ndev = 0;
     PF_CUDA(cudaGetDeviceCount(&ndev));
     PF_REQUIRE(device >= 0 && device < ndev, "device %d not available (%d devices)", device, ndev);
@@ -686,19 +817,31 @@ extern "C" int pf_extract_create(const pf_lidar_params* lidar, const pf_extract_
         delete h;
         return PF_ERR_INVALID;
     }
-    h->maxtl = h->tiles;
     h->edge_stride = 120 * lidar->num_lines;
-    // shared memory of k_ring_extract: points, keys, link bits, tile offsets, flags (+ source indices for the label output)
-    h->smem = (size_t)(h->rcap + 16) * 16 + (size_t)h->rcap * 4 + (size_t)(h->maxtl + 1) * 4 + h->rcap + (h->rcap + 16);
-    h->smem = (h->smem + 15) / 16 * 16;
-    h->smem_label = h->smem + (size_t)h->rcap * 4;
-    if (h->smem_label > (size_t)prop.sharedMemPerBlockOptin) {
-        set_error("max_ring_points %d / max_points %d need %zu B shared memory (> %zu)", h->rcap, cfg->max_points, h->smem_label,
+    // shared memory of one warp of k_sector_extract: a sector of a ring of rcap points (+5 points either side, +16 of slack for
+    // the register windows), candidate words, link bits, suppressed ranges (+ source indices for the label output)
+    h->scap = div_up((h->rcap - 10) / kSectors + 14, 32) * 32;
+    if (h->scap < 256) h->scap = 256;     // sector_pick hands up to 256 live words back through the candidate array
+    h->warp_smem = (h->scap + 16) * 16 + h->scap * 4 + (h->scap / 32 + 2) * 4;
+    h->warp_smem = div_up(h->warp_smem, 16) * 16;
+    h->warp_smem_label = h->warp_smem + h->scap * 4;
+    if ((size_t)kSecWarps * h->warp_smem_label > (size_t)prop.sharedMemPerBlockOptin) {
+        set_error("max_ring_points %d needs %d B shared memory (> %zu)", h->rcap, kSecWarps * h->warp_smem_label,
                   (size_t)prop.sharedMemPerBlockOptin);
         delete h;
         return PF_ERR_INVALID;
     }
-    PF_CUDA(cudaFuncSetAttribute(k_ring_extract, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_label));
+    PF_CUDA(cudaFuncSetAttribute(k_sector_extract<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSecWarps * h->warp_smem));
+    PF_CUDA(cudaFuncSetAttribute(k_sector_extract<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSecWarps * h->warp_smem_label));
+    {
+        int occ = 0, occ_label = 0;
+        PF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sector_extract<false>, kSecWarps * 32, (size_t)kSecWarps * h->warp_smem));
+        PF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_label, k_sector_extract<true>, kSecWarps * 32,
+                                                              (size_t)kSecWarps * h->warp_smem_label));
+        PF_REQUIRE(occ >= 1 && occ_label >= 1, "k_sector_extract does not fit on an SM");
+        h->ctas = occ * prop.multiProcessorCount;
+        h->ctas_label = occ_label * prop.multiProcessorCount;
+    }
     // fp32 range gate strictly inside [min_distance, max_distance]: everything else takes the exact double comparison
     h->gate_lo = (float)lidar->min_distance;
     if (!((double)h->gate_lo > lidar->min_distance)) h->gate_lo = nextafterf(h->gate_lo, INFINITY);
@@ -735,9 +878,13 @@ extern "C" int pf_extract_create(const pf_lidar_params* lidar, const pf_extract_
     PF_CUDA(cudaMalloc(&h->d_cnt1, sizeof(int) * 2));
     PF_CUDA(cudaMalloc(&h->d_n_edge, sizeof(int) * h->max_batch));
     PF_CUDA(cudaMalloc(&h->d_n_surf, sizeof(int) * h->max_batch));
-    PF_CUDA(cudaMalloc(&h->d_done, sizeof(unsigned long long) * h->max_batch * kMaxLines));
+    PF_CUDA(cudaMalloc(&h->d_tile_off, sizeof(int) * (size_t)h->max_batch * kMaxLines * (h->tiles + 1)));
+    PF_CUDA(cudaMalloc(&h->d_ring_info, sizeof(int4) * (size_t)h->max_batch * kMaxLines));
+    PF_CUDA(cudaMalloc(&h->d_done_sec, sizeof(unsigned long long) * h->max_batch * kMaxLines * kSectors));
+    PF_CUDA(cudaMalloc(&h->d_done_ring, sizeof(unsigned long long) * h->max_batch * kMaxLines));
     PF_CUDA(cudaMalloc(&h->d_ctrl, sizeof(unsigned) * 4));
-    PF_CUDA(cudaMemset(h->d_done, 0, sizeof(unsigned long long) * h->max_batch * kMaxLines));
+    PF_CUDA(cudaMemset(h->d_done_sec, 0, sizeof(unsigned long long) * h->max_batch * kMaxLines * kSectors));
+    PF_CUDA(cudaMemset(h->d_done_ring, 0, sizeof(unsigned long long) * h->max_batch * kMaxLines));
     PF_CUDA(cudaMemset(h->d_ctrl, 0, sizeof(unsigned) * 4));
     PF_CUDA(cudaMallocHost(&h->h_counts, sizeof(int) * 3 * h->max_batch));
     PF_CUDA(cudaMallocHost(&h->h_ctrl, sizeof(unsigned) * 4));
@@ -750,7 +897,8 @@ extern "C" int pf_extract_destroy(pf_extract* h) {
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     cudaFree(h->d_pts); cudaFree(h->d_ringid); cudaFree(h->d_ring_tiles); cudaFree(h->d_tile_pure); cudaFree(h->d_label); cudaFree(h->d_edge);
-    cudaFree(h->d_surf); cudaFree(h->d_n); cudaFree(h->d_n_edge); cudaFree(h->d_n_surf); cudaFree(h->d_done);
+    cudaFree(h->d_surf); cudaFree(h->d_n); cudaFree(h->d_n_edge); cudaFree(h->d_n_surf); cudaFree(h->d_done_sec);
+    cudaFree(h->d_done_ring); cudaFree(h->d_tile_off); cudaFree(h->d_ring_info);
     cudaFree(h->d_edge1); cudaFree(h->d_surf1); cudaFree(h->d_cnt1);
     cudaFree(h->d_ctrl);
     cudaFreeHost(h->h_counts); cudaFreeHost(h->h_ctrl);
