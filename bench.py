@@ -177,7 +177,7 @@ def run_reference(args):
 # ----------------------------------------------------------------------------------------------------------------
 def roofline_leg(pfb, capi, torch, scans, dev):
     """Batched extraction (K1) with a working set larger than L2, CUDA-event timed on the extractor's stream."""
-    batch, stride = 128, MAX_POINTS
+    batch, stride = int(os.environ.get('PF_BENCH_BATCH', '128')), MAX_POINTS
     ex = capi.Extractor(num_lines=64, max_points=stride, max_batch=batch, max_ring_points=int(os.environ.get('PF_BENCH_RCAP', '0')))
     x = np.zeros((batch, stride, 4), np.float32)
     n = np.zeros(batch, np.int32)

@@ -82,14 +82,14 @@ __device__ __noinline__ int ring_id_exact(float x, float y, float z, int num_lin
     return id;
 }
 
-// fp32 evaluation of the same decision; returns -1 when the point is too close to a decision boundary to call.
+// fp32 evaluation of the same decision, straight-line; returns -1 when the point is too close to a decision boundary to call.
 // atan(t) = t P(t^2) on |t| <= 0.75 (least-squares fit, |error| < 6e-6 deg).  Error budget of the bin position u (bins are 1/3,
 // 1/2, 4/3 or 2 degrees wide): t is known to ~4e-7 relative (fma, MUFU.RSQ at 2 ulp, one product) = 1e-5 deg at 25 deg, the
 // polynomial adds 6e-6 deg and its evaluation ~5e-6 deg: < 7e-5 bins in the worst case (3 bins per degree); anything within
-// kEps = 2.5e-4 of an integer / a gate goes to the exact path.
-__device__ __forceinline__ int ring_id_fast_t(float t, int num_lines) {
+// kEps = 2.5e-4 of an integer or within 4 kEps of a validity gate goes to the exact path.
+template <int LINES>
+__device__ __forceinline__ int ring_id_fast_t(float t) {
     constexpr float kEps = 2.5e-4f;
-    if (!(fabsf(t) <= 0.75f)) return -1;
     const float u2 = __fmul_rn(t, t);
     float p = 0x1.2dafa8p-6f;
     p = __fmaf_rn(p, u2, -0x1.df9d38p-5f);
@@ -101,48 +101,51 @@ __device__ __forceinline__ int ring_id_fast_t(float t, int num_lines) {
     const float ang = __fmul_rn(__fmul_rn(p, t), 57.29577951308232f);
     float u;
     int base = 0;
-    if (num_lines == 64) {
-        if (fabsf(ang + 8.83f) < kEps) return -1;
-        if (ang >= -8.83f) {
-            if (ang > 2.0f - kEps) return ang > 2.0f + kEps ? 255 : -1;
-            u = __fmaf_rn(2.0f - ang, 3.0f, 0.5f);
-        } else {
-            if (ang < -24.33f + kEps) return ang < -24.33f - kEps ? 255 : -1;
-            u = __fmaf_rn(-8.83f - ang, 2.0f, 0.5f);
-            base = 32;
-        }
-    } else if (num_lines == 32) {
+    bool drop = false, unsure = !(fabsf(t) <= 0.75f);
+    if (LINES == 64) {
+        // upper block (angle >= -8.83): u = (2 - a) 3 + 0.5, valid while a <= 2 (u >= 0.5); lower block: u = (-8.83 - a) 2 + 0.5,
+        // valid while a >= -24.33 (u <= 31.5).  Either side of the split gives ring 32, away from any integer of u.
+        const bool lower = ang < -8.83f;
+        u = lower ? __fmaf_rn(ang, -2.0f, -17.16f) : __fmaf_rn(ang, -3.0f, 6.5f);
+        base = lower ? 32 : 0;
+        drop = lower ? u > 31.5f : u < 0.5f;
+        unsure = unsure || fabsf(u - (lower ? 31.5f : 0.5f)) < 4.0f * kEps;
+    } else if (LINES == 32) {
         u = __fmul_rn(ang + 30.666666f, 0.75f);
-        if (u < kEps) return u < -1.0f - kEps ? 255 : -1;    // int() truncates towards zero: (-1, 0] is ring 0
+        drop = u < -1.0f;                               // int() truncates towards zero: (-1, 0] is ring 0, left to the exact path
+        unsure = unsure || fabsf(u + 0.5f) < 0.5f + kEps;
     } else {
         u = __fmaf_rn(ang + 15.0f, 0.5f, 0.5f);
-        if (u < kEps) return u < -1.0f - kEps ? 255 : -1;
+        drop = u < -1.0f;
+        unsure = unsure || fabsf(u + 0.5f) < 0.5f + kEps;
     }
     const float fl = floorf(u), fr = u - fl;
-    if (fr < kEps || fr > 1.0f - kEps) return -1;
-    const int id = base + (int)fl;
-    return id < num_lines ? id : 255;
+    unsure = unsure || fabsf(fr - 0.5f) > 0.5f - kEps;
+    int id = base + (int)fl;
+    id = (drop || id >= LINES) ? 255 : id;
+    return unsure ? -1 : id;
 }
 
 // fp32 fast path on top of one MUFU.RSQ: dist = s * rsqrt(s) and z / dist = z * rsqrt(s) are good to ~3 ulp; the range gate is
 // pulled in by 1e-6 relative so that the approximate distance can never decide a point the reference's (double)sqrtf comparison
 // would not.
-__device__ __forceinline__ int ring_id_dev(float x, float y, float z, int num_lines, double min_d, double max_d, float gate_lo,
-                                           float gate_hi) {
+template <int LINES>
+__device__ __forceinline__ int ring_id_dev(float x, float y, float z, double min_d, double max_d, float gate_lo, float gate_hi) {
     const float s = __fmaf_rn(x, x, __fmul_rn(y, y));
     const float r = rsqrtf(s);
     const float dist = __fmul_rn(s, r);
-    int id = -1;
-    if (dist > gate_lo && dist < gate_hi && fabsf(z) < 3.0e38f) id = ring_id_fast_t(__fmul_rn(z, r), num_lines);
+    int id = ring_id_fast_t<LINES>(__fmul_rn(z, r));
+    if (!(dist > gate_lo && dist < gate_hi && fabsf(z) < 3.0e38f)) id = -1;
     if (id < 0) {
         if (!(isfinite(x) && isfinite(y) && isfinite(z))) return 255;   // x86 int(NaN) = INT_MIN: the reference drops these
-        id = ring_id_exact(x, y, z, num_lines, min_d, max_d);
+        id = ring_id_exact(x, y, z, LINES, min_d, max_d);
     }
     return id;
 }
 
 // One warp per 256-point tile (8 coalesced 512-byte rows, all loads in flight before the first use): ring id byte per point,
 // and the tile summary (one ring only -> "pure"; else the set of rings present) from registers and warp votes alone.
+template <int LINES, bool kLabel>
 __global__ void __launch_bounds__(kClassifyThreads) k_ring_classify(ExtractParams P, float gate_lo, float gate_hi) {
     const int s = blockIdx.y, lane = threadIdx.x & 31;
     const int tile = blockIdx.x * (kClassifyThreads / 32) + (threadIdx.x >> 5);
@@ -164,8 +167,8 @@ __global__ void __launch_bounds__(kClassifyThreads) k_ring_classify(ExtractParam
     for (int k = 0; k < R; ++k) {
         ring[k] = 255;
         if (i0 + 32 * k < n) {
-            ring[k] = ring_id_dev(p[k].x, p[k].y, p[k].z, P.num_lines, P.min_d, P.max_d, gate_lo, gate_hi);
-            if (P.label) P.label[g + 32 * k] = 0;
+            ring[k] = ring_id_dev<LINES>(p[k].x, p[k].y, p[k].z, P.min_d, P.max_d, gate_lo, gate_hi);
+            if (kLabel) P.label[g + 32 * k] = 0;
         }
         P.ringid[g + 32 * k] = (uint8_t)ring[k];
     }
@@ -301,9 +304,27 @@ __device__ __forceinline__ unsigned shr_clamp(unsigned v, unsigned s) {
 // the descending walk unless another live candidate shares its key bucket; then the exact double values decide (ties: higher
 // index first).  NPL words per lane live in registers; every round is one redux.max, the flag update of the suppressed range
 // (lane w keeps the flag bits of rel 32 w .. 32 w + 31) and a range kill.  Returns the pick count (<= 21).
+// Flag bits of the picks made so far (:128-145), all at once: lane l < 20 ORs the suppressed range of pick l into the sector's
+// flag words in shared memory, lane 20 the position of a 21st pick; lane w gets back the word of rel 32 w .. 32 w + 31.
+__device__ __forceinline__ unsigned pick_flags(const uint16_t* srng, unsigned* sflagw, int cnt, int myedge, int lane) {
+    if (lane < cnt) {
+        unsigned rlo = (unsigned)myedge, m11 = 1u;
+        if (lane < kEdgePerSector) {
+            const unsigned rs = srng[myedge];
+            rlo = rs & 511u;
+            m11 = (2u << (rs >> 9)) - 1u;
+        }
+        const unsigned sh = rlo & 31u;
+        atomicOr(&sflagw[rlo >> 5], m11 << sh);
+        if (sh > 21u) atomicOr(&sflagw[(rlo >> 5) + 1], m11 >> (32u - sh));     // 11 bits at most: spills over from bit 22 on
+    }
+    __syncwarp();
+    return lane < 16 ? sflagw[lane] : 0u;
+}
+
 template <int NPL>
-__device__ __forceinline__ int sector_pick(unsigned* scand, int C, const unsigned* slink, uint16_t* srng, int Ls, int lane,
-                                           unsigned& flagw, int& myedge) {
+__device__ __forceinline__ int sector_pick(unsigned* scand, int C, const unsigned* slink, uint16_t* srng, unsigned* sflagw, int Ls,
+                                           int lane, unsigned& flagw, int& myedge) {
     unsigned word[NPL];
 #pragma unroll
     for (int k = 0; k < NPL; ++k) word[k] = (k * 32 + lane < C) ? scand[k * 32 + lane] : 0u;
@@ -330,7 +351,6 @@ __device__ __forceinline__ int sector_pick(unsigned* scand, int C, const unsigne
         for (int l = k + 1; l < NPL; ++l) dup |= (word[k] != 0u) && ((word[k] ^ word[l]) >> 9) == 0u;
     const bool anydup = __any_sync(kFull, dup);
     __syncwarp();
-    const int wbase = lane * 32;
     int cnt = 0;
     while (true) {
         unsigned m = word[0];
@@ -343,26 +363,22 @@ __device__ __forceinline__ int sector_pick(unsigned* scand, int C, const unsigne
         const int rel = (int)(M & 511u);
         if ((top & (top - 1u)) != 0u || (anydup && __any_sync(kFull, dup && (m >> 9) == bucket))) {
             // two live candidates share the top bucket: hand the live words back and let the exact (slow) walk finish the sector
+            flagw = pick_flags(srng, sflagw, cnt, myedge, lane);
 #pragma unroll
             for (int k = 0; k < NPL; ++k) scand[k * 32 + lane] = word[k];
             __syncwarp();
             return -1 - cnt;
         }
         cnt++;                                                                      // :118-119
-        if (cnt > kEdgePerSector) {                                                 // :121-126 the 21st is picked, not emitted
-            if ((rel >> 5) == lane) flagw |= 1u << (rel & 31);
-            break;
-        }
-        if (lane == cnt - 1) myedge = rel;
+        if (lane == cnt - 1) myedge = rel;                                          // lane l keeps the l-th pick
+        if (cnt > kEdgePerSector) break;                                            // :121-126 the 21st is picked, not emitted
         const unsigned rs = srng[rel];
         const unsigned rlo = rs & 511u, span = rs >> 9;
-        const unsigned m11 = (2u << span) - 1u;
-        const int sh = (int)rlo - wbase;
-        flagw |= shl_clamp(m11, (unsigned)sh) | shr_clamp(m11, (unsigned)(-sh));
 #pragma unroll
         for (int k = 0; k < NPL; ++k)
             if ((word[k] & 511u) - rlo <= span) word[k] = 0u;
     }
+    flagw = pick_flags(srng, sflagw, cnt, myedge, lane);
     return cnt;
 }
 
@@ -431,7 +447,8 @@ __global__ void __launch_bounds__(kSecWarps * 32, 14) k_sector_extract(ExtractPa
     unsigned* scand = reinterpret_cast<unsigned*>(sp + S + 16);          // [S] candidate words; once they sit in registers the
     uint16_t* srng = reinterpret_cast<uint16_t*>(scand);                 //     same bytes hold the suppressed range per position
     unsigned* slink = scand + S;                                         // [S / 32 + 2] link bits: bit q = short step q -> q+1
-    int* ssrc = reinterpret_cast<int*>(slink + S / 32 + 2);              // [S] source index (label output only)
+    unsigned* sflagw = slink + S / 32 + 2;                               // [18] flag bits of the sector (picked / suppressed)
+    int* ssrc = reinterpret_cast<int*>(sflagw + 18);                     // [S] source index (label output only)
 
     const unsigned epoch = *reinterpret_cast<volatile unsigned int*>(&P.ctrl[1]);
     const int nsec = P.batch * P.num_lines * kSectors;       // < 2^23 (host): the float division below is exact
@@ -500,7 +517,7 @@ __global__ void __launch_bounds__(kSecWarps * 32, 14) k_sector_extract(ExtractPa
                     }
                 }
             }
-            if (lane < S / 32 + 2) slink[lane] = 0u;
+            for (int i = lane; i < S / 32 + 2 + 18; i += 32) slink[i] = 0u;      // link bits and flag words
             cp_async_wait_all();
             __syncwarp();
 
@@ -589,9 +606,9 @@ __global__ void __launch_bounds__(kSecWarps * 32, 14) k_sector_extract(ExtractPa
 
             // D. greedy pick (:99-209)
             int cnt, cw = C;
-            if (C <= 64) { cnt = sector_pick<2>(scand, C, slink, srng, Ls, lane, flagw, myedge); cw = 64; }
-            else if (C <= 128) { cnt = sector_pick<4>(scand, C, slink, srng, Ls, lane, flagw, myedge); cw = 128; }
-            else if (C <= 256) { cnt = sector_pick<8>(scand, C, slink, srng, Ls, lane, flagw, myedge); cw = 256; }
+            if (C <= 64) { cnt = sector_pick<2>(scand, C, slink, srng, sflagw, Ls, lane, flagw, myedge); cw = 64; }
+            else if (C <= 128) { cnt = sector_pick<4>(scand, C, slink, srng, sflagw, Ls, lane, flagw, myedge); cw = 128; }
+            else if (C <= 256) { cnt = sector_pick<8>(scand, C, slink, srng, sflagw, Ls, lane, flagw, myedge); cw = 256; }
             else cnt = -1;
             if (cnt < 0) cnt = sector_pick_large(sp, scand, cw, slink, Ls, lane, flagw, myedge, -1 - cnt);
             ne = min(cnt, kEdgePerSector);
@@ -758,7 +775,20 @@ static int extract_launch(pf_extract* h, const float4* d_xyzi, const int* d_n, i
         P.stride = stride; P.tiles = tiles; P.edge_stride = edge_stride; P.batch = nb;
         P.num_lines = h->lidar.num_lines; P.rcap = h->rcap; P.scap = h->scap;
         P.min_d = h->lidar.min_distance; P.max_d = h->lidar.max_distance;
-        k_ring_classify<<<dim3(div_up(tiles, kClassifyThreads / 32), nb), kClassifyThreads, 0, h->stream>>>(P, h->gate_lo, h->gate_hi);
+        {
+            const dim3 grid(div_up(tiles, kClassifyThreads / 32), nb);
+            auto launch = [&](auto kern) { kern<<<grid, kClassifyThreads, 0, h->stream>>>(P, h->gate_lo, h->gate_hi); };
+            const int nl = h->lidar.num_lines;
+            if (d_label) {
+                if (nl == 64) launch(k_ring_classify<64, true>);
+                else if (nl == 32) launch(k_ring_classify<32, true>);
+                else launch(k_ring_classify<16, true>);
+            } else {
+                if (nl == 64) launch(k_ring_classify<64, false>);
+                else if (nl == 32) launch(k_ring_classify<32, false>);
+                else launch(k_ring_classify<16, false>);
+            }
+        }
         k_ring_index<<<div_up(nb * h->lidar.num_lines, 8), 256, 0, h->stream>>>(P);
         const int want = div_up(nb * h->lidar.num_lines * kSectors, kSecWarps);
         if (d_label) {
@@ -822,7 +852,7 @@ extern "C" int pf_extract_create(const pf_lidar_params* lidar, const pf_extract_
     // the register windows), candidate words, link bits, suppressed ranges (+ source indices for the label output)
     h->scap = div_up((h->rcap - 10) / kSectors + 14, 32) * 32;
     if (h->scap < 256) h->scap = 256;     // sector_pick hands up to 256 live words back through the candidate array
-    h->warp_smem = (h->scap + 16) * 16 + h->scap * 4 + (h->scap / 32 + 2) * 4;
+    h->warp_smem = (h->scap + 16) * 16 + h->scap * 4 + (h->scap / 32 + 2 + 18) * 4;
     h->warp_smem = div_up(h->warp_smem, 16) * 16;
     h->warp_smem_label = h->warp_smem + h->scap * 4;
     if ((size_t)kSecWarps * h->warp_smem_label > (size_t)prop.sharedMemPerBlockOptin) {
