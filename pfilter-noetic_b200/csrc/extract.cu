@@ -48,6 +48,8 @@ struct ExtractParams {
     uint8_t* tile_pure;       // [batch][tiles] ring id when the tile is a full tile of one ring, else 255
     int* tile_off;            // [batch][64][tiles + 1] ring positions at which the tiles of the ring's range start
     int4* ring_info;          // [batch][64] {first tile, tiles in range, points of the ring, -}
+    int4* sec_desc;           // [batch][64][6] {local points (0 = ring not processed), first ring position, first source index when
+                              //                 the sector is one contiguous run of the input (else -1), first tile of the range}
     uint8_t* label;           // [batch][stride] or null
     float4* edge;             // [batch][edge_stride]
     float4* surf;             // [batch][stride]
@@ -254,6 +256,28 @@ __global__ void __launch_bounds__(256) k_ring_index(ExtractParams P) {
     if (lane == 0) {
         off[ncand] = carry;
         P.ring_info[(size_t)s * kMaxLines + r] = make_int4(tlo, ncand, carry, 0);
+        if (carry > P.rcap) atomicOr(&P.ctrl[2], 1u);     // ring larger than the configured capacity
+    }
+    __syncwarp();
+    // sector descriptors (:81-92): lane k locates sector k in the tile range; when every tile it touches is a pure tile of this
+    // ring, its points are ONE contiguous run of the input and the extract kernel copies them without looking at any other table
+    if (lane < kSectors) {
+        const int nr = carry, k = lane;
+        int4 d = make_int4(0, 0, -1, 0);
+        if (nr >= 131 && nr <= P.rcap) {                  // :67
+            const int total = nr - 10, L = total / kSectors;
+            const int lo = L * k, hi = (k == kSectors - 1) ? total - 1 : lo + L - 1;   // hi excluded (:83-88)
+            const int n_loc = hi - lo + 10, p0 = lo, p1 = lo + n_loc;
+            int a = 0, b = ncand;                         // first tile with off[c + 1] > p0
+            while (a < b) {
+                const int m = (a + b) >> 1;
+                if (off[m + 1] <= p0) a = m + 1; else b = m;
+            }
+            bool contiguous = true;
+            for (int c = a; c < ncand && off[c] < p1; ++c) contiguous = contiguous && pure[tlo + c] == r;
+            d = make_int4(n_loc, p0, contiguous ? (tlo + a) * kTile + (p0 - off[a]) : -1, a);
+        }
+        P.sec_desc[((size_t)s * kMaxLines + r) * kSectors + k] = d;
     }
 }
 
@@ -455,6 +479,7 @@ __global__ void __launch_bounds__(kSecWarps * 32, 14) k_sector_extract(ExtractPa
     const float inv_batch = 1.0f / (float)P.batch;
     const unsigned lt = lanemask_lt();
 
+    // (tickets are NOT fetched ahead: a ticket held back by a busy warp starts late and everything behind it in the scan waits)
     while (true) {
         int ticket = 0;
         if (lane == 0) ticket = (int)atomicAdd(&P.ctrl[0], 1u);
@@ -462,58 +487,54 @@ __global__ void __launch_bounds__(kSecWarps * 32, 14) k_sector_extract(ExtractPa
         if (ticket >= nsec) break;
         const int rk = __float2int_rd(((float)ticket + 0.5f) * inv_batch), s = ticket - rk * P.batch;
         const int r = rk / kSectors, k = rk - r * kSectors;
-        const int4 info = P.ring_info[(size_t)s * kMaxLines + r];
-        const int tlo = info.x, ncand = info.y, nr = info.z;
-        bool active = nr >= 131;                                   // :67
-        if (nr > P.rcap) {
-            active = false;
-            if (lane == 0 && k == 0) atomicOr(&P.ctrl[2], 1u);     // ring larger than the configured capacity
-        }
-        int ne = 0, Ls = 0, myedge = 0;
+        const int4 desc = P.sec_desc[(size_t)(s * kMaxLines + r) * kSectors + k];
+        const int n_loc = desc.x;
+        const bool active = n_loc > 0;
+        const int Ls = active ? n_loc - 10 : 0;
+        int ne = 0, myedge = 0;
         unsigned flagw = 0u;
         if (active) {
-            const int total = nr - 10, L = total / kSectors;
-            const int lo = L * k, hi = (k == kSectors - 1) ? total - 1 : lo + L - 1;   // hi excluded (:83-88)
-            Ls = hi - lo;
-            const int n_loc = Ls + 10, p0 = lo, p1 = lo + n_loc;     // ring positions [p0, p1) = local [0, n_loc)
             const float4* pts = P.pts + (size_t)s * P.stride;
-            const uint8_t* rid = P.ringid + (size_t)s * P.stride;
-            const uint8_t* pure = P.tile_pure + (size_t)s * P.tiles;
-            const int* off = P.tile_off + ((size_t)s * kMaxLines + r) * (P.tiles + 1);
-
-            // A. first tile of the ring's range that reaches ring position p0
-            int c = 0;
-            for (int cb = 0; cb < ncand; cb += 32) {
-                const int cc = cb + lane;
-                const unsigned le = __ballot_sync(kFull, cc < ncand && off[cc + 1] <= p0);
-                c += __popc(le);
-                if (le != kFull) break;
-            }
-            // B. stable gather (:62)
-            for (; c < ncand; ++c) {
-                const int beg = off[c];
-                if (beg >= p1) break;
-                const int end = off[c + 1];
-                if (end == beg) continue;
-                const int tbase = (tlo + c) * kTile;
-                if (pure[tlo + c] == r) {
-                    const int ps = max(beg, p0), pe = min(end, p1);
-                    for (int pos = ps + lane; pos < pe; pos += 32) {
-                        cp_async_16(sp + (pos - p0), pts + tbase + (pos - beg));
-                        if (kLabel) ssrc[pos - p0] = tbase + (pos - beg);
-                    }
-                } else {
-                    int run = beg;
-                    for (int row = 0; row < kTile / 32 && run < p1; ++row) {
-                        const int i = tbase + row * 32 + lane;
-                        const bool mt = rid[i] == r;
-                        const unsigned mm = __ballot_sync(kFull, mt);
-                        const int pos = run + __popc(mm & lt);
-                        if (mt && pos >= p0 && pos < p1) {
-                            cp_async_16(sp + (pos - p0), pts + i);
-                            if (kLabel) ssrc[pos - p0] = i;
+            if (desc.z >= 0) {
+                // A. ring-major input: the sector is one contiguous run of the scan
+                const float4* src = pts + desc.z;
+                for (int q = lane; q < n_loc; q += 32) {
+                    cp_async_16(sp + q, src + q);
+                    if (kLabel) ssrc[q] = desc.z + q;
+                }
+            } else {
+                // B. general order: stable gather (:62) from the ring's tile range, tile by tile
+                const int p0 = desc.y, p1 = p0 + n_loc;
+                const int4 info = P.ring_info[(size_t)s * kMaxLines + r];
+                const int tlo = info.x, ncand = info.y;
+                const uint8_t* rid = P.ringid + (size_t)s * P.stride;
+                const uint8_t* pure = P.tile_pure + (size_t)s * P.tiles;
+                const int* off = P.tile_off + ((size_t)s * kMaxLines + r) * (P.tiles + 1);
+                for (int c = desc.w; c < ncand; ++c) {
+                    const int beg = off[c];
+                    if (beg >= p1) break;
+                    const int end = off[c + 1];
+                    if (end == beg) continue;
+                    const int tbase = (tlo + c) * kTile;
+                    if (pure[tlo + c] == r) {
+                        const int ps = max(beg, p0), pe = min(end, p1);
+                        for (int pos = ps + lane; pos < pe; pos += 32) {
+                            cp_async_16(sp + (pos - p0), pts + tbase + (pos - beg));
+                            if (kLabel) ssrc[pos - p0] = tbase + (pos - beg);
                         }
-                        run += __popc(mm);
+                    } else {
+                        int run = beg;
+                        for (int row = 0; row < kTile / 32 && run < p1; ++row) {
+                            const int i = tbase + row * 32 + lane;
+                            const bool mt = rid[i] == r;
+                            const unsigned mm = __ballot_sync(kFull, mt);
+                            const int pos = run + __popc(mm & lt);
+                            if (mt && pos >= p0 && pos < p1) {
+                                cp_async_16(sp + (pos - p0), pts + i);
+                                if (kLabel) ssrc[pos - p0] = i;
+                            }
+                            run += __popc(mm);
+                        }
                     }
                 }
             }
@@ -720,6 +741,7 @@ struct pf_extract {
     uint8_t* d_tile_pure = nullptr;
     int* d_tile_off = nullptr;
     int4* d_ring_info = nullptr;
+    int4* d_sec_desc = nullptr;
     float gate_lo = 0, gate_hi = 0;
     uint8_t* d_label = nullptr;
     float4* d_edge = nullptr;
@@ -769,6 +791,7 @@ static int extract_launch(pf_extract* h, const float4* d_xyzi, const int* d_n, i
         P.n_surf = d_n_surf + s0;
         P.tile_off = h->d_tile_off + (size_t)s0 * kMaxLines * (h->tiles + 1);
         P.ring_info = h->d_ring_info + (size_t)s0 * kMaxLines;
+        P.sec_desc = h->d_sec_desc + (size_t)s0 * kMaxLines * kSectors;
         P.done_sec = h->d_done_sec + (size_t)s0 * kMaxLines * kSectors;
         P.done_ring = h->d_done_ring + (size_t)s0 * kMaxLines;
         P.ctrl = h->d_ctrl;
@@ -910,6 +933,7 @@ extern "C" int pf_extract_create(const pf_lidar_params* lidar, const pf_extract_
     PF_CUDA(cudaMalloc(&h->d_n_surf, sizeof(int) * h->max_batch));
     PF_CUDA(cudaMalloc(&h->d_tile_off, sizeof(int) * (size_t)h->max_batch * kMaxLines * (h->tiles + 1)));
     PF_CUDA(cudaMalloc(&h->d_ring_info, sizeof(int4) * (size_t)h->max_batch * kMaxLines));
+    PF_CUDA(cudaMalloc(&h->d_sec_desc, sizeof(int4) * (size_t)h->max_batch * kMaxLines * kSectors));
     PF_CUDA(cudaMalloc(&h->d_done_sec, sizeof(unsigned long long) * h->max_batch * kMaxLines * kSectors));
     PF_CUDA(cudaMalloc(&h->d_done_ring, sizeof(unsigned long long) * h->max_batch * kMaxLines));
     PF_CUDA(cudaMalloc(&h->d_ctrl, sizeof(unsigned) * 4));
@@ -928,7 +952,7 @@ extern "C" int pf_extract_destroy(pf_extract* h) {
     cudaStreamSynchronize(h->stream);
     cudaFree(h->d_pts); cudaFree(h->d_ringid); cudaFree(h->d_ring_tiles); cudaFree(h->d_tile_pure); cudaFree(h->d_label); cudaFree(h->d_edge);
     cudaFree(h->d_surf); cudaFree(h->d_n); cudaFree(h->d_n_edge); cudaFree(h->d_n_surf); cudaFree(h->d_done_sec);
-    cudaFree(h->d_done_ring); cudaFree(h->d_tile_off); cudaFree(h->d_ring_info);
+    cudaFree(h->d_done_ring); cudaFree(h->d_tile_off); cudaFree(h->d_ring_info); cudaFree(h->d_sec_desc);
     cudaFree(h->d_edge1); cudaFree(h->d_surf1); cudaFree(h->d_cnt1);
     cudaFree(h->d_ctrl);
     cudaFreeHost(h->h_counts); cudaFreeHost(h->h_ctrl);
