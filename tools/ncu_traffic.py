@@ -21,7 +21,7 @@ def kernels(rep):
             v = float(d[name].replace(",", ""))
             u = units[hdr.index(name)]
             return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
-        res.append({"kernel": d["Kernel Name"].split("(")[0].split("::")[-1], "dram_read": val("dram__bytes_read.sum"),
+        res.append({"kernel": d["Kernel Name"].split("(")[0].split("<")[0].split("::")[-1].replace("void ", "").strip(), "dram_read": val("dram__bytes_read.sum"),
                     "dram_write": val("dram__bytes_write.sum"), "time_us": float(d["gpu__time_duration.sum"].replace(",", "")) / (1e3 if units[hdr.index("gpu__time_duration.sum")] in ("ns", "nsecond") else 1),
                     "l2_hit_pct": float(d["lts__t_sector_hit_rate.pct"])})
     return res
@@ -34,9 +34,12 @@ def first(ks, name):
 k1, k9, k4 = kernels(sys.argv[1]), kernels(sys.argv[2]), kernels(sys.argv[3])
 out = {"source": [os.path.basename(a) for a in sys.argv[1:4]],
        "note": "ncu --set full --clock-control none; caches flushed before every kernel, so re-reads that hit L2 in the real pipeline show up as DRAM here"}
-c, e = first(k1, "k_ring_classify"), first(k1, "k_ring_extract")
-out["k1"] = {"classify": c, "extract": e, "bytes_per_launch_group": c["dram_read"] + c["dram_write"] + e["dram_read"] + e["dram_write"],
-             "share_of_group_time": {"k_ring_classify": c["time_us"] / (c["time_us"] + e["time_us"]), "k_ring_extract": e["time_us"] / (c["time_us"] + e["time_us"])}}
+c, x, e = first(k1, "k_ring_classify"), first(k1, "k_ring_index"), first(k1, "k_sector_extract")
+t_all = c["time_us"] + x["time_us"] + e["time_us"]
+out["k1"] = {"classify": c, "index": x, "extract": e,
+             "bytes_per_launch_group": sum(k["dram_read"] + k["dram_write"] for k in (c, x, e)),
+             "share_of_group_time": {"k_ring_classify": c["time_us"] / t_all, "k_ring_index": x["time_us"] / t_all,
+                                     "k_sector_extract": e["time_us"] / t_all}}
 a, b = first(k9, "k_mm_count"), first(k9, "k_mm_write")
 out["k9"] = {"count": a, "write": b, "bytes_per_update": a["dram_read"] + a["dram_write"] + b["dram_read"] + b["dram_write"]}
 q = first(k4, "k_knn5_tap")
