@@ -174,6 +174,12 @@ struct pf_odom {
     int npairs = 1;
     int pair[2][2] = {{0, 1}, {0, 0}};   // [pair] = {line-type kind, plane-type kind}; the null kind (kKinds - 1) stands in for "none"
     Workspace ws;
+    // the search grids over the current maps do not depend on this frame's features: they are built on a second stream (own
+    // workspace), forked at the start of the update and joined before the first association pass (PF_ODOM_FORK=0: in line)
+    Workspace ws_grid;
+    cudaStream_t stream_grid = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    bool fork_grid = true;
     float4* d_feat[kKinds] = {};
     int* d_nfeat = nullptr;              // [kKinds]
     Pt* d_ds[kKinds] = {};
@@ -237,6 +243,7 @@ constexpr int kNull = kKinds - 1;
 int odom_alloc(pf_odom* h) {
     const int fcap = h->fcap, bufcap = h->bufcap;
     PF_CHECK(workspace_create(h->ws, 2 * bufcap, h->stream));
+    PF_CHECK(workspace_create(h->ws_grid, 2 * bufcap, h->stream_grid));
     PF_CUDA(cudaMalloc(&h->d_nfeat, sizeof(int) * kKinds));
     PF_CUDA(cudaMalloc(&h->d_nds, sizeof(int) * kKinds));
     PF_CUDA(cudaMemset(h->d_nfeat, 0, sizeof(int) * kKinds));
@@ -381,6 +388,28 @@ int record_update(pf_odom* h, const float4* const feat[kKinds], const int* const
         k_predict<<<1, 32, 0, h->stream>>>(h->d_sh, h->d_state, G);
         ws.launches += 1;
     }
+    // search grids over the current maps: forked onto the second stream (captured as a parallel branch of the graph)
+    auto grids = [&](Workspace& gw) -> int {
+        for (int p = 0; p < h->npairs; ++p) {
+            if (p > 0 || &gw != &ws) PF_CHECK(workspace_begin_step(gw));      // the second pair reuses the tickets and state slots
+            GridBuild G{};
+            for (int j = 0; j < 2; ++j) {
+                const int k = h->pair[p][j];
+                G.map[j] = h->d_map[cur][k]; G.n_map[j] = h->d_nmap[cur] + k; G.pts[j] = h->d_gpts[k];
+                G.cell_start[j] = h->d_cs[k]; G.cell_end[j] = h->d_ce[k]; G.geom[j] = h->d_geom + 6 * k;
+            }
+            PF_CHECK(build_grids(gw, G, 2, mub[h->pair[p][0]], mub[h->pair[p][1]]));
+        }
+        return PF_OK;
+    };
+    if (h->fork_grid) {
+        PF_CUDA(cudaEventRecord(h->ev_fork, h->stream));
+        PF_CUDA(cudaStreamWaitEvent(h->stream_grid, h->ev_fork, 0));
+        const uint64_t l0 = h->ws_grid.launches;
+        PF_CHECK(grids(h->ws_grid));
+        ws.launches += h->ws_grid.launches - l0;
+        PF_CUDA(cudaEventRecord(h->ev_join, h->stream_grid));
+    }
     // VoxelGrid down-sampling, leaf sizes as set by init (:189-190): setLeafSize takes floats
     for (int p = 0; p < h->npairs; ++p) {
         VoxParams V{};
@@ -393,17 +422,8 @@ int record_update(pf_odom* h, const float4* const feat[kKinds], const int* const
         PF_CHECK(voxelize(ws, V, p, ub[h->pair[p][0]], ub[h->pair[p][1]]));
     }
     mark(1);
-    // search grids over the current maps
-    for (int p = 0; p < h->npairs; ++p) {
-        if (p > 0) PF_CHECK(workspace_begin_step(ws));      // the second pair reuses the tickets and state slots
-        GridBuild G{};
-        for (int j = 0; j < 2; ++j) {
-            const int k = h->pair[p][j];
-            G.map[j] = h->d_map[cur][k]; G.n_map[j] = h->d_nmap[cur] + k; G.pts[j] = h->d_gpts[k];
-            G.cell_start[j] = h->d_cs[k]; G.cell_end[j] = h->d_ce[k]; G.geom[j] = h->d_geom + 6 * k;
-        }
-        PF_CHECK(build_grids(ws, G, 2, mub[h->pair[p][0]], mub[h->pair[p][1]]));
-    }
+    if (h->fork_grid) PF_CUDA(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
+    else PF_CHECK(grids(ws));
     mark(2);
     // optimisation passes
     AssocParams A[2]{};
@@ -614,6 +634,10 @@ int odom_create(const pf_odom_params* p, int device, bool bpf, pf_odom** out) {
     if (h->mcap < h->fcap) h->mcap = h->fcap;   // the raw first-frame clouds become the maps (:217-222)
     h->bufcap = h->mcap + h->fcap;
     PF_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    PF_CUDA(cudaStreamCreateWithFlags(&h->stream_grid, cudaStreamNonBlocking));
+    PF_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+    PF_CUDA(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+    { const char* e = getenv("PF_ODOM_FORK"); if (e && atoi(e) == 0) h->fork_grid = false; }
     PF_CUDA(cudaEventCreateWithFlags(&h->ev, cudaEventDisableTiming));
     for (int b = 0; b < 2; ++b) PF_CUDA(cudaEventCreateWithFlags(&h->ev_done[b], cudaEventDisableTiming));
     int rc = odom_alloc(h);
@@ -633,6 +657,10 @@ extern "C" int pf_odom_destroy(pf_odom* h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     for (int b = 0; b < 2; ++b) if (h->graph_exec[b]) cudaGraphExecDestroy(h->graph_exec[b]);
     workspace_destroy(h->ws);
+    workspace_destroy(h->ws_grid);
+    if (h->stream_grid) cudaStreamDestroy(h->stream_grid);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
     map_merge_scratch_destroy(h->msc);
     cudaFree(h->d_nfeat); cudaFree(h->d_nds); cudaFree(h->d_geom); cudaFree(h->d_nmap[0]); cudaFree(h->d_nmap[1]);
     for (int k = 0; k < kKinds; ++k) {
