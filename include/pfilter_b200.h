@@ -62,7 +62,9 @@ typedef struct pf_extract pf_extract;
 typedef struct pf_extract_config {
     int32_t max_points;        /* capacity per scan (points); rounded up to a multiple of 256 */
     int32_t max_batch;         /* scans per batched launch */
-    int32_t max_ring_points;   /* capacity of one ring (points staged in shared memory); 0 = default 2560 */
+    int32_t max_ring_points;   /* capacity of one ring; sizes the per-warp shared memory (a sector of the ring) and so the
+                                  occupancy of the extract kernel: set it to the sensor's points per ring plus a margin;
+                                  0 = default 2304, maximum 3040 */
 } pf_extract_config;
 
 /* LaserProcessingClass::init, src/laserProcessingClass.cpp:4-8 */

@@ -24,6 +24,7 @@
 // k_sector_extract hits L2 when the batch fits there.
 #include <math.h>
 
+#include <algorithm>
 #include <vector>
 
 #include "common.cuh"
@@ -131,19 +132,28 @@ __device__ __forceinline__ int ring_id_fast_t(float t) {
 // fp32 fast path on top of one MUFU.RSQ: dist = s * rsqrt(s) and z / dist = z * rsqrt(s) are good to ~3 ulp; the range gate is
 // pulled in by 1e-6 relative so that the approximate distance can never decide a point the reference's (double)sqrtf comparison
 // would not.
+// (blo, bhi): band of t = tan(elevation) that lies strictly inside the ring r0 of the lane's first point (c_ring_band): the other
+// seven points of the lane are in the same ring in ring-major input, and two compares confirm it without the polynomial.
 template <int LINES>
-__device__ __forceinline__ int ring_id_dev(float x, float y, float z, double min_d, double max_d, float gate_lo, float gate_hi) {
+__device__ __forceinline__ int ring_id_dev(float x, float y, float z, double min_d, double max_d, float gate_lo, float gate_hi,
+                                           float blo, float bhi, int r0) {
     const float s = __fmaf_rn(x, x, __fmul_rn(y, y));
     const float r = rsqrtf(s);
     const float dist = __fmul_rn(s, r);
-    int id = ring_id_fast_t<LINES>(__fmul_rn(z, r));
-    if (!(dist > gate_lo && dist < gate_hi && fabsf(z) < 3.0e38f)) id = -1;
+    const float t = __fmul_rn(z, r);
+    const bool gate_ok = dist > gate_lo && dist < gate_hi && fabsf(z) < 3.0e38f;
+    if (gate_ok && t > blo && t < bhi) return r0;
+    int id = gate_ok ? ring_id_fast_t<LINES>(t) : -1;
     if (id < 0) {
         if (!(isfinite(x) && isfinite(y) && isfinite(z))) return 255;   // x86 int(NaN) = INT_MIN: the reference drops these
         id = ring_id_exact(x, y, z, LINES, min_d, max_d);
     }
     return id;
 }
+
+// [ring][0 / 1]: tan of the ring's elevation interval pulled in by 1e-3 degrees on either side (host: ring_band_table), for the
+// sensor of the handle that launched last on this device (all handles of one sensor type share it)
+__constant__ float c_ring_band[3][kMaxLines][2];
 
 // One warp per 256-point tile (8 coalesced 512-byte rows, all loads in flight before the first use): ring id byte per point,
 // and the tile summary (one ring only -> "pure"; else the set of rings present) from registers and warp votes alone.
@@ -165,11 +175,14 @@ __global__ void __launch_bounds__(kClassifyThreads) k_ring_classify(ExtractParam
     for (int k = 0; k < R; ++k)
         if (i0 + 32 * k < n) p[k] = ld_stream_f4(P.pts + g + 32 * k);
     int ring[R];
+    constexpr int kCfg = LINES == 64 ? 2 : LINES == 32 ? 1 : 0;
+    float blo = 2.0f, bhi = -2.0f;       // empty band: the first point always takes the full path
 #pragma unroll
     for (int k = 0; k < R; ++k) {
         ring[k] = 255;
         if (i0 + 32 * k < n) {
-            ring[k] = ring_id_dev<LINES>(p[k].x, p[k].y, p[k].z, P.min_d, P.max_d, gate_lo, gate_hi);
+            ring[k] = ring_id_dev<LINES>(p[k].x, p[k].y, p[k].z, P.min_d, P.max_d, gate_lo, gate_hi, blo, bhi, ring[0]);
+            if (k == 0 && ring[0] < LINES) { blo = c_ring_band[kCfg][ring[0]][0]; bhi = c_ring_band[kCfg][ring[0]][1]; }
             if (kLabel) P.label[g + 32 * k] = 0;
         }
         P.ringid[g + 32 * k] = (uint8_t)ring[k];
@@ -770,6 +783,60 @@ struct pf_extract {
 
 namespace pf {
 
+// ring id of an elevation angle in degrees, the reference's arithmetic (src/laserProcessingClass.cpp:30-61) in double
+static int ring_of_angle(double angle, int num_lines) {
+    int id;
+    if (num_lines == 64) {
+        if (angle >= -8.83) id = (int)((2 - angle) * 3.0 + 0.5);
+        else id = 32 + (int)((-8.83 - angle) * 2.0 + 0.5);
+        if (angle > 2 || angle < -24.33 || id > 63 || id < 0) return -1;
+    } else if (num_lines == 32) {
+        id = (int)((angle + 92.0 / 3.0) * 3.0 / 4.0);
+        if (id > 31 || id < 0) return -1;
+    } else {
+        id = (int)((angle + 15) / 2 + 0.5);
+        if (id > 15 || id < 0) return -1;
+    }
+    return id;
+}
+
+// For every ring the interval of tan(elevation) that maps to it, pulled in by 1e-3 degrees (fifty times the fp32 error of the
+// kernel's t): all decision angles (integer bin positions of either block, the validity gates, the block split) are collected,
+// the ring between two neighbours is the ring of their midpoint, adjacent intervals of one ring are merged.
+static void ring_band_table(int num_lines, float band[kMaxLines][2]) {
+    std::vector<double> cut;
+    for (int k = -2; k <= 66; ++k) {
+        if (num_lines == 64) { cut.push_back(2.0 - (k - 0.5) / 3.0); cut.push_back(-8.83 - (k - 0.5) / 2.0); }
+        else if (num_lines == 32) cut.push_back(k * 4.0 / 3.0 - 92.0 / 3.0);
+        else cut.push_back((k - 0.5) * 2.0 - 15.0);
+    }
+    if (num_lines == 64) { cut.push_back(2.0); cut.push_back(-24.33); cut.push_back(-8.83); }
+    std::sort(cut.begin(), cut.end());
+    double lo[kMaxLines], hi[kMaxLines];
+    bool seen[kMaxLines], closed[kMaxLines];
+    for (int r = 0; r < kMaxLines; ++r) { seen[r] = closed[r] = false; lo[r] = hi[r] = 0; }
+    int prev = -1;
+    for (size_t i = 0; i + 1 < cut.size(); ++i) {
+        if (!(cut[i + 1] > cut[i])) continue;
+        const int r = ring_of_angle(0.5 * (cut[i] + cut[i + 1]), num_lines);
+        if (r >= 0) {
+            if (!seen[r]) { seen[r] = true; lo[r] = cut[i]; hi[r] = cut[i + 1]; }
+            else if (prev == r && !closed[r]) hi[r] = cut[i + 1];
+            else closed[r] = true;                 // a second, separate interval of the same ring: keep the first only
+        }
+        if (prev >= 0 && prev != r) closed[prev] = true;
+        prev = r;
+    }
+    const double kMargin = 1e-3, kRad = 3.14159265358979323846 / 180.0;
+    for (int r = 0; r < kMaxLines; ++r) {
+        band[r][0] = 2.0f; band[r][1] = -2.0f;
+        if (r < num_lines && seen[r] && hi[r] - lo[r] > 4 * kMargin) {
+            band[r][0] = (float)tan((lo[r] + kMargin) * kRad);
+            band[r][1] = (float)tan((hi[r] - kMargin) * kRad);
+        }
+    }
+}
+
 static int extract_launch(pf_extract* h, const float4* d_xyzi, const int* d_n, int batch, int stride, float4* d_edge,
                           int* d_n_edge, int edge_stride, float4* d_surf, int* d_n_surf, uint8_t* d_label) {
     PF_REQUIRE(stride % kTile == 0 && stride <= h->stride, "stride %d must be a multiple of %d and <= %d", stride, kTile, h->stride);
@@ -913,6 +980,12 @@ extern "C" int pf_extract_create(const pf_lidar_params* lidar, const pf_extract_
         h->group = g < 1 ? 1 : g;
     }
     PF_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    {
+        float band[kMaxLines][2];
+        ring_band_table(lidar->num_lines, band);
+        const int cfg_idx = lidar->num_lines == 64 ? 2 : lidar->num_lines == 32 ? 1 : 0;
+        PF_CUDA(cudaMemcpyToSymbol(c_ring_band, band, sizeof(band), sizeof(band) * cfg_idx));
+    }
     const size_t np = (size_t)h->max_batch * h->stride;
     PF_CUDA(cudaMalloc(&h->d_pts, np * 16));
     PF_CUDA(cudaMalloc(&h->d_ringid, np));

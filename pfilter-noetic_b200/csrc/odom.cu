@@ -182,8 +182,15 @@ struct pf_odom {
     bool fork_grid = true;
     float4* d_feat[kKinds] = {};
     int* d_nfeat = nullptr;              // [kKinds]
-    Pt* d_ds[kKinds] = {};
-    int* d_nds = nullptr;                // [kKinds]
+    Pt* d_ds[2][kKinds] = {};            // down-sampled feature clouds, double buffered like the maps (slot = map buffer of the update)
+    int* d_nds[2] = {nullptr, nullptr};  // [slot] -> [kKinds]
+    // The VoxelGrid down-sampling of a frame needs its features only, not the map: it runs on its own stream / workspace, so the
+    // down-sampling of frame k+1 overlaps the pose solve and map update of frame k (PF_ODOM_OVERLAP=0 or timing taps: in line)
+    Workspace ws_ds;
+    cudaStream_t stream_ds = nullptr;
+    cudaEvent_t ev_ds_done[2] = {nullptr, nullptr}, ev_upd_done[2] = {nullptr, nullptr}, ev_feat = nullptr;
+    bool ev_upd_set[2] = {false, false};
+    bool overlap_ds = true;
     Pt* d_map[2][kKinds] = {};           // [buffer][kind]
     int* d_nmap[2] = {nullptr, nullptr}; // [buffer] -> 2 * kKinds ints: n_map[kind], then n_sorted[kind] (merge.cuh: sorted prefix)
     MapMergeScratch msc{};
@@ -245,9 +252,12 @@ int odom_alloc(pf_odom* h) {
     PF_CHECK(workspace_create(h->ws, 2 * bufcap, h->stream));
     PF_CHECK(workspace_create(h->ws_grid, 2 * bufcap, h->stream_grid));
     PF_CUDA(cudaMalloc(&h->d_nfeat, sizeof(int) * kKinds));
-    PF_CUDA(cudaMalloc(&h->d_nds, sizeof(int) * kKinds));
+    PF_CHECK(workspace_create(h->ws_ds, 2 * fcap, h->stream_ds));
+    for (int b = 0; b < 2; ++b) {
+        PF_CUDA(cudaMalloc(&h->d_nds[b], sizeof(int) * kKinds));
+        PF_CUDA(cudaMemset(h->d_nds[b], 0, sizeof(int) * kKinds));
+    }
     PF_CUDA(cudaMemset(h->d_nfeat, 0, sizeof(int) * kKinds));
-    PF_CUDA(cudaMemset(h->d_nds, 0, sizeof(int) * kKinds));
     PF_CUDA(cudaMalloc(&h->d_geom, sizeof(int) * 6 * kKinds));
     for (int b = 0; b < 2; ++b) {
         PF_CUDA(cudaMalloc(&h->d_nmap[b], sizeof(int) * 2 * kKinds));
@@ -257,7 +267,7 @@ int odom_alloc(pf_odom* h) {
         if (k >= h->nk && k != kNull) continue;
         const int fc = k == kNull ? 16 : fcap, bc = k == kNull ? 16 : bufcap;
         PF_CUDA(cudaMalloc(&h->d_feat[k], sizeof(float4) * fc));
-        PF_CUDA(cudaMalloc(&h->d_ds[k], sizeof(Pt) * fc));
+        for (int b = 0; b < 2; ++b) PF_CUDA(cudaMalloc(&h->d_ds[b][k], sizeof(Pt) * fc));
         for (int b = 0; b < 2; ++b) PF_CUDA(cudaMalloc(&h->d_map[b][k], sizeof(Pt) * bc));
         PF_CUDA(cudaMalloc(&h->d_gpts[k], sizeof(float4) * bc));
         const size_t cells = k == kNull ? 16 : (size_t)kGridCellCap;
@@ -292,6 +302,7 @@ int odom_alloc(pf_odom* h) {
     PF_CUDA(cudaMallocHost(&h->h_ring, sizeof(OdomShared) * pf_odom::kRing));
     h->timing = getenv("PF_ODOM_TIMING") != nullptr;
     { const char* g = getenv("PF_ODOM_GRAPH"); h->use_graph = !(g && g[0] == '0') && !h->timing; }
+    { const char* g = getenv("PF_ODOM_OVERLAP"); h->overlap_ds = !(g && g[0] == '0') && !h->timing; }
     if (h->timing) for (int i = 0; i < 8; ++i) PF_CUDA(cudaEventCreate(&h->tev[i]));
     for (int i = 0; i < pf_odom::kRing; ++i) PF_CUDA(cudaEventCreateWithFlags(&h->ring_ev[i], cudaEventDisableTiming));
     k_odom_reset<<<1, 32, 0, h->stream>>>(h->d_sh, h->d_state);
@@ -372,6 +383,22 @@ int enqueue_init(pf_odom* h, const float4* const feat[kKinds], const int* const 
     return PF_OK;
 }
 
+// VoxelGrid down-sampling of the frame's feature clouds into slot `slot`, leaf sizes as set by init (:189-190): setLeafSize takes
+// floats.  Enqueued on the workspace's stream.
+int record_downsample(pf_odom* h, Workspace& w, const float4* const feat[kKinds], const int* const n_feat[kKinds], const int ub[kKinds], int slot) {
+    for (int p = 0; p < h->npairs; ++p) {
+        VoxParams V{};
+        V.mode = VOX_PCL;
+        for (int j = 0; j < 2; ++j) {
+            const int k = h->pair[p][j];
+            V.c[j] = VoxCloud{reinterpret_cast<const Pt*>(feat[k]), n_feat[k], h->d_ds[slot][k], h->d_nds[slot] + k,
+                              (float)(h->prm.map_resolution * h->leaf_mul[k]), 1};
+        }
+        PF_CHECK(voxelize(w, V, p, ub[h->pair[p][0]], ub[h->pair[p][1]]));
+    }
+    return PF_OK;
+}
+
 // The launch sequence of one update, enqueued on h->stream (directly, or into a stream capture).  ub / mub: upper bounds of the
 // feature and map counts (launch geometry only: every kernel is grid-stride or persistent and reads the exact device counts).
 int record_update(pf_odom* h, const float4* const feat[kKinds], const int* const n_feat[kKinds], const int ub[kKinds], const int mub[kKinds],
@@ -410,17 +437,7 @@ int record_update(pf_odom* h, const float4* const feat[kKinds], const int* const
         ws.launches += h->ws_grid.launches - l0;
         PF_CUDA(cudaEventRecord(h->ev_join, h->stream_grid));
     }
-    // VoxelGrid down-sampling, leaf sizes as set by init (:189-190): setLeafSize takes floats
-    for (int p = 0; p < h->npairs; ++p) {
-        VoxParams V{};
-        V.mode = VOX_PCL;
-        for (int j = 0; j < 2; ++j) {
-            const int k = h->pair[p][j];
-            V.c[j] = VoxCloud{reinterpret_cast<const Pt*>(feat[k]), n_feat[k], h->d_ds[k], h->d_nds + k,
-                              (float)(h->prm.map_resolution * h->leaf_mul[k]), 1};
-        }
-        PF_CHECK(voxelize(ws, V, p, ub[h->pair[p][0]], ub[h->pair[p][1]]));
-    }
+    if (!h->overlap_ds) PF_CHECK(record_downsample(h, ws, feat, n_feat, ub, cur));
     mark(1);
     if (h->fork_grid) PF_CUDA(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
     else PF_CHECK(grids(ws));
@@ -431,7 +448,7 @@ int record_update(pf_odom* h, const float4* const feat[kKinds], const int* const
     for (int p = 0; p < h->npairs; ++p) {
         for (int j = 0; j < 2; ++j) {
             const int k = h->pair[p][j];
-            A[p].c[j] = AssocCloud{h->d_ds[k], h->d_nds + k, h->d_map[cur][k], h->d_nmap[cur] + k,
+            A[p].c[j] = AssocCloud{h->d_ds[cur][k], h->d_nds[cur] + k, h->d_map[cur][k], h->d_nmap[cur] + k,
                                    KnnGrid{h->d_gpts[k], h->d_cs[k], h->d_ce[k], h->d_geom + 6 * k},
                                    h->d_head[k], h->d_hits[k], h->d_next[k], h->d_nn[k], h->d_flag[k], h->d_g8[k], h->d_wobs[k], h->d_wspa[k]};
         }
@@ -449,7 +466,7 @@ int record_update(pf_odom* h, const float4* const feat[kKinds], const int* const
         for (int p = 0; p < h->npairs; ++p)
             for (int j = 0; j < 2; ++j)
                 if (h->pair[p][j] == k) { pp = p; jj = j; }
-        L.src[k] = ResidualSrc{h->type[k], h->d_ds[k], nullptr, h->d_flag[k], h->d_g8[k], h->d_nds + k, h->d_wobs[k], h->d_wspa[k],
+        L.src[k] = ResidualSrc{h->type[k], h->d_ds[cur][k], nullptr, h->d_flag[k], h->d_g8[k], h->d_nds[cur] + k, h->d_wobs[k], h->d_wspa[k],
                                h->d_wminmax + 8 * pp + 4 * jj};
         ub_src[k] = ub[k];
     }
@@ -468,7 +485,7 @@ int record_update(pf_odom* h, const float4* const feat[kKinds], const int* const
         AppendParams P{};
         for (int j = 0; j < 2; ++j) {
             const int k = h->pair[p][j];
-            P.ds[j] = h->d_ds[k]; P.n_ds[j] = h->d_nds + k; P.map[j] = h->d_map[cur][k]; P.n_map[j] = h->d_nmap[cur] + k; P.slot[j] = k;
+            P.ds[j] = h->d_ds[cur][k]; P.n_ds[j] = h->d_nds[cur] + k; P.map[j] = h->d_map[cur][k]; P.n_map[j] = h->d_nmap[cur] + k; P.slot[j] = k;
         }
         P.write_pose = p == 0;
         P.sh = h->d_sh; P.S = h->d_state; P.map_cap = h->bufcap;
@@ -506,7 +523,9 @@ int record_update(pf_odom* h, const float4* const feat[kKinds], const int* const
     return PF_OK;
 }
 
-int enqueue_update(pf_odom* h, const float4* const feat_in[kKinds], const int* const n_feat_in[kKinds], const int ub_in[kKinds]) {
+// feat_ready: event after which the feature clouds may be read (null: they are ordered on h->stream already)
+int enqueue_update(pf_odom* h, const float4* const feat_in[kKinds], const int* const n_feat_in[kKinds], const int ub_in[kKinds],
+                   cudaEvent_t feat_ready) {
     if (h->optimization_count > 2) h->optimization_count--;   // :232-233
     ring_refresh(h);
     const float4* feat[kKinds];
@@ -524,6 +543,18 @@ int enqueue_update(pf_odom* h, const float4* const feat_in[kKinds], const int* c
     const int passes = h->optimization_count;
     h->last_passes = passes;
     const int cur = h->cur;
+    if (h->overlap_ds) {
+        // down-sampling on its own stream: after the features are there and after the update that last read this slot
+        if (!feat_ready) { PF_CUDA(cudaEventRecord(h->ev_feat, h->stream)); feat_ready = h->ev_feat; }
+        PF_CUDA(cudaStreamWaitEvent(h->stream_ds, feat_ready, 0));
+        if (h->ev_upd_set[cur]) PF_CUDA(cudaStreamWaitEvent(h->stream_ds, h->ev_upd_done[cur], 0));
+        const uint64_t l0 = h->ws_ds.launches;
+        PF_CHECK(workspace_begin_step(h->ws_ds));
+        PF_CHECK(record_downsample(h, h->ws_ds, feat, n_feat, ub, cur));
+        h->ws.launches += h->ws_ds.launches - l0;
+        PF_CUDA(cudaEventRecord(h->ev_ds_done[cur], h->stream_ds));
+        PF_CUDA(cudaStreamWaitEvent(h->stream, h->ev_ds_done[cur], 0));
+    }
     bool replayed = false;
     if (h->use_graph && passes == 2 && h->sorted_known) {
         // steady state: replay the captured launch sequence of this map buffer; (re)capture when the inputs moved or outgrew its
@@ -573,6 +604,8 @@ int enqueue_update(pf_odom* h, const float4* const feat_in[kKinds], const int* c
         }
     }
     if (!replayed) PF_CHECK(record_update(h, feat, n_feat, ub, mub, passes, h->sorted_known, app));
+    PF_CUDA(cudaEventRecord(h->ev_upd_done[cur], h->stream));
+    h->ev_upd_set[cur] = true;
     h->sorted_known = true;
     h->cur = cur ^ 1;
     for (int k = 0; k < kKinds; ++k) h->map_ub[k] = app[k];     // the update never grows a map beyond old + appended
@@ -635,6 +668,12 @@ int odom_create(const pf_odom_params* p, int device, bool bpf, pf_odom** out) {
     h->bufcap = h->mcap + h->fcap;
     PF_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     PF_CUDA(cudaStreamCreateWithFlags(&h->stream_grid, cudaStreamNonBlocking));
+    PF_CUDA(cudaStreamCreateWithFlags(&h->stream_ds, cudaStreamNonBlocking));
+    PF_CUDA(cudaEventCreateWithFlags(&h->ev_feat, cudaEventDisableTiming));
+    for (int b = 0; b < 2; ++b) {
+        PF_CUDA(cudaEventCreateWithFlags(&h->ev_ds_done[b], cudaEventDisableTiming));
+        PF_CUDA(cudaEventCreateWithFlags(&h->ev_upd_done[b], cudaEventDisableTiming));
+    }
     PF_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
     PF_CUDA(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
     { const char* e = getenv("PF_ODOM_FORK"); if (e && atoi(e) == 0) h->fork_grid = false; }
@@ -658,13 +697,17 @@ extern "C" int pf_odom_destroy(pf_odom* h) {
     for (int b = 0; b < 2; ++b) if (h->graph_exec[b]) cudaGraphExecDestroy(h->graph_exec[b]);
     workspace_destroy(h->ws);
     workspace_destroy(h->ws_grid);
+    workspace_destroy(h->ws_ds);
+    if (h->stream_ds) cudaStreamDestroy(h->stream_ds);
+    if (h->ev_feat) cudaEventDestroy(h->ev_feat);
+    for (int b = 0; b < 2; ++b) { if (h->ev_ds_done[b]) cudaEventDestroy(h->ev_ds_done[b]); if (h->ev_upd_done[b]) cudaEventDestroy(h->ev_upd_done[b]); }
     if (h->stream_grid) cudaStreamDestroy(h->stream_grid);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
     map_merge_scratch_destroy(h->msc);
-    cudaFree(h->d_nfeat); cudaFree(h->d_nds); cudaFree(h->d_geom); cudaFree(h->d_nmap[0]); cudaFree(h->d_nmap[1]);
+    cudaFree(h->d_nfeat); cudaFree(h->d_nds[0]); cudaFree(h->d_nds[1]); cudaFree(h->d_geom); cudaFree(h->d_nmap[0]); cudaFree(h->d_nmap[1]);
     for (int k = 0; k < kKinds; ++k) {
-        cudaFree(h->d_feat[k]); cudaFree(h->d_ds[k]); cudaFree(h->d_map[0][k]); cudaFree(h->d_map[1][k]);
+        cudaFree(h->d_feat[k]); cudaFree(h->d_ds[0][k]); cudaFree(h->d_ds[1][k]); cudaFree(h->d_map[0][k]); cudaFree(h->d_map[1][k]);
         cudaFree(h->d_gpts[k]); cudaFree(h->d_cs[k]); cudaFree(h->d_ce[k]); cudaFree(h->d_head[k]); cudaFree(h->d_hits[k]);
         cudaFree(h->d_next[k]); cudaFree(h->d_nn[k]); cudaFree(h->d_flag[k]); cudaFree(h->d_g8[k]);
         cudaFree(h->d_wobs[k]); cudaFree(h->d_wspa[k]);
@@ -693,7 +736,7 @@ int host_frame(pf_odom* h, int nk_expected, const float* const feat[], const int
     int ub[kKinds];
     for (int k = 0; k < kKinds; ++k) { df[k] = h->d_feat[k]; dn[k] = h->d_nfeat + k; ub[k] = k < h->nk ? n[k] : 0; }
     if (init) { PF_CHECK(enqueue_init(h, df, dn, ub)); }
-    else { PF_CHECK(enqueue_update(h, df, dn, ub)); }
+    else { PF_CHECK(enqueue_update(h, df, dn, ub, nullptr)); }
     return finish_frame(h, pose_out);
 }
 }  // namespace
@@ -736,15 +779,18 @@ static int process_extracted(pf_odom* h, pf_extract* ex, double pose_out[7], boo
     pf_extract_device_outputs(ex, &feat[0], &nf[0], &feat[1], &nf[1], &exs, &ub[0], &ub[1], &slot);
     PF_REQUIRE(ub[1] <= h->fcap, "scan of %d points exceeds max_features %d", ub[1], h->fcap);
     PF_CUDA(cudaEventRecord(h->ev, exs));
-    PF_CUDA(cudaStreamWaitEvent(h->stream, h->ev, 0));
+    cudaStream_t reader = h->stream;       // the stream that reads the extractor's outputs
     if (!h->inited) {
+        PF_CUDA(cudaStreamWaitEvent(h->stream, h->ev, 0));
         PF_CHECK(enqueue_init(h, feat, nf, ub));
     } else {
-        PF_CHECK(enqueue_update(h, feat, nf, ub));
+        if (h->overlap_ds) reader = h->stream_ds;      // only the down-sampling reads them
+        else PF_CUDA(cudaStreamWaitEvent(h->stream, h->ev, 0));
+        PF_CHECK(enqueue_update(h, feat, nf, ub, h->ev));
     }
-    // The extractor's outputs are double buffered: the next extraction writes the OTHER slot, so it may run while this update
-    // still reads this one; it only has to wait for the update that read that other slot (the previous frame).
-    PF_CUDA(cudaEventRecord(h->ev_done[slot], h->stream));
+    // The extractor's outputs are double buffered: the next extraction writes the OTHER slot, so it may run while this frame
+    // still reads this one; it only has to wait for the reader of that other slot (the previous frame).
+    PF_CUDA(cudaEventRecord(h->ev_done[slot], reader));
     h->ev_done_set[slot] = true;
     if (h->ev_done_set[slot ^ 1]) PF_CUDA(cudaStreamWaitEvent(exs, h->ev_done[slot ^ 1], 0));
     return sync ? finish_frame(h, pose_out) : PF_OK;
@@ -875,7 +921,7 @@ extern "C" int pf_odom_get_iter_poses(pf_odom* h, double* poses, int cap, int* n
 extern "C" int pf_odom_get_stats(pf_odom* h, pf_odom_stats* s) {
     PF_REQUIRE(h && s, "bad argument");
     PF_CUDA(cudaSetDevice(h->device));
-    PF_CUDA(cudaMemcpyAsync(h->h_counts, h->d_nds, sizeof(int) * kKinds, cudaMemcpyDeviceToHost, h->stream));
+    PF_CUDA(cudaMemcpyAsync(h->h_counts, h->d_nds[h->cur ^ 1], sizeof(int) * kKinds, cudaMemcpyDeviceToHost, h->stream));
     PF_CUDA(cudaMemcpyAsync(h->h_counts + kKinds, h->d_nmap[h->cur], sizeof(int) * kKinds, cudaMemcpyDeviceToHost, h->stream));
     PF_CUDA(cudaMemcpyAsync(h->h_state, h->d_state, sizeof(LmState), cudaMemcpyDeviceToHost, h->stream));
     PF_CUDA(cudaStreamSynchronize(h->stream));
