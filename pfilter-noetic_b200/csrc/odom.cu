@@ -234,6 +234,7 @@ struct pf_odom {
     int graph_ub[2][kKinds] = {};        // feature upper bounds the graph was sized for
     int graph_mub[2][kKinds] = {};       // map upper bounds the graph was sized for
     uint64_t graph_launches[2] = {0, 0};
+    bool graph_overlap[2] = {false, false};   // whether the graph was captured without the down-sampling (it ran on the second stream)
     int graph_captures = 0;
     int map_exact[kKinds] = {};          // last exactly known map sizes (read-backs); map_ub may run ahead of them when frames are queued
     // optional phase timing (PF_ODOM_TIMING=1): CUDA events at the phase boundaries of the last update
@@ -402,7 +403,7 @@ int record_downsample(pf_odom* h, Workspace& w, const float4* const feat[kKinds]
 // The launch sequence of one update, enqueued on h->stream (directly, or into a stream capture).  ub / mub: upper bounds of the
 // feature and map counts (launch geometry only: every kernel is grid-stride or persistent and reads the exact device counts).
 int record_update(pf_odom* h, const float4* const feat[kKinds], const int* const n_feat[kKinds], const int ub[kKinds], const int mub[kKinds],
-                  int passes, bool sorted_known, int app[kKinds]) {
+                  int passes, bool sorted_known, int app[kKinds], bool overlap) {
     Workspace& ws = h->ws;
     const int cur = h->cur, nxt = cur ^ 1;
     auto mark = [&](int i) { if (h->timing) cudaEventRecord(h->tev[i], h->stream); };
@@ -437,7 +438,7 @@ int record_update(pf_odom* h, const float4* const feat[kKinds], const int* const
         ws.launches += h->ws_grid.launches - l0;
         PF_CUDA(cudaEventRecord(h->ev_join, h->stream_grid));
     }
-    if (!h->overlap_ds) PF_CHECK(record_downsample(h, ws, feat, n_feat, ub, cur));
+    if (!overlap) PF_CHECK(record_downsample(h, ws, feat, n_feat, ub, cur));
     mark(1);
     if (h->fork_grid) PF_CUDA(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
     else PF_CHECK(grids(ws));
@@ -524,8 +525,11 @@ int record_update(pf_odom* h, const float4* const feat[kKinds], const int* const
 }
 
 // feat_ready: event after which the feature clouds may be read (null: they are ordered on h->stream already)
+// overlap: down-sample on the second stream (frames queued back to back); a caller that blocks on every frame gains nothing from it
+// and saves the stream hops by keeping it in line
 int enqueue_update(pf_odom* h, const float4* const feat_in[kKinds], const int* const n_feat_in[kKinds], const int ub_in[kKinds],
-                   cudaEvent_t feat_ready) {
+                   cudaEvent_t feat_ready, bool overlap) {
+    overlap = overlap && h->overlap_ds;
     if (h->optimization_count > 2) h->optimization_count--;   // :232-233
     ring_refresh(h);
     const float4* feat[kKinds];
@@ -543,7 +547,7 @@ int enqueue_update(pf_odom* h, const float4* const feat_in[kKinds], const int* c
     const int passes = h->optimization_count;
     h->last_passes = passes;
     const int cur = h->cur;
-    if (h->overlap_ds) {
+    if (overlap) {
         // down-sampling on its own stream: after the features are there and after the update that last read this slot
         if (!feat_ready) { PF_CUDA(cudaEventRecord(h->ev_feat, h->stream)); feat_ready = h->ev_feat; }
         PF_CUDA(cudaStreamWaitEvent(h->stream_ds, feat_ready, 0));
@@ -560,7 +564,7 @@ int enqueue_update(pf_odom* h, const float4* const feat_in[kKinds], const int* c
         // steady state: replay the captured launch sequence of this map buffer; (re)capture when the inputs moved or outgrew its
         // sizing.  The sizing only sets grid dimensions (the kernels are grid-stride and read exact device counts), so the test uses
         // the last exactly known map sizes, not the host's running upper bound, which runs ahead while frames are queued.
-        bool fits = h->graph_exec[cur] != nullptr;
+        bool fits = h->graph_exec[cur] != nullptr && h->graph_overlap[cur] == overlap;
         for (int k = 0; k < kKinds && fits; ++k)
             fits = h->graph_feat[cur][k] == feat[k] && h->graph_nfeat[cur][k] == n_feat[k] && ub[k] <= h->graph_ub[cur][k] &&
                    h->map_exact[k] <= h->graph_mub[cur][k];
@@ -577,7 +581,7 @@ int enqueue_update(pf_odom* h, const float4* const feat_in[kKinds], const int* c
             const uint64_t l0 = h->ws.launches;
             bool ok = cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
             if (ok) {
-                const int rc = record_update(h, feat, n_feat, gub, gmub, passes, true, app);
+                const int rc = record_update(h, feat, n_feat, gub, gmub, passes, true, app, overlap);
                 ok = cudaStreamEndCapture(h->stream, &graph) == cudaSuccess && rc == PF_OK && graph != nullptr;
             }
             if (ok) ok = cudaGraphInstantiate(&h->graph_exec[cur], graph, 0) == cudaSuccess;
@@ -590,6 +594,7 @@ int enqueue_update(pf_odom* h, const float4* const feat_in[kKinds], const int* c
                 h->graph_exec[cur] = nullptr;
                 h->use_graph = false;
             } else {
+                h->graph_overlap[cur] = overlap;
                 for (int k = 0; k < kKinds; ++k) {
                     h->graph_feat[cur][k] = feat[k]; h->graph_nfeat[cur][k] = n_feat[k];
                     h->graph_ub[cur][k] = gub[k]; h->graph_mub[cur][k] = gmub[k];
@@ -603,7 +608,7 @@ int enqueue_update(pf_odom* h, const float4* const feat_in[kKinds], const int* c
             replayed = true;
         }
     }
-    if (!replayed) PF_CHECK(record_update(h, feat, n_feat, ub, mub, passes, h->sorted_known, app));
+    if (!replayed) PF_CHECK(record_update(h, feat, n_feat, ub, mub, passes, h->sorted_known, app, overlap));
     PF_CUDA(cudaEventRecord(h->ev_upd_done[cur], h->stream));
     h->ev_upd_set[cur] = true;
     h->sorted_known = true;
@@ -736,7 +741,7 @@ int host_frame(pf_odom* h, int nk_expected, const float* const feat[], const int
     int ub[kKinds];
     for (int k = 0; k < kKinds; ++k) { df[k] = h->d_feat[k]; dn[k] = h->d_nfeat + k; ub[k] = k < h->nk ? n[k] : 0; }
     if (init) { PF_CHECK(enqueue_init(h, df, dn, ub)); }
-    else { PF_CHECK(enqueue_update(h, df, dn, ub, nullptr)); }
+    else { PF_CHECK(enqueue_update(h, df, dn, ub, nullptr, false)); }
     return finish_frame(h, pose_out);
 }
 }  // namespace
@@ -784,9 +789,10 @@ static int process_extracted(pf_odom* h, pf_extract* ex, double pose_out[7], boo
         PF_CUDA(cudaStreamWaitEvent(h->stream, h->ev, 0));
         PF_CHECK(enqueue_init(h, feat, nf, ub));
     } else {
-        if (h->overlap_ds) reader = h->stream_ds;      // only the down-sampling reads them
+        const bool overlap = h->overlap_ds && !sync;
+        if (overlap) reader = h->stream_ds;            // only the down-sampling reads them
         else PF_CUDA(cudaStreamWaitEvent(h->stream, h->ev, 0));
-        PF_CHECK(enqueue_update(h, feat, nf, ub, h->ev));
+        PF_CHECK(enqueue_update(h, feat, nf, ub, h->ev, overlap));
     }
     // The extractor's outputs are double buffered: the next extraction writes the OTHER slot, so it may run while this frame
     // still reads this one; it only has to wait for the reader of that other slot (the previous frame).
