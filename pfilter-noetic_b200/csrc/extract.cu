@@ -324,6 +324,13 @@ __device__ __forceinline__ void cp_async_wait_all() {
     asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
 }
 
+// the reference's comparison of one step (:129-132, :138-141): float differences, double squares; out of line, it is taken only
+// when the fp32 value is within 1e-7 of the threshold
+__device__ __noinline__ bool short_step_exact(float dx, float dy, float dz) {
+    const double ddx = dx, ddy = dy, ddz = dz;
+    return !(__dadd_rn(__dadd_rn(__dmul_rn(ddx, ddx), __dmul_rn(ddy, ddy)), __dmul_rn(ddz, ddz)) > 0.05);
+}
+
 // shifts that give 0 for amounts >= 32 (PTX semantics), also for "negative" amounts seen as large unsigned numbers
 __device__ __forceinline__ unsigned shl_clamp(unsigned v, unsigned s) {
     unsigned r;
@@ -389,6 +396,7 @@ __device__ __forceinline__ int sector_pick(unsigned* scand, int C, const unsigne
     const bool anydup = __any_sync(kFull, dup);
     __syncwarp();
     int cnt = 0;
+#pragma unroll 1
     while (true) {
         unsigned m = word[0];
 #pragma unroll
@@ -582,8 +590,7 @@ __global__ void __launch_bounds__(kSecWarps * 32, 14) k_sector_extract(ExtractPa
                         const float2 sq = __fmul2_rn(dxy, dxy);
                         const float sf = __fmaf_rn(dzw.x, dzw.x, __fadd_rn(sq.x, sq.y));
                         if (fabsf(sf - 0.05f) > 1e-7f) return sf < 0.05f;
-                        const double ddx = dxy.x, ddy = dxy.y, ddz = dzw.x;
-                        return !(__dadd_rn(__dadd_rn(__dmul_rn(ddx, ddx), __dmul_rn(ddy, ddy)), __dmul_rn(ddz, ddz)) > 0.05);
+                        return short_step_exact(dxy.x, dxy.y, dzw.x);
                     };
                     const int qh = q0 + h * HW;
 #pragma unroll
@@ -641,7 +648,9 @@ __global__ void __launch_bounds__(kSecWarps * 32, 14) k_sector_extract(ExtractPa
             // D. greedy pick (:99-209)
             int cnt, cw = C;
             if (C <= 64) { cnt = sector_pick<2>(scand, C, slink, srng, sflagw, Ls, lane, flagw, myedge); cw = 64; }
+#ifndef PF_NO_NPL4
             else if (C <= 128) { cnt = sector_pick<4>(scand, C, slink, srng, sflagw, Ls, lane, flagw, myedge); cw = 128; }
+#endif
             else if (C <= 256) { cnt = sector_pick<8>(scand, C, slink, srng, sflagw, Ls, lane, flagw, myedge); cw = 256; }
             else cnt = -1;
             if (cnt < 0) cnt = sector_pick_large(sp, scand, cw, slink, Ls, lane, flagw, myedge, -1 - cnt);
