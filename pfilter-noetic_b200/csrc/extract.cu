@@ -245,17 +245,29 @@ __global__ void __launch_bounds__(256) k_ring_index(ExtractParams P) {
     const uint8_t* rid = P.ringid + (size_t)s * P.stride;
     int* off = P.tile_off + ((size_t)s * kMaxLines + r) * (P.tiles + 1);
     int carry = 0;
+    int off_incl0 = 0;              // first chunk: ring position at which tile `lane` ENDS (kept in registers for the sector search)
+    unsigned pure0 = 0u;            // first chunk: tiles that are pure tiles of this ring
     for (int c0 = 0; c0 < ncand; c0 += 32) {
         const int c = c0 + lane;
         const int pr = c < ncand ? pure[tlo + c] : 254;
         int cnt = pr == r ? kTile : 0;
         unsigned mixed = __ballot_sync(kFull, pr == 255);
-        while (mixed) {       // a tile with several rings (or dropped points): count this ring's bytes, 8 per lane
-            const int b = __ffs(mixed) - 1;
-            mixed &= mixed - 1u;
-            const uint2 v = *reinterpret_cast<const uint2*>(rid + (size_t)(tlo + c0 + b) * kTile + lane * 8);
-            const int m = __reduce_add_sync(kFull, count_bytes_eq(v.x, (unsigned)r) + count_bytes_eq(v.y, (unsigned)r));
-            if (lane == b) cnt = m;
+        while (mixed) {       // tiles with several rings (or dropped points): count this ring's bytes, 8 per lane, four tiles in flight
+            int b[4];
+            uint2 v[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                b[j] = mixed ? __ffs(mixed) - 1 : -1;
+                if (mixed) mixed &= mixed - 1u;
+                v[j] = make_uint2(0xffffffffu, 0xffffffffu);
+                if (b[j] >= 0) v[j] = *reinterpret_cast<const uint2*>(rid + (size_t)(tlo + c0 + b[j]) * kTile + lane * 8);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (b[j] < 0) break;       // uniform
+                const int m = __reduce_add_sync(kFull, count_bytes_eq(v[j].x, (unsigned)r) + count_bytes_eq(v[j].y, (unsigned)r));
+                if (lane == b[j]) cnt = m;
+            }
         }
         int x = cnt;
 #pragma unroll
@@ -264,6 +276,7 @@ __global__ void __launch_bounds__(256) k_ring_index(ExtractParams P) {
             if (lane >= o) x += y;
         }
         if (c < ncand) off[c] = carry + x - cnt;
+        if (c0 == 0) { off_incl0 = x; pure0 = __ballot_sync(kFull, pr == r); }
         carry += __shfl_sync(kFull, x, 31);
     }
     if (lane == 0) {
@@ -271,14 +284,37 @@ __global__ void __launch_bounds__(256) k_ring_index(ExtractParams P) {
         P.ring_info[(size_t)s * kMaxLines + r] = make_int4(tlo, ncand, carry, 0);
         if (carry > P.rcap) atomicOr(&P.ctrl[2], 1u);     // ring larger than the configured capacity
     }
-    __syncwarp();
-    // sector descriptors (:81-92): lane k locates sector k in the tile range; when every tile it touches is a pure tile of this
-    // ring, its points are ONE contiguous run of the input and the extract kernel copies them without looking at any other table
-    if (lane < kSectors) {
-        const int nr = carry, k = lane;
+    // sector descriptors (:81-92): sector k is located in the tile range; when every tile it touches is a pure tile of this ring,
+    // its points are ONE contiguous run of the input and the extract kernel copies them without looking at any other table
+    const int nr = carry;
+    const bool ring_ok = nr >= 131 && nr <= P.rcap;       // :67
+    const int total = nr - 10, L = total / kSectors;
+    if (ncand <= 32) {
+        // the whole tile range sits in the lanes' registers: six ballots instead of dependent loads
         int4 d = make_int4(0, 0, -1, 0);
-        if (nr >= 131 && nr <= P.rcap) {                  // :67
-            const int total = nr - 10, L = total / kSectors;
+#pragma unroll
+        for (int k = 0; k < kSectors; ++k) {
+            const int lo = L * k, hi = (k == kSectors - 1) ? total - 1 : lo + L - 1;   // hi excluded (:83-88)
+            const int n_loc = hi - lo + 10, p0 = lo, p1 = lo + n_loc;
+            const unsigned before = __ballot_sync(kFull, lane < ncand && off_incl0 <= p0);   // tiles that end at or before p0
+            const unsigned reach = __ballot_sync(kFull, lane < ncand && off_incl0 < p1);    // tiles that end before p1 (never the last)
+            const int a = __popc(before);                                               // first tile holding p0
+            const int e = min(__popc(reach), ncand - 1);                                // last tile holding a point below p1
+            const unsigned span = (e >= a) ? ((e - a == 31 ? kFull : ((1u << (e - a + 1)) - 1u)) << a) : 0u;
+            const int off_a = __shfl_sync(kFull, off_incl0, max(a - 1, 0));
+            if (lane == k && ring_ok) {
+                const bool contiguous = (pure0 & span) == span;
+                d = make_int4(n_loc, p0, contiguous ? (tlo + a) * kTile + (p0 - (a > 0 ? off_a : 0)) : -1, a);
+            }
+        }
+        if (lane < kSectors) P.sec_desc[((size_t)s * kMaxLines + r) * kSectors + lane] = d;
+        return;
+    }
+    __syncwarp();
+    if (lane < kSectors) {
+        const int k = lane;
+        int4 d = make_int4(0, 0, -1, 0);
+        if (ring_ok) {
             const int lo = L * k, hi = (k == kSectors - 1) ? total - 1 : lo + L - 1;   // hi excluded (:83-88)
             const int n_loc = hi - lo + 10, p0 = lo, p1 = lo + n_loc;
             int a = 0, b = ncand;                         // first tile with off[c + 1] > p0
