@@ -8,7 +8,7 @@ nf = int(sys.argv[2]) if len(sys.argv) > 2 else 8
 lines = [l for l in open(path) if l.startswith('"')]
 rows = [r for r in csv.DictReader(lines) if r.get("Metric Name") == "gpu__time_duration.sum"]
 ids = [i for i, r in enumerate(rows) if "k_predict" in r["Kernel Name"]]
-lo, hi = ids[-nf - 1] - 3, ids[-1] - 3     # a frame starts 3 launches before k_predict (set_int, classify, extract)
+lo, hi = ids[-nf - 1] - 4, ids[-1] - 4     # a frame starts 4 launches before k_predict (set_int, classify, index, extract)
 sel = rows[lo:hi]
 agg = OrderedDict()
 for r in sel:
