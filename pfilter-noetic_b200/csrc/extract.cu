@@ -360,11 +360,16 @@ __device__ __forceinline__ void cp_async_wait_all() {
     asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
 }
 
-// the reference's comparison of one step (:129-132, :138-141): float differences, double squares; out of line, it is taken only
-// when the fp32 value is within 1e-7 of the threshold
-__device__ __noinline__ bool short_step_exact(float dx, float dy, float dz) {
-    const double ddx = dx, ddy = dy, ddz = dz;
-    return !(__dadd_rn(__dadd_rn(__dmul_rn(ddx, ddx), __dmul_rn(ddy, ddy)), __dmul_rn(ddz, ddz)) > 0.05);
+// the reference's comparison (:129-132, :138-141) for the five steps between the six points at p: float differences, double
+// squares; out of line, it is taken only when an fp32 value is within 1e-7 of the threshold
+__device__ __noinline__ unsigned short_steps_exact(const float4* p) {
+    unsigned bits = 0u;
+    for (int j = 0; j < 5; ++j) {
+        const double ddx = (double)__fsub_rn(p[j + 1].x, p[j].x), ddy = (double)__fsub_rn(p[j + 1].y, p[j].y),
+                     ddz = (double)__fsub_rn(p[j + 1].z, p[j].z);
+        if (!(__dadd_rn(__dadd_rn(__dmul_rn(ddx, ddx), __dmul_rn(ddy, ddy)), __dmul_rn(ddz, ddz)) > 0.05)) bits |= 1u << j;
+    }
+    return bits;
 }
 
 // shifts that give 0 for amounts >= 32 (PTX semantics), also for "negative" amounts seen as large unsigned numbers
@@ -524,8 +529,8 @@ __global__ void __launch_bounds__(kSecWarps * 32, 14) k_sector_extract(ExtractPa
     const int lane = threadIdx.x & 31;
     const int S = P.scap;
     unsigned char* wsm = smem_raw + (size_t)(threadIdx.x >> 5) * P.warp_smem;
-    float4* sp = reinterpret_cast<float4*>(wsm);                         // [S + 16] sector points, local index q
-    unsigned* scand = reinterpret_cast<unsigned*>(sp + S + 16);          // [S] candidate words; once they sit in registers the
+    float4* sp = reinterpret_cast<float4*>(wsm);                         // [S + 24] sector points, local index q (+ window slack)
+    unsigned* scand = reinterpret_cast<unsigned*>(sp + S + 24);          // [S] candidate words; once they sit in registers the
     uint16_t* srng = reinterpret_cast<uint16_t*>(scand);                 //     same bytes hold the suppressed range per position
     unsigned* slink = scand + S;                                         // [S / 32 + 2] link bits: bit q = short step q -> q+1
     unsigned* sflagw = slink + S / 32 + 2;                               // [18] flag bits of the sector (picked / suppressed)
@@ -601,9 +606,11 @@ __global__ void __launch_bounds__(kSecWarps * 32, 14) k_sector_extract(ExtractPa
 
             // C. curvature, link bits, candidates
             int C = 0;
-            for (int qb = 5; qb < n_loc - 1; qb += 32 * kWin) {
+            // A lane owns the curvature positions q0 .. q0 + 9 and the ten steps q0 - 5 .. q0 + 4 (the first ten of its window), so the
+            // steps 0 .. 4 in front of the first position need no special case; one more lane than there are positions may be active
+            for (int qb = 5; qb - 5 < n_loc - 1; qb += 32 * kWin) {
                 const int q0 = qb + lane * kWin;
-                const bool act = q0 < n_loc - 1;
+                const bool act = q0 - 5 < n_loc - 1;
                 const int qa = act ? q0 : 5;
                 unsigned lm = 0u;
                 // two half windows of 15 points (5 positions each): keeps the register window at 45 floats
@@ -619,24 +626,24 @@ __global__ void __launch_bounds__(kSecWarps * 32, 14) k_sector_extract(ExtractPa
                         wxy[j] = make_float2(p.x, p.y); wzw[j] = make_float2(p.z, p.w);
                     }
                     const float2 neg1 = make_float2(-1.0f, -1.0f);
-                    // short steps between window slots j, j+1: float differences, double squares (:129-132), decided in
-                    // fp32 unless within 1e-7 of the threshold 0.05
-                    auto short_step = [&](int j) {
+                    const int qh = q0 + h * HW;
+                    // short steps between window slots j, j+1 = local points qh - 5 + j, + 1: float differences, double squares
+                    // (:129-132), decided in fp32; a value within 1e-7 of the threshold 0.05 sends the five steps to the exact test
+                    unsigned sb = 0u;
+                    bool unsure = false;
+#pragma unroll
+                    for (int j = 0; j < HW; ++j) {
                         const float2 dxy = __ffma2_rn(wxy[j], neg1, wxy[j + 1]), dzw = __ffma2_rn(wzw[j], neg1, wzw[j + 1]);   // b - a
                         const float2 sq = __fmul2_rn(dxy, dxy);
                         const float sf = __fmaf_rn(dzw.x, dzw.x, __fadd_rn(sq.x, sq.y));
-                        if (fabsf(sf - 0.05f) > 1e-7f) return sf < 0.05f;
-                        return short_step_exact(dxy.x, dxy.y, dzw.x);
-                    };
-                    const int qh = q0 + h * HW;
-#pragma unroll
-                    for (int j = 0; j < HW; ++j)
-                        if (short_step(j + 5) && qh + j + 1 < n_loc) lm |= 1u << (h * HW + j);
-                    if (qh == 5) {       // the first lane also owns the steps 0 .. 4 (kept above its own ten bits for now)
-#pragma unroll
-                        for (int j = 0; j < 5; ++j)
-                            if (short_step(j)) lm |= 1u << (kWin + j);
+                        unsure = unsure || fabsf(sf - 0.05f) <= 1e-7f;
+                        if (sf < 0.05f) sb |= 1u << j;
                     }
+                    if (unsure) sb = short_steps_exact(sp + (qa - 5 + h * HW));
+                    // steps that end beyond the local range do not exist (bits qh - 5 + j with qh - 5 + j + 1 < n_loc)
+                    const int nvalid = n_loc - 1 - (qh - 5);
+                    if (nvalid < HW) sb &= nvalid > 0 ? (1u << nvalid) - 1u : 0u;
+                    lm |= sb << (h * HW);
 #pragma unroll
                     for (int j = 0; j < HW; ++j) {
                         auto tap = [&](const float2* a) {     // left to right, t - 10 p = t + (-10 p) (:73-75)
@@ -667,16 +674,10 @@ __global__ void __launch_bounds__(kSecWarps * 32, 14) k_sector_extract(ExtractPa
                         C += __popc(cm);
                     }
                 }
-                if (act) {
-                    int q = q0;
-                    if (q0 == 5) {
-                        lm = ((lm & ((1u << kWin) - 1u)) << 5) | (lm >> kWin);
-                        q = 0;
-                    }
-                    if (lm != 0u) {
-                        atomicOr(&slink[q >> 5], lm << (q & 31));
-                        if ((q & 31) != 0 && (lm >> (32 - (q & 31))) != 0u) atomicOr(&slink[(q >> 5) + 1], lm >> (32 - (q & 31)));
-                    }
+                if (act && lm != 0u) {
+                    const int q = q0 - 5;
+                    atomicOr(&slink[q >> 5], lm << (q & 31));
+                    if ((q & 31) != 0 && (lm >> (32 - (q & 31))) != 0u) atomicOr(&slink[(q >> 5) + 1], lm >> (32 - (q & 31)));
                 }
             }
             __syncwarp();
@@ -987,7 +988,7 @@ extern "C" int pf_extract_create(const pf_lidar_params* lidar, const pf_extract_
     // the register windows), candidate words, link bits, suppressed ranges (+ source indices for the label output)
     h->scap = div_up((h->rcap - 10) / kSectors + 14, 32) * 32;
     if (h->scap < 256) h->scap = 256;     // sector_pick hands up to 256 live words back through the candidate array
-    h->warp_smem = (h->scap + 16) * 16 + h->scap * 4 + (h->scap / 32 + 2 + 18) * 4;
+    h->warp_smem = (h->scap + 24) * 16 + h->scap * 4 + (h->scap / 32 + 2 + 18) * 4;
     h->warp_smem = div_up(h->warp_smem, 16) * 16;
     h->warp_smem_label = h->warp_smem + h->scap * 4;
     if ((size_t)kSecWarps * h->warp_smem_label > (size_t)prop.sharedMemPerBlockOptin) {
