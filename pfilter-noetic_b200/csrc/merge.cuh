@@ -20,7 +20,7 @@
 
 namespace pf {
 
-constexpr int kMergeMaxGrid = 8 * kSMs;   // CTAs per cloud of the two streaming passes
+constexpr int kMergeMaxGrid = 16 * kSMs;   // CTAs per cloud of the two streaming passes
 
 struct MapMergeCloud {
     const Pt* buf;           // current map buffer (layout above)
