@@ -308,6 +308,8 @@ __global__ void __launch_bounds__(256) k_mm_count(MapMergeParams P) {
         cta_part += v;
     }
     if ((tid & 31) == 0 && cta_part) atomicAdd(&P.s.cta_sum[cloud * kMergeMaxGrid + blockIdx.x], cta_part);
+    // programmatic dependent launch: the write pass may start filling SMs while the last count CTAs drain
+    cudaTriggerProgrammaticLaunchCompletion();
 }
 
 // first index in [lo, hi) with a[idx] >= key (few entries: the heads / inserts that fall into one tile)
@@ -345,6 +347,7 @@ __global__ void __launch_bounds__(256, 8) k_mm_write(MapMergeParams P) {
     const int* ti = P.s.tile_i + (size_t)cloud * P.s.tile_cap;
     const int* agg = P.s.tile_agg + (size_t)cloud * P.s.tile_cap;
     const CropBox box = crop_of(P.center);
+    cudaGridDependencySynchronize();      // results of the count pass (no-op without a programmatic launch edge)
     // exclusive prefix of the CTA sums in front of this CTA
     int running;
     {
@@ -485,7 +488,23 @@ int map_merge(Workspace& ws, const MapMergeParams& P_in, int capB0, int capB1, i
 
     if (ws.ev_a) cudaEventRecord(ws.ev_a, ws.stream);
     k_mm_count<<<dim3(grid, 2), 256, 0, ws.stream>>>(P);
-    k_mm_write<<<dim3(grid, 2), 256, 0, ws.stream>>>(P);      // same grid: same tile partition
+    {
+        // same grid: same tile partition.  Outside stream capture the write pass is launched with a programmatic edge (its CTAs
+        // are scheduled while the count pass drains and wait in cudaGridDependencySynchronize): saves the launch gap of the pair
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        cudaStreamIsCapturing(ws.stream, &cap);
+        if (cap == cudaStreamCaptureStatusNone) {
+            cudaLaunchConfig_t cfg{};
+            cfg.gridDim = dim3(grid, 2); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = ws.stream;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            at[0].val.programmaticStreamSerializationAllowed = 1;
+            cfg.attrs = at; cfg.numAttrs = 1;
+            PF_CUDA(cudaLaunchKernelEx(&cfg, k_mm_write, P));
+        } else {
+            k_mm_write<<<dim3(grid, 2), 256, 0, ws.stream>>>(P);
+        }
+    }
     if (ws.ev_b) cudaEventRecord(ws.ev_b, ws.stream);
     k_mm_finish<<<2, 256, 0, ws.stream>>>(P);
     ws.launches += 5;
