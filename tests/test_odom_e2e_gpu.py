@@ -105,10 +105,13 @@ def test_graph_replay_is_bit_identical_to_plain_launches(pfb, capi, monkeypatch)
 
 
 def test_pipelined_submit_wait_equals_synchronous_calls(pfb, capi):
+    """Queued frames run the down-sampling on its own stream (overlapping the previous frame's solve and map update) and, from
+    frame 11 on, replay a graph without it; blocking calls keep it in line.  Poses and maps must not differ by a single bit."""
     p = pfb.synth.config("cfg2")
-    scans = [pfb.synth.scan(p, f) for f in range(16)]
+    scans = [pfb.synth.scan(p, f) for f in range(28)]
     ex, od = capi.Extractor(num_lines=64, max_points=131072), capi.Odometry(0.4, 0, 0.4, 75, max_map_points=262144)
     sync = np.array([capi.frame_process(ex, od, s) for s in scans])
+    sync_maps = [od.map_part(0), od.map_part(1)]
     ex.close(); od.close()
     ex, od = capi.Extractor(num_lines=64, max_points=131072), capi.Odometry(0.4, 0, 0.4, 75, max_map_points=262144)
     ids = [capi.frame_submit(ex, od, s) for s in scans[:3]]          # three frames in flight
@@ -119,5 +122,16 @@ def test_pipelined_submit_wait_equals_synchronous_calls(pfb, capi):
     out += [capi.frame_wait(od, i) for i in ids[-3:]]
     assert ids == list(range(len(scans)))
     assert np.array(out).tobytes() == sync.tobytes()
+    maps = [od.map_part(0), od.map_part(1)]
+    assert maps[0].tobytes() == sync_maps[0].tobytes() and maps[1].tobytes() == sync_maps[1].tobytes()
+    # mixing the two call styles on one handle (the graphs are re-captured for the other mode)
+    more = [pfb.synth.scan(p, f) for f in range(28, 34)]
+    a = [capi.frame_process(ex, od, s) for s in more[:3]]
+    i3 = [capi.frame_submit(ex, od, s) for s in more[3:]]
+    b = [capi.frame_wait(od, i) for i in i3]
+    ex2, od2 = capi.Extractor(num_lines=64, max_points=131072), capi.Odometry(0.4, 0, 0.4, 75, max_map_points=262144)
+    ref = np.array([capi.frame_process(ex2, od2, s) for s in scans + more])
+    assert np.array(a + b).tobytes() == ref[28:].tobytes()
+    ex2.close(); od2.close()
     with pytest.raises(capi.PfError):
         capi.frame_wait(od, 10_000)
