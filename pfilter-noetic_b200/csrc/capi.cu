@@ -1,5 +1,6 @@
 // Library-level C ABI entry points: version, error text, device count, pinned host memory.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -10,6 +11,10 @@ void set_error(const char* fmt, ...) {
     va_start(ap, fmt);
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
+}
+bool pdl_enabled() {
+    static const bool on = [] { const char* e = getenv("PF_PDL"); return !(e && e[0] == '0'); }();
+    return on;
 }
 }  // namespace pf
 

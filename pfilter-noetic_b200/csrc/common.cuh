@@ -55,9 +55,33 @@ __host__ __device__ inline uint32_t pt_r(uint32_t rgba) { return rgba & 0xffu; }
 __host__ __device__ inline uint32_t pt_g(uint32_t rgba) { return (rgba >> 8) & 0xffu; }
 
 inline int div_up(int a, int b) { return (a + b - 1) / b; }
+
+// Programmatic dependent launch (PF_PDL=0 disables): a kernel launched through launch_pdl may be scheduled as soon as every CTA of
+// the kernel in front of it in the stream has passed PF_PDL_ENTRY (or exited); its own PF_PDL_ENTRY then blocks until that kernel
+// has completed and its memory is visible.  A frame is a chain of ~25 small dependent kernels: the edge hides the launch latency
+// of every link (also inside the captured CUDA graph, where it becomes a programmatic edge).  Every kernel launched this way MUST
+// start with PF_PDL_ENTRY(); kernels without it in front of one (cooperative sort, memcpy, events) behave as ordinary predecessors.
+bool pdl_enabled();
 inline int64_t div_up64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 #ifdef __CUDACC__
+#define PF_PDL_ENTRY()                                  \
+    do {                                                \
+        cudaGridDependencySynchronize();                \
+        cudaTriggerProgrammaticLaunchCompletion();      \
+    } while (0)
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 __device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31u; }
 __device__ __forceinline__ unsigned lanemask_lt() {
     unsigned m;

@@ -14,6 +14,7 @@ __device__ __forceinline__ float ord2f_k(unsigned k) {
 
 // state slot: [0..5] map0 {~min, max}, [6..11] map1, [12..13] counts n0, n1, [14] n_total, [15] error
 __global__ void __launch_bounds__(256) k_grid_bounds(GridBuild G) {
+    PF_PDL_ENTRY();
     const int kind = blockIdx.y;
     const int n = *G.n_map[kind];
     const Pt* m = G.map[kind];
@@ -42,6 +43,7 @@ __global__ void __launch_bounds__(256) k_grid_bounds(GridBuild G) {
 
 // one block per map: origin / dims from the bounds
 __global__ void k_grid_geom(GridBuild G) {
+    PF_PDL_ENTRY();
     const int kind = blockIdx.x;
     if (threadIdx.x != 0) return;
     const unsigned* s = G.state + kind * 6;
@@ -71,6 +73,7 @@ __global__ void k_grid_geom(GridBuild G) {
 // (single pass, chained look-back), scatter (one atomic per point on the cell's cursor).  The order of the points inside a
 // cell is whatever the atomics produce; the search does not depend on it (exact distances, ties broken by the carried index).
 __global__ void __launch_bounds__(256) k_grid_clear(GridBuild G) {
+    PF_PDL_ENTRY();
     const int kind = blockIdx.y;
     const int* geom = G.geom[kind];
     const long long cells = (long long)geom[3] * geom[4] * geom[5];
@@ -80,6 +83,7 @@ __global__ void __launch_bounds__(256) k_grid_clear(GridBuild G) {
 }
 
 __global__ void __launch_bounds__(256) k_grid_count(GridBuild G, uint32_t* __restrict__ keys) {
+    PF_PDL_ENTRY();
     const int kind = blockIdx.y;
     const int n = *G.n_map[kind];
     const int base = kind == 0 ? 0 : *G.n_map[0];
@@ -99,6 +103,7 @@ __global__ void __launch_bounds__(256) k_grid_count(GridBuild G, uint32_t* __res
 
 constexpr int kGridScanTile = 2048;     // cells per tile of the scan (8 per thread)
 __global__ void __launch_bounds__(256) k_grid_scan(GridBuild G, unsigned long long* status, int status_stride, unsigned* ctrl) {
+    PF_PDL_ENTRY();
     const int kind = blockIdx.y;
     const int* geom = G.geom[kind];
     const long long cells = (long long)geom[3] * geom[4] * geom[5];
@@ -145,6 +150,7 @@ __global__ void __launch_bounds__(256) k_grid_scan(GridBuild G, unsigned long lo
 }
 
 __global__ void __launch_bounds__(256) k_grid_scatter(GridBuild G, const uint32_t* __restrict__ keys) {
+    PF_PDL_ENTRY();
     const int kind = blockIdx.y;
     const int n = *G.n_map[kind];
     const int base = kind == 0 ? 0 : *G.n_map[0];
@@ -168,12 +174,12 @@ int build_grids(Workspace& ws, const GridBuild& G_in, int slot, int cap0, int ca
     int nblk = div_up(capmax, 256 * 4);
     if (nblk > 4 * kSMs) nblk = 4 * kSMs;
     if (nblk < 1) nblk = 1;
-    k_grid_bounds<<<dim3(nblk, 2), 256, 0, ws.stream>>>(G);
-    k_grid_geom<<<2, 32, 0, ws.stream>>>(G);
-    k_grid_clear<<<dim3(4 * kSMs, 2), 256, 0, ws.stream>>>(G);
-    k_grid_count<<<dim3(nblk, 2), 256, 0, ws.stream>>>(G, ws.keys[0]);
-    k_grid_scan<<<dim3(4 * kSMs, 2), 256, 0, ws.stream>>>(G, ws.scan_status, ws.status_stride, ws.ctrl);
-    k_grid_scatter<<<dim3(nblk, 2), 256, 0, ws.stream>>>(G, ws.keys[0]);
+    PF_CUDA(launch_pdl(k_grid_bounds, dim3(nblk, 2), dim3(256), 0, ws.stream, G));
+    PF_CUDA(launch_pdl(k_grid_geom, dim3(2), dim3(32), 0, ws.stream, G));
+    PF_CUDA(launch_pdl(k_grid_clear, dim3(4 * kSMs, 2), dim3(256), 0, ws.stream, G));
+    PF_CUDA(launch_pdl(k_grid_count, dim3(nblk, 2), dim3(256), 0, ws.stream, G, ws.keys[0]));
+    PF_CUDA(launch_pdl(k_grid_scan, dim3(4 * kSMs, 2), dim3(256), 0, ws.stream, G, ws.scan_status, ws.status_stride, ws.ctrl));
+    PF_CUDA(launch_pdl(k_grid_scatter, dim3(nblk, 2), dim3(256), 0, ws.stream, G, ws.keys[0]));
     ws.launches += 6;
     PF_CUDA(cudaGetLastError());
     return PF_OK;

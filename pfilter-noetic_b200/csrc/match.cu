@@ -21,6 +21,7 @@ namespace pf {
 // costs a fraction of that pipe time per query.
 constexpr int kAssocBatch = 4;
 __global__ void __launch_bounds__(256) k_assoc_match(AssocParams P) {
+    PF_PDL_ENTRY();
     const int kind = blockIdx.y;
     const AssocCloud& c = P.c[kind];
     const unsigned lane = lane_id();
@@ -113,6 +114,7 @@ __global__ void __launch_bounds__(256) k_assoc_match(AssocParams P) {
 }
 
 __global__ void __launch_bounds__(128) k_assoc_persist(AssocParams P) {
+    PF_PDL_ENTRY();
     const int kind = blockIdx.y;
     const AssocCloud& c = P.c[kind];
     const int nq = *c.n_q;
@@ -181,8 +183,8 @@ int associate_pass(cudaStream_t stream, const AssocParams& P, int qcap0, int qca
     int gm = div_up(qcap, 8 * kAssocBatch), gp = div_up(qcap, 128);
     if (gm > 8 * kSMs) gm = 8 * kSMs;
     if (gp > 4 * kSMs) gp = 4 * kSMs;
-    k_assoc_match<<<dim3(gm, 2), 256, 0, stream>>>(P);
-    k_assoc_persist<<<dim3(gp, 2), 128, 0, stream>>>(P);
+    PF_CUDA(launch_pdl(k_assoc_match, dim3(gm, 2), dim3(256), 0, stream, P));
+    PF_CUDA(launch_pdl(k_assoc_persist, dim3(gp, 2), dim3(128), 0, stream, P));
     if (launches) *launches += 2;
     PF_CUDA(cudaGetLastError());
     return PF_OK;

@@ -89,6 +89,7 @@ __device__ __forceinline__ void put_exception(const MapMergeParams& P, int cloud
 }
 
 __global__ void __launch_bounds__(256) k_mm_keys(MapMergeParams P, uint32_t* __restrict__ keys) {
+    PF_PDL_ENTRY();
     const int cloud = blockIdx.y;
     const MapMergeCloud& c = P.c[cloud];
     const int mA = *c.n_sorted;
@@ -132,6 +133,7 @@ __global__ void __launch_bounds__(256) k_mm_keys(MapMergeParams P, uint32_t* __r
 
 __global__ void __launch_bounds__(256) k_mm_heads(MapMergeParams P, const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals,
                                                   unsigned long long* status, int status_stride, unsigned* ctrl, int ticket_word) {
+    PF_PDL_ENTRY();
     const int cloud = blockIdx.y;
     const MapMergeCloud& c = P.c[cloud];
     __shared__ int s_tile;
@@ -236,6 +238,7 @@ __device__ __forceinline__ TileRange tile_range(int mA) {
 // per tile of the sorted map part: first matched head / first insert at or behind the tile's first map index; zeroes the
 // per-tile and per-CTA counters of the count pass
 __global__ void __launch_bounds__(256) k_mm_tiles(MapMergeParams P) {
+    PF_PDL_ENTRY();
     const int cloud = blockIdx.y;
     const int mA = *P.c[cloud].n_sorted;
     const int ntiles = mA / kMergeTile + 1;
@@ -269,6 +272,7 @@ __global__ void __launch_bounds__(256) k_mm_tiles(MapMergeParams P) {
 // crop box and the delete rule, corrected by the matched voxels finished in k_mm_heads, plus the inserts that fall into the
 // tile.  No shared memory, no barrier: 16 B read per map point, one warp-aggregated atomic per warp and tile.
 __global__ void __launch_bounds__(256) k_mm_count(MapMergeParams P) {
+    PF_PDL_ENTRY();
     const int cloud = blockIdx.y;
     const MapMergeCloud& c = P.c[cloud];
     const int mA = *c.n_sorted;
@@ -308,8 +312,6 @@ __global__ void __launch_bounds__(256) k_mm_count(MapMergeParams P) {
         cta_part += v;
     }
     if ((tid & 31) == 0 && cta_part) atomicAdd(&P.s.cta_sum[cloud * kMergeMaxGrid + blockIdx.x], cta_part);
-    // programmatic dependent launch: the write pass may start filling SMs while the last count CTAs drain
-    cudaTriggerProgrammaticLaunchCompletion();
 }
 
 // first index in [lo, hi) with a[idx] >= key (few entries: the heads / inserts that fall into one tile)
@@ -347,7 +349,7 @@ __global__ void __launch_bounds__(256, 8) k_mm_write(MapMergeParams P) {
     const int* ti = P.s.tile_i + (size_t)cloud * P.s.tile_cap;
     const int* agg = P.s.tile_agg + (size_t)cloud * P.s.tile_cap;
     const CropBox box = crop_of(P.center);
-    cudaGridDependencySynchronize();      // results of the count pass (no-op without a programmatic launch edge)
+    PF_PDL_ENTRY();                       // results of the count pass (everything above only reads what earlier kernels left)
     // exclusive prefix of the CTA sums in front of this CTA
     int running;
     {
@@ -425,6 +427,7 @@ __global__ void __launch_bounds__(256, 8) k_mm_write(MapMergeParams P) {
 }
 
 __global__ void __launch_bounds__(256) k_mm_finish(MapMergeParams P) {
+    PF_PDL_ENTRY();
     const int cloud = blockIdx.x;
     const MapMergeCloud& c = P.c[cloud];
     const int ns = *c.n_sorted_out;
@@ -472,41 +475,29 @@ int map_merge(Workspace& ws, const MapMergeParams& P_in, int capB0, int capB1, i
     const int capBmax = capB0 > capB1 ? capB0 : capB1, capAmax = capA0 > capA1 ? capA0 : capA1;
     int nblk = div_up(capBmax > 0 ? capBmax : 1, 256 * 4);
     if (nblk > 4 * kSMs) nblk = 4 * kSMs;
-    k_mm_keys<<<dim3(nblk, 2), 256, 0, ws.stream>>>(P, ws.keys[0]);
+    PF_CUDA(launch_pdl(k_mm_keys, dim3(nblk, 2), dim3(256), 0, ws.stream, P, ws.keys[0]));
     ws.launches += 1;
     int rb = 0;
     PF_CHECK(radix_sort(ws, reinterpret_cast<const int*>(P.state) + 8, capB > 0 ? capB : 1, 4, true, &rb));
     int tiles = div_up(capBmax > 0 ? capBmax : 1, 256);
     if (tiles > 6 * kSMs) tiles = 6 * kSMs;
-    k_mm_heads<<<dim3(tiles, 2), 256, 0, ws.stream>>>(P, ws.keys[rb], ws.vals[rb], ws.scan_status, ws.status_stride, ws.ctrl, 5);
+    PF_CUDA(launch_pdl(k_mm_heads, dim3(tiles, 2), dim3(256), 0, ws.stream, P, ws.keys[rb], ws.vals[rb], ws.scan_status, ws.status_stride, ws.ctrl, 5));
     const int mtiles_all = capAmax / kMergeTile + 1;
     int tblk = div_up(mtiles_all + 1, 256);
     if (tblk > 2 * kSMs) tblk = 2 * kSMs;
-    k_mm_tiles<<<dim3(tblk, 2), 256, 0, ws.stream>>>(P);
+    PF_CUDA(launch_pdl(k_mm_tiles, dim3(tblk, 2), dim3(256), 0, ws.stream, P));
     int grid = mtiles_all;
     if (grid > kMergeMaxGrid) grid = kMergeMaxGrid;
 
     if (ws.ev_a) cudaEventRecord(ws.ev_a, ws.stream);
-    k_mm_count<<<dim3(grid, 2), 256, 0, ws.stream>>>(P);
+    PF_CUDA(launch_pdl(k_mm_count, dim3(grid, 2), dim3(256), 0, ws.stream, P));
     {
-        // same grid: same tile partition.  Outside stream capture the write pass is launched with a programmatic edge (its CTAs
-        // are scheduled while the count pass drains and wait in cudaGridDependencySynchronize): saves the launch gap of the pair
-        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
-        cudaStreamIsCapturing(ws.stream, &cap);
-        if (cap == cudaStreamCaptureStatusNone) {
-            cudaLaunchConfig_t cfg{};
-            cfg.gridDim = dim3(grid, 2); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = ws.stream;
-            cudaLaunchAttribute at[1];
-            at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-            at[0].val.programmaticStreamSerializationAllowed = 1;
-            cfg.attrs = at; cfg.numAttrs = 1;
-            PF_CUDA(cudaLaunchKernelEx(&cfg, k_mm_write, P));
-        } else {
-            k_mm_write<<<dim3(grid, 2), 256, 0, ws.stream>>>(P);
-        }
+        // same grid: same tile partition.  The write pass is launched with a programmatic edge (its CTAs are scheduled while the
+        // count pass drains and wait in cudaGridDependencySynchronize): saves the launch gap of the pair
+        PF_CUDA(launch_pdl(k_mm_write, dim3(grid, 2), dim3(256), 0, ws.stream, P));
     }
     if (ws.ev_b) cudaEventRecord(ws.ev_b, ws.stream);
-    k_mm_finish<<<2, 256, 0, ws.stream>>>(P);
+    PF_CUDA(launch_pdl(k_mm_finish, dim3(2), dim3(256), 0, ws.stream, P));
     ws.launches += 5;
     PF_CUDA(cudaGetLastError());
     return PF_OK;

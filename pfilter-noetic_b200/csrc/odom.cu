@@ -55,6 +55,7 @@ __global__ void k_odom_reset(OdomShared* sh, LmState* S) {
 struct GuardSpec { const int* n_map[3]; int min_pts[3]; int count; };
 
 __global__ void k_predict(OdomShared* sh, LmState* S, GuardSpec G) {
+    PF_PDL_ENTRY();
     if (threadIdx.x != 0) return;
     {   // laserCloudCornerMap->points.size() > 10 && laserCloudSurfMap->points.size() > 50 (:247); BPF: beam, pillar > 10, facade > 50 (:720)
         int ok = 1;
@@ -97,6 +98,7 @@ struct AppendParams {
 
 // odom <- (q_w_curr, t_w_curr) (:278-280) and addPointsToMap's append loop (:592-604)
 __global__ void __launch_bounds__(256) k_append(AppendParams A) {
+    PF_PDL_ENTRY();
     const int kind = blockIdx.y;
     __shared__ double s_pose[7];
     if (threadIdx.x < 7) s_pose[threadIdx.x] = A.S->x[threadIdx.x];
@@ -142,6 +144,7 @@ __global__ void __launch_bounds__(256) k_init_map(InitParams I) {
 
 __global__ void k_check_map_cap(const int* n_map0, const int* n_map1, int slot0, int slot1, int cap, OdomShared* sh, int last_pair,
                                 const unsigned* merge_err) {
+    PF_PDL_ENTRY();
     if (threadIdx.x != 0) return;
     if (*n_map0 > cap || *n_map1 > cap) atomicOr(&sh->err, 1);
     if (*merge_err) atomicOr(&sh->err, (int)(*merge_err & 30u));
@@ -413,7 +416,7 @@ int record_update(pf_odom* h, const float4* const feat[kKinds], const int* const
         GuardSpec G{};
         G.count = h->nk;
         for (int k = 0; k < h->nk; ++k) { G.n_map[k] = h->d_nmap[cur] + k; G.min_pts[k] = h->min_map[k]; }
-        k_predict<<<1, 32, 0, h->stream>>>(h->d_sh, h->d_state, G);
+        PF_CUDA(launch_pdl(k_predict, dim3(1), dim3(32), 0, h->stream, h->d_sh, h->d_state, G));
         ws.launches += 1;
     }
     // search grids over the current maps: forked onto the second stream (captured as a parallel branch of the graph)
@@ -491,7 +494,7 @@ int record_update(pf_odom* h, const float4* const feat[kKinds], const int* const
         P.write_pose = p == 0;
         P.sh = h->d_sh; P.S = h->d_state; P.map_cap = h->bufcap;
         P.pose_hist = h->d_pose_hist;
-        k_append<<<dim3(kSMs, 2), 256, 0, h->stream>>>(P);
+        PF_CUDA(launch_pdl(k_append, dim3(kSMs, 2), dim3(256), 0, h->stream, P));
         ws.launches += 1;
     }
     for (int p = 0; p < h->npairs; ++p) {
@@ -516,7 +519,7 @@ int record_update(pf_odom* h, const float4* const feat[kKinds], const int* const
             capa[j] = mub[k];
         }
         PF_CHECK(map_merge(ws, M, capb[0], capb[1], capa[0], capa[1]));
-        k_check_map_cap<<<1, 32, 0, h->stream>>>(h->d_nmap[nxt] + ka, h->d_nmap[nxt] + kb, ka, kb, h->mcap, h->d_sh, p == h->npairs - 1 ? 1 : 0, map_merge_error_word(ws));
+        PF_CUDA(launch_pdl(k_check_map_cap, dim3(1), dim3(32), 0, h->stream, h->d_nmap[nxt] + ka, h->d_nmap[nxt] + kb, ka, kb, h->mcap, h->d_sh, p == h->npairs - 1 ? 1 : 0, map_merge_error_word(ws)));
         ws.launches += 1;
     }
     PF_CUDA(cudaGetLastError());

@@ -161,6 +161,7 @@ __global__ void __launch_bounds__(kSortThreads) k_sort_coop(uint32_t* keys0, uin
 // (warp-private digit counters keep the sort stable).
 __global__ void __launch_bounds__(1024) k_sort_small(uint32_t* keys0, uint32_t* vals0, uint32_t* keys1, uint32_t* vals1,
                                                      const int* __restrict__ n_dev, int passes, int vals_iota) {
+    PF_PDL_ENTRY();
     const int n = *n_dev;
     if (n > kSmallSort || n <= 0) return;      // large inputs are sorted by k_sort_coop
     __shared__ unsigned wc[32][kRadix];
@@ -233,6 +234,7 @@ __global__ void __launch_bounds__(1024) k_sort_small(uint32_t* keys0, uint32_t* 
 }
 
 __global__ void k_begin_step(unsigned int* ctrl) {
+    PF_PDL_ENTRY();
     if (threadIdx.x == 0) ctrl[0] += 1;
     else if (threadIdx.x < kCtrlWords) ctrl[threadIdx.x] = 0;
 }
@@ -263,7 +265,7 @@ void workspace_destroy(Workspace& ws) {
 }
 
 int workspace_begin_step(Workspace& ws) {
-    k_begin_step<<<1, kCtrlWords, 0, ws.stream>>>(ws.ctrl);
+    PF_CUDA(launch_pdl(k_begin_step, dim3(1), dim3(kCtrlWords), 0, ws.stream, ws.ctrl));
     ws.launches += 1;
     PF_CUDA(cudaGetLastError());
     return PF_OK;
@@ -284,7 +286,7 @@ int radix_sort(Workspace& ws, const int* n_dev, int n_cap, int passes, bool vals
     }
     if (nb > ws.coop_blocks) nb = ws.coop_blocks;
     int iota = vals_iota ? 1 : 0, nb_cap = ws.nb_cap;
-    k_sort_small<<<1, 1024, 0, ws.stream>>>(ws.keys[0], ws.vals[0], ws.keys[1], ws.vals[1], n_dev, passes, iota);
+    PF_CUDA(launch_pdl(k_sort_small, dim3(1), dim3(1024), 0, ws.stream, ws.keys[0], ws.vals[0], ws.keys[1], ws.vals[1], n_dev, passes, iota));
     ws.launches += 1;
     void* args[] = {&ws.keys[0], &ws.vals[0], &ws.keys[1], &ws.vals[1], (void*)&n_dev, &passes, &iota, &ws.hist, &ws.totals, &nb_cap};
     PF_CUDA(cudaLaunchCooperativeKernel((const void*)k_sort_coop, dim3(nb), dim3(kSortThreads), args, 0, ws.stream));

@@ -237,6 +237,7 @@ __device__ __noinline__ void lm_advance(const LmParams& P, LmState* S, const dou
 // Nothing returns to the host; rank 0 writes the state back at the end.
 __global__ void __cluster_dims__(kLmCluster, 1, 1) __launch_bounds__(kLmThreads) k_lm_solve(LmParams P, const double* pose_src, int first_pass,
                                                                                                 int list_cap) {
+    PF_PDL_ENTRY();
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
     const unsigned rank = cluster.block_rank();
@@ -382,7 +383,7 @@ int lm_solve(cudaStream_t stream, const LmParams& P, const double* pose_src, int
         PF_CUDA(cudaFuncSetAttribute(k_lm_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem > 48 * 1024 ? smem : 48 * 1024)));
         smem_set = smem > 48 * 1024 ? smem : 48 * 1024;
     }
-    k_lm_solve<<<kLmCluster, kLmThreads, smem, stream>>>(P, pose_src, first_pass, list_cap);
+    PF_CUDA(launch_pdl(k_lm_solve, dim3(kLmCluster), dim3(kLmThreads), smem, stream, P, pose_src, first_pass, list_cap));
     if (launches) *launches += 1;
     PF_CUDA(cudaGetLastError());
     return PF_OK;
