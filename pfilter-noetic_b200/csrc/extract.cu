@@ -159,6 +159,7 @@ __constant__ float c_ring_band[3][kMaxLines][2];
 // and the tile summary (one ring only -> "pure"; else the set of rings present) from registers and warp votes alone.
 template <int LINES, bool kLabel>
 __global__ void __launch_bounds__(kClassifyThreads) k_ring_classify(ExtractParams P, float gate_lo, float gate_hi) {
+    PF_PDL_ENTRY();
     const int s = blockIdx.y, lane = threadIdx.x & 31;
     const int tile = blockIdx.x * (kClassifyThreads / 32) + (threadIdx.x >> 5);
     if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
@@ -217,6 +218,7 @@ __global__ void __launch_bounds__(kClassifyThreads) k_ring_classify(ExtractParam
 }
 
 __global__ void k_set_int(int* p, int v) {
+    PF_PDL_ENTRY();
     if (threadIdx.x == 0) *p = v;
 }
 
@@ -231,6 +233,7 @@ __device__ __forceinline__ int count_bytes_eq(unsigned x, unsigned b) {
 // One warp per (scan, ring): ring position at which every tile of the ring's tile range starts (exclusive prefix of the
 // per-tile point counts) and the ring's size, so that any sector of the ring can be located without touching the others.
 __global__ void __launch_bounds__(256) k_ring_index(ExtractParams P) {
+    PF_PDL_ENTRY();
     const int lane = threadIdx.x & 31;
     const int item = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (item >= P.batch * P.num_lines) return;
@@ -525,6 +528,7 @@ __device__ __noinline__ int sector_pick_large(const float4* sp, unsigned* scand,
 // the earlier rings' words plus the earlier sectors of its own ring: the compacted clouds are written once, from shared memory.
 template <bool kLabel>
 __global__ void __launch_bounds__(kSecWarps * 32, 14) k_sector_extract(ExtractParams P) {
+    PF_PDL_ENTRY();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
     const int S = P.scap;
@@ -913,7 +917,7 @@ static int extract_launch(pf_extract* h, const float4* d_xyzi, const int* d_n, i
         P.min_d = h->lidar.min_distance; P.max_d = h->lidar.max_distance;
         {
             const dim3 grid(div_up(tiles, kClassifyThreads / 32), nb);
-            auto launch = [&](auto kern) { kern<<<grid, kClassifyThreads, 0, h->stream>>>(P, h->gate_lo, h->gate_hi); };
+            auto launch = [&](auto kern) { launch_pdl(kern, grid, dim3(kClassifyThreads), 0, h->stream, P, h->gate_lo, h->gate_hi); };
             const int nl = h->lidar.num_lines;
             if (d_label) {
                 if (nl == 64) launch(k_ring_classify<64, true>);
@@ -925,14 +929,15 @@ static int extract_launch(pf_extract* h, const float4* d_xyzi, const int* d_n, i
                 else launch(k_ring_classify<16, false>);
             }
         }
-        k_ring_index<<<div_up(nb * h->lidar.num_lines, 8), 256, 0, h->stream>>>(P);
+        launch_pdl(k_ring_index, dim3(div_up(nb * h->lidar.num_lines, 8)), dim3(256), 0, h->stream, P);
         const int want = div_up(nb * h->lidar.num_lines * kSectors, kSecWarps);
         if (d_label) {
             P.warp_smem = h->warp_smem_label;
-            k_sector_extract<true><<<want < h->ctas_label ? want : h->ctas_label, kSecWarps * 32, (size_t)kSecWarps * h->warp_smem_label, h->stream>>>(P);
+            launch_pdl(k_sector_extract<true>, dim3(want < h->ctas_label ? want : h->ctas_label), dim3(kSecWarps * 32), (size_t)kSecWarps * h->warp_smem_label,
+                       h->stream, P);
         } else {
             P.warp_smem = h->warp_smem;
-            k_sector_extract<false><<<want < h->ctas ? want : h->ctas, kSecWarps * 32, (size_t)kSecWarps * h->warp_smem, h->stream>>>(P);
+            launch_pdl(k_sector_extract<false>, dim3(want < h->ctas ? want : h->ctas), dim3(kSecWarps * 32), (size_t)kSecWarps * h->warp_smem, h->stream, P);
         }
         h->launches += 3;
     }
@@ -1110,7 +1115,7 @@ int pf_extract_enqueue_single(pf_extract* h, const float* xyzi, int n, int devic
     PF_REQUIRE(h && (xyzi || n == 0), "null argument");
     PF_REQUIRE(n >= 0 && n <= h->stride, "scan of %d points exceeds max_points %d", n, h->stride);
     PF_CUDA(cudaSetDevice(h->device));
-    k_set_int<<<1, 32, 0, h->stream>>>(h->d_n, n);
+    PF_CUDA(launch_pdl(k_set_int, dim3(1), dim3(32), 0, h->stream, h->d_n, n));
     h->launches += 1;
     const float4* src = h->d_pts;
     if (device_input) {

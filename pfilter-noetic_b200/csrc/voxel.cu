@@ -42,6 +42,7 @@ __device__ __forceinline__ bool in_crop(const VoxParams& P, const Pt& p) {
 
 // state slot layout (unsigned words): [0..5] cloud0 {~min xyz, max xyz}, [6..11] cloud1, [12..13] nvalid, [14] n_total, [15] err
 __global__ void __launch_bounds__(256) k_vox_bounds(VoxParams P) {
+    PF_PDL_ENTRY();
     const VoxCloud& c = P.c[blockIdx.y];
     const int n = c.n_in ? *c.n_in : 0;
     unsigned mn[3] = {0u, 0u, 0u}, mx[3] = {0u, 0u, 0u};   // mn holds ~ord(min): both reduce with max
@@ -96,6 +97,7 @@ __device__ __forceinline__ VoxGrid vox_grid(const VoxParams& P, int cloud, float
 }
 
 __global__ void __launch_bounds__(256) k_vox_keys(VoxParams P, uint32_t* __restrict__ keys) {
+    PF_PDL_ENTRY();
     const int cloud = blockIdx.y;
     const VoxCloud& c = P.c[cloud];
     const int n = c.n_in ? *c.n_in : 0;
@@ -179,6 +181,7 @@ __device__ __forceinline__ bool vox_finish(const VoxSum& a, const VoxParams& P, 
 constexpr int kVoxShortRun = 16;
 __global__ void __launch_bounds__(256) k_vox_reduce(VoxParams P, const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals,
                                                     unsigned long long* status, int status_stride, unsigned* ctrl, int ticket_word, int site) {
+    PF_PDL_ENTRY();
     const int cloud = blockIdx.y;
     const VoxCloud& c = P.c[cloud];
     __shared__ int s_tile, s_nlong;
@@ -290,16 +293,16 @@ int voxelize(Workspace& ws, const VoxParams& P_in, int slot, int cap0, int cap1)
     int nblk = div_up(capmax, 256 * 4);
     if (nblk > 4 * kSMs) nblk = 4 * kSMs;
     if (nblk < 1) nblk = 1;
-    k_vox_bounds<<<dim3(nblk, 2), 256, 0, ws.stream>>>(P);
-    k_vox_keys<<<dim3(nblk, 2), 256, 0, ws.stream>>>(P, ws.keys[0]);
+    PF_CUDA(launch_pdl(k_vox_bounds, dim3(nblk, 2), dim3(256), 0, ws.stream, P));
+    PF_CUDA(launch_pdl(k_vox_keys, dim3(nblk, 2), dim3(256), 0, ws.stream, P, ws.keys[0]));
     ws.launches += 2;
     const int* n_total = reinterpret_cast<const int*>(P.state) + 14;
     int rb = 0;
     PF_CHECK(radix_sort(ws, n_total, cap, 4, true, &rb));
     int tiles = div_up(capmax, 256);
     if (tiles > 6 * kSMs) tiles = 6 * kSMs;
-    k_vox_reduce<<<dim3(tiles < 1 ? 1 : tiles, 2), 256, 0, ws.stream>>>(P, ws.keys[rb], ws.vals[rb], ws.scan_status, ws.status_stride, ws.ctrl,
-                                                                       1 + 2 * slot, slot);
+    PF_CUDA(launch_pdl(k_vox_reduce, dim3(tiles < 1 ? 1 : tiles, 2), dim3(256), 0, ws.stream, P, ws.keys[rb], ws.vals[rb], ws.scan_status,
+                       ws.status_stride, ws.ctrl, 1 + 2 * slot, slot));
     ws.launches += 1;
     PF_CUDA(cudaGetLastError());
     return PF_OK;
