@@ -249,6 +249,8 @@ def extra_kernel_legs(capi, dev_index):
           "traffic": _traffic().get("k9", {}).get("bytes_per_update"),
           "ms_stream_kernel": t["ms_stream"], "ms_whole_update": t["ms_total"],
           "frac_whole_update": bytes_k9 / (t["ms_total"] * 1e-3) / 1e9 / peak}
+    if os.environ.get("PF_EXTRA_ONLY") == "k9":      # quick iteration on the map update alone (tools/bench_extra.py)
+        return {"k9_map_merge": k9}
     nq = 1_000_000
     sel = rng.integers(0, len(m0), nq)
     q = np.zeros((nq, 4), np.float32)
