@@ -158,7 +158,9 @@ __global__ void __launch_bounds__(kSortThreads) k_sort_coop(uint32_t* keys0, uin
 // Small inputs (n <= kSmallSort): the whole sort in ONE CTA of 1024 threads, passes separated by __syncthreads only.  The frame
 // loop sorts a few thousand new map points every frame; four cooperative passes with two grid barriers each cost ~50 us for
 // them, this kernel ~10 us.  Warp w owns the contiguous keys [256 w, 256 w + 256) and ranks them in 8 ordered rounds of 32
-// (warp-private digit counters keep the sort stable).
+// (warp-private digit counters keep the sort stable).  Between the passes keys and values live in shared memory (128 KB
+// ping-pong): only the first pass reads and only the last pass writes global memory.
+constexpr size_t kSmallSortSmem = sizeof(unsigned) * 4 * kSmallSort;
 __global__ void __launch_bounds__(1024) k_sort_small(uint32_t* keys0, uint32_t* vals0, uint32_t* keys1, uint32_t* vals1,
                                                      const int* __restrict__ n_dev, int passes, int vals_iota) {
     PF_PDL_ENTRY();
@@ -167,12 +169,14 @@ __global__ void __launch_bounds__(1024) k_sort_small(uint32_t* keys0, uint32_t* 
     __shared__ unsigned wc[32][kRadix];
     __shared__ unsigned dbase[kRadix];
     __shared__ unsigned wtot[8];
+    extern __shared__ unsigned s_pp[];          // [2][2][kSmallSort]: keys and values ping-pong between the passes in shared memory
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-    for (int p = 0; p < passes; ++p) {
-        const uint32_t* kin = (p & 1) ? keys1 : keys0;
-        const uint32_t* vin = (p & 1) ? vals1 : vals0;
-        uint32_t* kout = (p & 1) ? keys0 : keys1;
-        uint32_t* vout = (p & 1) ? vals0 : vals1;
+    for (int p = 0; p < passes; ++p) {          // pass 0 reads the global input, the last pass writes the global output
+        const uint32_t* kin = p == 0 ? keys0 : s_pp + ((p - 1) & 1) * 2 * kSmallSort;
+        const uint32_t* vin = p == 0 ? vals0 : s_pp + ((p - 1) & 1) * 2 * kSmallSort + kSmallSort;
+        const bool last = p + 1 == passes;
+        uint32_t* kout = last ? ((p & 1) ? keys0 : keys1) : s_pp + (p & 1) * 2 * kSmallSort;
+        uint32_t* vout = last ? ((p & 1) ? vals0 : vals1) : s_pp + (p & 1) * 2 * kSmallSort + kSmallSort;
         const int shift = p * kRadixBits;
 #pragma unroll
         for (int k = 0; k < 8; ++k) wc[(tid >> 8) + 4 * k][tid & 255] = 0;
@@ -229,7 +233,7 @@ __global__ void __launch_bounds__(1024) k_sort_small(uint32_t* keys0, uint32_t* 
                 vout[pos] = val[k];
             }
         }
-        __syncthreads();      // global writes of this CTA are visible to it after the barrier
+        __syncthreads();
     }
 }
 
@@ -240,6 +244,7 @@ __global__ void k_begin_step(unsigned int* ctrl) {
 }
 
 int workspace_create(Workspace& ws, int cap, cudaStream_t stream) {
+    PF_CUDA(cudaFuncSetAttribute(k_sort_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmallSortSmem));   // per device
     ws.stream = stream;
     ws.cap = cap;
     ws.nb_cap = div_up(cap, kSortTile);
@@ -286,7 +291,7 @@ int radix_sort(Workspace& ws, const int* n_dev, int n_cap, int passes, bool vals
     }
     if (nb > ws.coop_blocks) nb = ws.coop_blocks;
     int iota = vals_iota ? 1 : 0, nb_cap = ws.nb_cap;
-    PF_CUDA(launch_pdl(k_sort_small, dim3(1), dim3(1024), 0, ws.stream, ws.keys[0], ws.vals[0], ws.keys[1], ws.vals[1], n_dev, passes, iota));
+    PF_CUDA(launch_pdl(k_sort_small, dim3(1), dim3(1024), kSmallSortSmem, ws.stream, ws.keys[0], ws.vals[0], ws.keys[1], ws.vals[1], n_dev, passes, iota));
     ws.launches += 1;
     void* args[] = {&ws.keys[0], &ws.vals[0], &ws.keys[1], &ws.vals[1], (void*)&n_dev, &passes, &iota, &ws.hist, &ws.totals, &nb_cap};
     PF_CUDA(cudaLaunchCooperativeKernel((const void*)k_sort_coop, dim3(nb), dim3(kSortThreads), args, 0, ws.stream));
