@@ -107,10 +107,26 @@ __device__ __forceinline__ unsigned long long l2_policy_evict_last() {
     asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
     return pol;
 }
+__device__ __forceinline__ unsigned long long l2_policy_evict_normal() {
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ unsigned long long l2_policy_evict_unchanged() {
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_unchanged.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+// 0 = evict_last, 1 = evict_normal, 2 = evict_first, 3 = evict_unchanged
+__device__ __forceinline__ unsigned long long l2_policy_evict_first();
+__device__ __forceinline__ unsigned long long l2_policy_by_code(int c);
 __device__ __forceinline__ unsigned long long l2_policy_evict_first() {
     unsigned long long pol;
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
     return pol;
+}
+__device__ __forceinline__ unsigned long long l2_policy_by_code(int c) {
+    return c == 0 ? l2_policy_evict_last() : c == 1 ? l2_policy_evict_normal() : c == 2 ? l2_policy_evict_first() : l2_policy_evict_unchanged();
 }
 __device__ __forceinline__ float4 ld_f4_l2hint(const void* p, unsigned long long pol) {
     float4 v;

@@ -272,7 +272,8 @@ __global__ void __launch_bounds__(256) k_mm_tiles(MapMergeParams P) {
 // Streaming pass 1 (count): how many points every tile of the sorted map part will emit -- its own points that survive the
 // crop box and the delete rule, corrected by the matched voxels finished in k_mm_heads, plus the inserts that fall into the
 // tile.  No shared memory, no barrier: 16 B read per map point, one warp-aggregated atomic per warp and tile.
-__global__ void __launch_bounds__(256) k_mm_count(MapMergeParams P) {
+template <bool PREFETCH>
+__global__ void __launch_bounds__(256, PREFETCH ? 5 : 8) k_mm_count(MapMergeParams P) {
     PF_PDL_ENTRY();
     const int cloud = blockIdx.y;
     const MapMergeCloud& c = P.c[cloud];
@@ -285,7 +286,7 @@ __global__ void __launch_bounds__(256) k_mm_count(MapMergeParams P) {
     const CropBox box = crop_of(P.center);
     const int tid = threadIdx.x;
     int cta_part = 0;
-    const unsigned long long keep_in_l2 = l2_policy_evict_last();
+    const unsigned long long keep_in_l2 = l2_policy_by_code(P.hint % 10);
     auto load_tile = [&](int t, Pt (&q)[4]) {
         const int base = t * kMergeTile;
 #pragma unroll
@@ -296,15 +297,18 @@ __global__ void __launch_bounds__(256) k_mm_count(MapMergeParams P) {
         }
     };
     Pt p[4];
-    if (R.lo < R.hi) load_tile(R.lo, p);
+    if (PREFETCH && R.lo < R.hi) load_tile(R.lo, p);
     for (int t = R.lo; t < R.hi; ++t) {
         Pt nxt[4];
-        if (t + 1 < R.hi) load_tile(t + 1, nxt);       // the next tile's loads are in flight while this one is counted
+        if (PREFETCH) { if (t + 1 < R.hi) load_tile(t + 1, nxt); }      // the next tile's loads are in flight while this one is counted
+        else load_tile(t, p);
         int v = 0;
 #pragma unroll
         for (int k = 0; k < 4; ++k) v += (in_box(box, p[k]) && single_point_kept(P, p[k].rgba)) ? 1 : 0;
+        if (PREFETCH) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) p[k] = nxt[k];
+            for (int k = 0; k < 4; ++k) p[k] = nxt[k];
+        }
         const int mLo = tm[t], mHi = tm[t + 1];
         for (int h = mLo + tid; h < mHi; h += 256) v += P.s.m_delta[lbase + h];
         if (tid == 0) v += ti[t + 1] - ti[t];
@@ -361,7 +365,8 @@ __global__ void __launch_bounds__(256, 8) k_mm_write(MapMergeParams P) {
         running = total;                        // inclusive of this CTA: output end of its last tile
     }
     if (R.hi == R.ntiles && tid == 0) *c.n_sorted_out = running;
-    const unsigned long long use_once = l2_policy_evict_first();
+    const unsigned long long use_once = l2_policy_by_code(P.hint / 10 % 10);
+    const unsigned long long out_pol = l2_policy_by_code(P.hint / 100 % 10);
     for (int tile = R.hi - 1, par = 0; tile >= R.lo; --tile, par ^= 1) {
         const int emit = agg[tile];
         const int gbase = running - emit;
@@ -414,7 +419,7 @@ __global__ void __launch_bounds__(256, 8) k_mm_write(MapMergeParams P) {
                 const int i = base + k * 256 + tid;
                 int pos = gbase + s_segpre[par][k * 8 + w] + __popc(mask[k] & lanemask_lt());
                 if (iHi > iLo) pos += lower_bound_i(i_ra, iLo, iHi, i + 1) - iLo;      // inserts in front of this point
-                st_f4_l2hint(c.out + pos, *reinterpret_cast<const float4*>(&p[k]), use_once);
+                st_f4_l2hint(c.out + pos, *reinterpret_cast<const float4*>(&p[k]), out_pol);
             }
         }
         const int kept = s_segpre[par][32];
@@ -684,6 +689,11 @@ void map_merge_scratch_destroy(MapMergeScratch& s) {
 int map_merge(Workspace& ws, const MapMergeParams& P_in, int capB0, int capB1, int capA0, int capA1) {
     MapMergeParams P = P_in;
     P.state = ws.ctrl + kSlotBase + 3 * kSlotWords;
+    // L2 eviction priorities of the two streaming passes as decimal digits (count loads, write loads, write stores; 0 = evict_last,
+    // 1 = normal, 2 = evict_first, 3 = unchanged).  Measured on an 8.2 M-point map (profiles/k9_l2_hint_sweep_r1.txt): marking
+    // the count pass's lines evict_first beats keeping them for the write pass (evict_last) by 5 %
+    static const int hint_env = [] { const char* e = getenv("PF_MM_HINT"); return e ? atoi(e) : 212; }();
+    P.hint = hint_env;
     const int capB = capB0 + capB1;
     PF_REQUIRE(capB <= ws.cap, "map_merge: %d unsorted points exceed workspace capacity %d", capB, ws.cap);
     PF_REQUIRE(capB0 <= P.s.cap && capB1 <= P.s.cap, "map_merge: %d / %d unsorted points exceed the scratch capacity %d", capB0, capB1, P.s.cap);
@@ -711,7 +721,11 @@ int map_merge(Workspace& ws, const MapMergeParams& P_in, int capB0, int capB1, i
         PF_CUDA(launch_pdl(k_mm_single, dim3(fgrid, 2), dim3(256), 0, ws.stream, P, P.s.fstatus, ws.ctrl));
         ws.launches += 4;
     } else {
-        PF_CUDA(launch_pdl(k_mm_count, dim3(grid, 2), dim3(256), 0, ws.stream, P));
+        // count pass: 8 CTAs per SM at 32 registers without a register prefetch measured 3 % faster than 5 CTAs with one
+        // (PF_MM_COUNT=0 selects the prefetching form)
+        static const int count_variant = [] { const char* e = getenv("PF_MM_COUNT"); return e ? atoi(e) : 1; }();
+        if (count_variant == 1) PF_CUDA(launch_pdl(k_mm_count<false>, dim3(grid, 2), dim3(256), 0, ws.stream, P));
+        else PF_CUDA(launch_pdl(k_mm_count<true>, dim3(grid, 2), dim3(256), 0, ws.stream, P));
         // same grid: same tile partition.  The write pass is launched with a programmatic edge (its CTAs are scheduled while the
         // count pass drains and wait in cudaGridDependencySynchronize): saves the launch gap of the pair
         PF_CUDA(launch_pdl(k_mm_write, dim3(grid, 2), dim3(256), 0, ws.stream, P));

@@ -48,6 +48,7 @@ struct MapMergeParams {
     int k_new; float theta_p; int theta_max;
     MapMergeScratch s;
     unsigned* state;         // filled by map_merge(): state slot
+    int hint;                // filled by map_merge(): L2 eviction-priority experiment switch (PF_MM_HINT)
 };
 
 // capB0 / capB1: upper bounds of (n_app - n_sorted); capA0 / capA1: upper bounds of n_sorted.
