@@ -223,7 +223,7 @@ def roofline_leg(pfb, capi, torch, scans, dev):
             "achieved": achieved, "peak": peak, "peak_source": how, "unit": "GB/s", "frac": achieved / peak,
             "traffic": tr.get("bytes_per_launch_group"), "algorithmic_bytes": 32.0 * pts,
             "limiter": "instruction issue, not DRAM: ~290 warp instructions per 32 points in k_sector_extract (greedy pick 1/3, curvature 1/4) at "
-                       "2.4-2.6 IPC with 28 resident warps per SM; k_ring_classify runs at ~50 % of DRAM peak (profiles/k1_extract_r1v_ncu_summary.txt)",
+                       "2.4-2.6 IPC with 28 resident warps per SM; k_ring_classify runs at 78 % of DRAM peak (profiles/k1_extract_r1z_ncu_summary.txt)",
             "kernel_share_of_group": tr.get("share_of_group_time"),
             "bytes_per_point": 32, "achieved_io_bytes": (16.0 * pts + 16.0 * out_pts) / (ms * 1e-3) / 1e9,
             "ms_per_launch_group": ms, "launches_per_group": launches, "scans_per_s_extract_only": batch / ms * 1e3}
