@@ -158,14 +158,13 @@ __global__ void __launch_bounds__(256) k_mm_heads(MapMergeParams P, const uint32
         if (tile * 256 >= nv) return;
         const int e = s0 + tile * 256 + threadIdx.x;
         bool matched = false, ins = false;
-        int rA = 0, len = 0, delta = 0;
+        int rA = 0, delta = 0;
         Pt o{0.f, 0.f, 0.f, 0u};
         if (e < end) {
             const unsigned key = keys[e];
             if (e == s0 || keys[e - 1] != key) {
                 int e2 = e + 1;
                 while (e2 < end && keys[e2] == key) ++e2;
-                len = e2 - e;
                 const long long k64 = key64_of_key30(key);
                 int lo = 0, hi = mA;
                 while (lo < hi) {

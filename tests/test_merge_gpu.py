@@ -5,6 +5,10 @@ The merge consumes a map whose first part is already sorted by voxel key (what t
 extra points, and must produce the same voxels, centroids (bit-exact: canonical summation order) and counters as
 re-sorting everything; only the position of "exceptions" (centroids that float rounding pushed out of their voxel) differs:
 they trail the sorted part.  So maps are compared as multisets, and the sorted part must be strictly ascending in key."""
+import os
+import subprocess
+import sys
+
 import numpy as np
 import pytest
 
@@ -146,6 +150,17 @@ def test_merge_adversarial_small_inputs(capi, oracle, seed):
     m0s, exc = _split_sorted(m0, leaf)
     assert len(exc) <= 4
     _check(capi, oracle, m0s, np.concatenate([exc, extra]), center1, leaf, prm)
+
+
+def test_merge_single_pass_variant():
+    """PF_MM_VARIANT=1 (k_mm_single: one streaming pass with a decoupled look-back) must produce the same maps as the default
+    count pass + write pass.  The switch is read once per process, so the parity tests of this file run again in a child."""
+    env = dict(os.environ, PF_MM_VARIANT="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-m", "gpu", "-p", "no:cacheprovider",
+                        "-k", "matches_full or chain_of or large_map or adversarial_small or unsorted_start or empty_inputs"],
+                       env=env, capture_output=True, text=True, timeout=900, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-1000:]
+    assert " passed" in r.stdout
 
 
 @pytest.mark.parametrize("seed", range(4))
