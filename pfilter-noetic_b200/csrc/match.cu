@@ -19,7 +19,10 @@ namespace pf {
 // lane g fits the geometry of query g.  The fp64 line / plane fit is ~3000 dependent instructions; run redundantly by all 32
 // lanes of a warp per query it made the kernel bound by fp64 issue (ncu: 37 us for 7.6 k queries); packed one query per lane it
 // costs a fraction of that pipe time per query.
-constexpr int kAssocBatch = 4;
+#ifndef PF_ASSOC_BATCH
+#define PF_ASSOC_BATCH 4
+#endif
+constexpr int kAssocBatch = PF_ASSOC_BATCH;
 __global__ void __launch_bounds__(256) k_assoc_match(AssocParams P) {
     PF_PDL_ENTRY();
     const int kind = blockIdx.y;

@@ -6,7 +6,7 @@
 //   surf (SurfNormAnalyticCostFunction, :56-78):                        r = n . lp + d,  J = n^T [ -[lp]x  I ]
 //   applies ceres::HuberLoss(0.1) with Ceres' corrector (rho'' <= 0 -> scale r and J by sqrt(rho')), accumulates the 21
 //   upper entries of J^T J, the 6 of J^T r and the cost in fp64 registers, reduces by warp shuffles + shared memory to one
-//   partial per CTA; rank 0 of the 8-CTA cluster sums the partials in a fixed order through distributed shared memory
+//   partial per CTA; every CTA of the 12-CTA cluster sums the partials in a fixed order through distributed shared memory
 //   (deterministic) and runs the Levenberg-Marquardt state machine, so a whole solve (<= 5 evaluations) is one launch
 //   and nothing returns to the host.
 #include <cooperative_groups.h>
@@ -378,10 +378,19 @@ int lm_solve(cudaStream_t stream, const LmParams& P, const double* pose_src, int
     const size_t smem = sizeof(int) * (size_t)list_cap;
     PF_REQUIRE(P.nsrc >= 1 && P.nsrc <= kLmMaxSrc, "lm_solve: %d residual sources", P.nsrc);
     PF_REQUIRE(smem <= 160 * 1024, "lm_solve: %d residual candidates per CTA exceed the solver's shared-memory list", list_cap);
-    static size_t smem_set = 0;
-    if (smem > smem_set) {
+    // function attributes are per device: a process may hold handles on several
+    int dev = 0;
+    PF_CUDA(cudaGetDevice(&dev));
+    static size_t smem_set[64] = {};
+    static bool cluster_set[64] = {};
+    const int slot = dev & 63;
+    if (kLmCluster > 8 && !cluster_set[slot]) {       // more than the portable cluster size
+        PF_CUDA(cudaFuncSetAttribute(k_lm_solve, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        cluster_set[slot] = true;
+    }
+    if (smem > smem_set[slot]) {
         PF_CUDA(cudaFuncSetAttribute(k_lm_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem > 48 * 1024 ? smem : 48 * 1024)));
-        smem_set = smem > 48 * 1024 ? smem : 48 * 1024;
+        smem_set[slot] = smem > 48 * 1024 ? smem : 48 * 1024;
     }
     PF_CUDA(launch_pdl(k_lm_solve, dim3(kLmCluster), dim3(kLmThreads), smem, stream, P, pose_src, first_pass, list_cap));
     if (launches) *launches += 1;

@@ -48,8 +48,14 @@ struct LmParams {
     int weight_type;          // 0, 1, 2, 12: residual weights (src/odomEstimationClass.cpp:389-423, src/lidarOptimization.cpp:25-28, :62-63)
 };
 
-constexpr int kLmCluster = 8;    // CTAs of the solver cluster (8 SMs, distributed shared memory reduction)
-constexpr int kLmThreads = 256;  // 2048 threads; 255 registers per thread keep the serial state machine out of local memory
+#ifndef PF_LM_CLUSTER
+#define PF_LM_CLUSTER 12
+#endif
+#ifndef PF_LM_THREADS
+#define PF_LM_THREADS 256
+#endif
+constexpr int kLmCluster = PF_LM_CLUSTER;    // CTAs of the solver cluster (distributed shared memory reduction); 12 needs the non-portable cluster attribute, measured: 4: 2870, 8: 3125, 12: 3223, 16: 3215 scans/s
+constexpr int kLmThreads = PF_LM_THREADS;  // 255 registers per thread keep the serial state machine out of local memory
 
 // One launch = one complete solve: at most 1 + 4 evaluations (max_num_iterations = 4) and the trust-region state machine.
 // pose_src: device pose to start from (null: keep state->x); first_pass resets the outer-iteration counter.
