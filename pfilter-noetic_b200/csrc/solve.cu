@@ -116,70 +116,9 @@ __device__ void lm_finish(const LmParams& P, LmState* S, bool writer = true) {
 }
 
 // Compute the next trust-region step from (H, g) at x; invalid steps shrink the radius without an evaluation.
-#ifndef PF_LM_V
-#define PF_LM_V 0
-#endif
-#if PF_LM_V >= 2
-// the same operations in the same order as chol6_solve (math.cuh), loops left rolled: the trust-region step is run by ONE thread
-// while the cluster waits, and a straight-line copy of it costs more in instruction fetch than the rolled loops cost in local loads
-__device__ __noinline__ bool chol6_solve_rolled(const double* U21, const double* b, double* y) {
-    double L[6][6];
-    {
-        int k = 0;
-#pragma unroll 1
-        for (int i = 0; i < 6; ++i)
-#pragma unroll 1
-            for (int j = i; j < 6; ++j) { L[j][i] = U21[k]; ++k; }
-    }
-    bool ok = true;
-    double inv[6];
-#pragma unroll 1
-    for (int j = 0; j < 6; ++j) {
-        double s = L[j][j];
-#pragma unroll 1
-        for (int p = 0; p < j; ++p) s -= L[j][p] * L[j][p];
-        if (!(s > 0.0)) ok = false;
-        const double d = sqrt(s);
-        L[j][j] = d;
-        inv[j] = 1.0 / d;
-#pragma unroll 1
-        for (int i = j + 1; i < 6; ++i) {
-            double t = L[i][j];
-#pragma unroll 1
-            for (int p = 0; p < j; ++p) t -= L[i][p] * L[j][p];
-            L[i][j] = t * inv[j];
-        }
-    }
-    if (!ok) return false;
-    double z[6];
-#pragma unroll 1
-    for (int i = 0; i < 6; ++i) {
-        double s = b[i];
-#pragma unroll 1
-        for (int p = 0; p < i; ++p) s -= L[i][p] * z[p];
-        z[i] = s * inv[i];
-    }
-#pragma unroll 1
-    for (int i = 5; i >= 0; --i) {
-        double s = z[i];
-#pragma unroll 1
-        for (int p = i + 1; p < 6; ++p) s -= L[p][i] * y[p];
-        y[i] = s * inv[i];
-    }
-    bool fin = true;
-#pragma unroll 1
-    for (int i = 0; i < 6; ++i) fin = fin && isfinite(y[i]);
-    return fin;
-}
-#define PF_CHOL6 chol6_solve_rolled
-#else
-#define PF_CHOL6 chol6_solve
-#endif
-#if PF_LM_V >= 1
+// Out of line: the step is called from two places of lm_advance and run by ONE thread while the cluster waits; one copy of its
+// ~1000 straight-line fp64 instructions measured 1-2 % faster end to end than two (a rolled, local-memory Cholesky: 10 % slower).
 __device__ __noinline__ void lm_propose(const LmParams& P, LmState* S, bool writer) {
-#else
-__device__ void lm_propose(const LmParams& P, LmState* S, bool writer) {
-#endif
     while (true) {
         if (S->iter >= 4) { lm_finish(P, S, writer); return; }               // max_num_iterations = 4 (:265)
         S->iter += 1;
@@ -209,7 +148,7 @@ __device__ void lm_propose(const LmParams& P, LmState* S, bool writer) {
             for (int a = 0; a < 6; ++a) A[dpos[a]] += S->diag[a] * inv_radius;
         }
         double y[6];
-        bool ok = PF_CHOL6(A, gs, y);                              // (J^T J + D^T D) y = J^T r ; step = -y
+        bool ok = chol6_solve(A, gs, y);                              // (J^T J + D^T D) y = J^T r ; step = -y
         S->reuse_diag = 1;
         double mcc = 0;
         if (ok) {
