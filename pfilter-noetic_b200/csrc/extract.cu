@@ -1133,7 +1133,8 @@ int pf_extract_enqueue_single(pf_extract* h, const float* xyzi, int n, int devic
 
 // accessors for the device-resident hand-off (odom.cu)
 void pf_extract_device_outputs(pf_extract* h, const float4** edge, const int** n_edge, const float4** surf, const int** n_surf,
-                               cudaStream_t* stream, int* edge_cap, int* surf_cap, int* slot) {
+                               cudaStream_t* stream, int* edge_cap, int* surf_cap, int* slot, const unsigned** err_word) {
+    *err_word = h->d_ctrl + 2;
     *edge = h->out_edge(); *n_edge = h->out_n_edge(); *surf = h->out_surf(); *n_surf = h->out_n_surf(); *stream = h->stream;
     *slot = h->slot;
     *edge_cap = h->edge_stride < h->last_n ? h->edge_stride : h->last_n; *surf_cap = h->last_n;   // upper bounds of the device counts

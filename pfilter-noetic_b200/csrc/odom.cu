@@ -31,7 +31,8 @@ struct OdomShared {   // small device-resident block
     IsoDev odom, last_odom;
     double pose[7];        // pose of the last finished update (what the caller reads)
     int n_app[4];          // map sizes after appending the new points (per kind slot)
-    int err;               // bit 0: map capacity exceeded; bits 1..3: map merge (voxel coordinate range, exception capacity, internal)
+    int err;               // bit 0: map capacity exceeded; bits 1..4: map merge (voxel coordinate range, exception capacity, internal);
+                           // kErrGrid / kErrVoxel / kErrRing (primitives.cuh): search grid, VoxelGrid index space, extractor ring capacity
     int guard;             // the maps hold enough points to associate (:247 / BPF :720)
     int n_map[4];          // map sizes after the last update (read back with the pose: tight launch bounds for the next frame)
     long long frame;       // frame index this block describes
@@ -126,14 +127,18 @@ __global__ void __launch_bounds__(256) k_append(AppendParams A) {
     }
 }
 
-struct InitParams { const float4* feat[2]; const int* n_feat[2]; Pt* map[2]; int* n_map[2]; int* n_sorted[2]; int slot[2]; int map_cap; OdomShared* sh; };
+struct InitParams { const float4* feat[2]; const int* n_feat[2]; Pt* map[2]; int* n_map[2]; int* n_sorted[2]; int slot[2]; int map_cap; OdomShared* sh;
+                    const unsigned* extract_err; };
 
 // initMapWithPoints (:217-222): the raw first-frame clouds become the maps
 __global__ void __launch_bounds__(256) k_init_map(InitParams I) {
     const int kind = blockIdx.y;
     int n = *I.n_feat[kind];
     if (n > I.map_cap) { n = I.map_cap; if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(&I.sh->err, 1); }
-    if (blockIdx.x == 0 && threadIdx.x == 0) { *I.n_map[kind] = n; *I.n_sorted[kind] = 0; I.sh->n_map[I.slot[kind]] = n; I.sh->frame = 0; }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        *I.n_map[kind] = n; *I.n_sorted[kind] = 0; I.sh->n_map[I.slot[kind]] = n; I.sh->frame = 0;
+        if (I.extract_err && *I.extract_err) atomicOr(&I.sh->err, (int)kErrRing);
+    }
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const float4 f = I.feat[kind][i];
         Pt o;
@@ -142,12 +147,19 @@ __global__ void __launch_bounds__(256) k_init_map(InitParams I) {
     }
 }
 
+// Error words of everything that worked on this frame: the control blocks of the handle's three workspaces (main stream, forked grid
+// build, overlapped down-sampling; sticky + live, see ws_error_bits) and the extractor's error word when the features came from one.
+struct ErrSources { const unsigned* ctrl[3]; const unsigned* extract_err; };
+
 __global__ void k_check_map_cap(const int* n_map0, const int* n_map1, int slot0, int slot1, int cap, OdomShared* sh, int last_pair,
-                                const unsigned* merge_err) {
+                                ErrSources E) {
     PF_PDL_ENTRY();
     if (threadIdx.x != 0) return;
     if (*n_map0 > cap || *n_map1 > cap) atomicOr(&sh->err, 1);
-    if (*merge_err) atomicOr(&sh->err, (int)(*merge_err & 30u));
+    unsigned e = 0u;
+    for (int i = 0; i < 3; ++i) if (E.ctrl[i]) e |= ws_error_bits(E.ctrl[i]);
+    if (E.extract_err && *E.extract_err) e |= kErrRing;
+    if (e) atomicOr(&sh->err, (int)e);
     sh->n_map[slot0] = *n_map0;
     sh->n_map[slot1] = *n_map1;
     if (last_pair) sh->frame += 1;     // the frame this block now describes
@@ -159,7 +171,7 @@ using namespace pf;
 
 // accessors implemented in extract.cu
 void pf_extract_device_outputs(pf_extract* h, const float4** edge, const int** n_edge, const float4** surf, const int** n_surf,
-                               cudaStream_t* stream, int* edge_cap, int* surf_cap, int* slot);
+                               cudaStream_t* stream, int* edge_cap, int* surf_cap, int* slot, const unsigned** err_word);
 int pf_extract_enqueue_single(pf_extract* h, const float* xyzi, int n, int device_input, int want_label);
 
 struct pf_odom {
@@ -218,6 +230,8 @@ struct pf_odom {
     int* h_counts = nullptr;             // [16]
     double* h_iter = nullptr;            // [16*7]
     bool inited = false;
+    const unsigned* extract_err = nullptr;   // error word of the extractor whose outputs feed this handle (null: host feature clouds)
+    long long waited_upto = -1;          // newest frame whose result the caller has collected (pf_frame_wait / any blocking call)
     int optimization_count = 2;          // :198
     int last_passes = 0;
     // host-side upper bounds of the device-resident counts (launch geometry only; the kernels read the exact counts)
@@ -372,6 +386,7 @@ int enqueue_init(pf_odom* h, const float4* const feat[kKinds], const int* const 
         }
         I.map_cap = h->mcap;
         I.sh = h->d_sh;
+        I.extract_err = h->extract_err;
         k_init_map<<<dim3(2 * kSMs, 2), 256, 0, h->stream>>>(I);
         h->ws.launches += 1;
     }
@@ -519,7 +534,12 @@ int record_update(pf_odom* h, const float4* const feat[kKinds], const int* const
             capa[j] = mub[k];
         }
         PF_CHECK(map_merge(ws, M, capb[0], capb[1], capa[0], capa[1]));
-        PF_CUDA(launch_pdl(k_check_map_cap, dim3(1), dim3(32), 0, h->stream, h->d_nmap[nxt] + ka, h->d_nmap[nxt] + kb, ka, kb, h->mcap, h->d_sh, p == h->npairs - 1 ? 1 : 0, map_merge_error_word(ws)));
+        ErrSources E{};
+        E.ctrl[0] = ws.ctrl;
+        E.ctrl[1] = h->fork_grid ? h->ws_grid.ctrl : nullptr;
+        E.ctrl[2] = overlap ? h->ws_ds.ctrl : nullptr;
+        E.extract_err = h->extract_err;
+        PF_CUDA(launch_pdl(k_check_map_cap, dim3(1), dim3(32), 0, h->stream, h->d_nmap[nxt] + ka, h->d_nmap[nxt] + kb, ka, kb, h->mcap, h->d_sh, p == h->npairs - 1 ? 1 : 0, E));
         ws.launches += 1;
     }
     PF_CUDA(cudaGetLastError());
@@ -623,18 +643,26 @@ int enqueue_update(pf_odom* h, const float4* const feat_in[kKinds], const int* c
 }
 
 
+// device error bits of a frame -> status + text
+int decode_frame_error(const pf_odom* h, int err) {
+    if (err == 0) return PF_OK;
+    if (err & 1) set_error("local map exceeded max_map_points = %d", h->mcap);
+    else if (err & (int)kErrMergeMask)
+        set_error("map update failed (bits %d: 2 = voxel coordinates outside the key range, 4 = more than %d centroids left their voxel, 8 / 16 = internal)",
+                  err & (int)kErrMergeMask, kMergeExcCap);
+    else if (err & (int)kErrGrid)
+        set_error("local map extent exceeds the search grid (%d cells of 1 m): the matches of this frame are void", kGridCellCap);
+    else if (err & (int)kErrVoxel) set_error("VoxelGrid index space overflow while down-sampling the frame's features (extent / leaf too large)");
+    else if (err & (int)kErrRing) set_error("a scan ring held more points than the extractor's max_ring_points: the ring's features are missing");
+    else set_error("device error bits %d", err);
+    return PF_ERR_CAPACITY;
+}
+
 int finish_frame(pf_odom* h, double pose_out[7]) {
     PF_CUDA(cudaMemcpyAsync(h->h_sh, h->d_sh, sizeof(OdomShared), cudaMemcpyDeviceToHost, h->stream));
     PF_CUDA(cudaStreamSynchronize(h->stream));
-    if (h->h_sh->err & 1) {
-        set_error("local map exceeded max_map_points = %d", h->mcap);
-        return PF_ERR_CAPACITY;
-    }
-    if (h->h_sh->err & 30) {
-        set_error("map update failed (bits %d: 2 = map_resolution below 0.2 m, 4 = more than %d centroids left their voxel, 8 / 16 = internal)",
-                  h->h_sh->err & 30, kMergeExcCap);
-        return PF_ERR_CAPACITY;
-    }
+    h->waited_upto = h->frame - 1;
+    PF_CHECK(decode_frame_error(h, h->h_sh->err));
     if (pose_out) memcpy(pose_out, h->h_sh->pose, sizeof(double) * 7);
     if (h->inited) {
         for (int k = 0; k < kKinds; ++k) { h->map_ub[k] = h->h_sh->n_map[k]; h->map_exact[k] = h->h_sh->n_map[k]; }
@@ -732,12 +760,19 @@ extern "C" int pf_odom_destroy(pf_odom* h) {
 }
 
 namespace {
+void set_extract_err(pf_odom* h, const unsigned* w) {
+    if (h->extract_err == w) return;
+    for (int b = 0; b < 2; ++b)      // the error word is baked into the captured graphs
+        if (h->graph_exec[b]) { cudaGraphExecDestroy(h->graph_exec[b]); h->graph_exec[b] = nullptr; }
+    h->extract_err = w;
+}
 // host feature clouds -> device, then init / update
 int host_frame(pf_odom* h, int nk_expected, const float* const feat[], const int n[], bool init, double* pose_out) {
     PF_REQUIRE(h, "null handle");
     PF_REQUIRE(h->nk == nk_expected, "this handle was created for %d feature kinds, the call passes %d", h->nk, nk_expected);
     if (!init && !h->inited) { set_error("update before init_map"); return PF_ERR_STATE; }
     PF_CUDA(cudaSetDevice(h->device));
+    set_extract_err(h, nullptr);
     PF_CHECK(upload_features(h, feat, n));
     const float4* df[kKinds];
     const int* dn[kKinds];
@@ -784,7 +819,9 @@ static int process_extracted(pf_odom* h, pf_extract* ex, double pose_out[7], boo
     int ub[kKinds] = {0, 0, 0, 0};
     cudaStream_t exs;
     int slot = 0;
-    pf_extract_device_outputs(ex, &feat[0], &nf[0], &feat[1], &nf[1], &exs, &ub[0], &ub[1], &slot);
+    const unsigned* exerr = nullptr;
+    pf_extract_device_outputs(ex, &feat[0], &nf[0], &feat[1], &nf[1], &exs, &ub[0], &ub[1], &slot, &exerr);
+    set_extract_err(h, exerr);
     PF_REQUIRE(ub[1] <= h->fcap, "scan of %d points exceeds max_features %d", ub[1], h->fcap);
     PF_CUDA(cudaEventRecord(h->ev, exs));
     cudaStream_t reader = h->stream;       // the stream that reads the extractor's outputs
@@ -827,6 +864,10 @@ extern "C" int pf_frame_process_device(pf_extract* ex, pf_odom* od, const void* 
 // nodes as separate processes.  The scan buffer must stay valid (and should be pinned) until the frame has been waited for.
 extern "C" int pf_frame_submit(pf_extract* ex, pf_odom* od, const float* xyzi, int n, long long* frame_id) {
     PF_REQUIRE(ex && od, "null handle");
+    if (od->frame - 1 - od->waited_upto >= pf_odom::kRing) {     // the result slot of the oldest uncollected frame would be overwritten
+        set_error("%d frames are outstanding: pf_frame_wait for frame %lld first", pf_odom::kRing, od->waited_upto + 1);
+        return PF_ERR_STATE;
+    }
     PF_CHECK(pf_extract_enqueue_single(ex, xyzi, n, 0, 0));
     PF_CHECK(process_extracted(od, ex, nullptr, false));
     if (frame_id) *frame_id = od->frame - 1;
@@ -842,8 +883,8 @@ extern "C" int pf_frame_wait(pf_odom* h, long long frame_id, double pose_out[7])
         if (h->ring_frame[slot] != frame_id) continue;
         PF_CUDA(cudaEventSynchronize(h->ring_ev[slot]));
         const OdomShared& sh = h->h_ring[slot];
-        if (sh.err & 1) { set_error("local map exceeded max_map_points = %d", h->mcap); return PF_ERR_CAPACITY; }
-        if (sh.err & 30) { set_error("map update failed (bits %d)", sh.err & 30); return PF_ERR_CAPACITY; }
+        if (frame_id > h->waited_upto) h->waited_upto = frame_id;
+        PF_CHECK(decode_frame_error(h, sh.err));
         memcpy(pose_out, sh.pose, sizeof(double) * 7);
         return PF_OK;
     }
@@ -865,9 +906,11 @@ extern "C" int pf_odom_get_pose_history(pf_odom* h, long long first_frame, int c
     PF_REQUIRE(first_frame + count <= h->frame && h->frame - first_frame <= kPoseHist, "frames [%lld, %lld) are not in the history (have < %lld, depth %d)",
                first_frame, first_frame + count, h->frame, kPoseHist);
     PF_CUDA(cudaSetDevice(h->device));
+    // the requested slots are contiguous modulo the ring: one copy, or two when the range wraps
+    const int s0 = (int)(first_frame % kPoseHist), c0 = count < kPoseHist - s0 ? count : kPoseHist - s0;
+    if (c0 > 0) PF_CUDA(cudaMemcpyAsync(poses, h->d_pose_hist + 7 * s0, sizeof(double) * 7 * c0, cudaMemcpyDeviceToHost, h->stream));
+    if (count > c0) PF_CUDA(cudaMemcpyAsync(poses + 7 * c0, h->d_pose_hist, sizeof(double) * 7 * (count - c0), cudaMemcpyDeviceToHost, h->stream));
     PF_CUDA(cudaStreamSynchronize(h->stream));
-    for (int i = 0; i < count; ++i)
-        PF_CUDA(cudaMemcpy(poses + 7 * i, h->d_pose_hist + 7 * ((first_frame + i) % kPoseHist), sizeof(double) * 7, cudaMemcpyDeviceToHost));
     return PF_OK;
 }
 

@@ -237,9 +237,16 @@ __global__ void __launch_bounds__(1024) k_sort_small(uint32_t* keys0, uint32_t* 
     }
 }
 
+// The state slots are wiped at every step; the error bits they carry (ws_error_bits) are first folded into the sticky word, so an
+// overflow seen by an early stage of a frame (or by the first kind pair of a BPF frame) is still there when the frame's last kernel
+// collects the errors.
 __global__ void k_begin_step(unsigned int* ctrl) {
     PF_PDL_ENTRY();
+    __shared__ unsigned s_err;
+    if (threadIdx.x == 0) s_err = ws_error_bits(ctrl);
+    __syncthreads();
     if (threadIdx.x == 0) ctrl[0] += 1;
+    else if (threadIdx.x == kStickyErrWord) ctrl[kStickyErrWord] = s_err;
     else if (threadIdx.x < kCtrlWords) ctrl[threadIdx.x] = 0;
 }
 

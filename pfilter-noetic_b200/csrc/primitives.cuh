@@ -19,6 +19,14 @@ constexpr int kSmallSort = 8192;   // inputs up to this size are sorted by one C
 constexpr int kCtrlWords = 256;
 constexpr int kSlotBase = 32;
 constexpr int kSlotWords = 32;
+// Word 15 of a state slot carries the error bits of the stage that owns the slot.  Slot use inside an odometry handle: 0 / 1 VoxelGrid
+// down-sampling of a kind pair (voxel.cu), 2 search-grid build (knn.cu), 3 streaming map update (merge.cu).  The last control word is
+// sticky: k_begin_step folds the slots' error bits into it before it wipes them.
+constexpr int kStickyErrWord = kCtrlWords - 1;
+constexpr unsigned kErrMergeMask = 30u;   // map update: 2 voxel coordinate range, 4 exception capacity, 8 / 16 internal (merge.cu)
+constexpr unsigned kErrGrid = 32u;        // map extent exceeds the search grid (kGridCellCap cells of 1 m)
+constexpr unsigned kErrVoxel = 64u;       // VoxelGrid index space exceeds 31 bits (pcl::VoxelGrid's "leaf size too small" case)
+constexpr unsigned kErrRing = 128u;       // a scan ring exceeded the extractor's max_ring_points (the ring was dropped)
 
 struct Workspace {
     cudaStream_t stream = nullptr;
@@ -45,6 +53,14 @@ int workspace_begin_step(Workspace& ws);
 int radix_sort(Workspace& ws, const int* n_dev, int n_cap, int passes, bool vals_iota, int* result_buf);
 
 #ifdef __CUDACC__
+// error bits of a workspace as seen right now: sticky word | live slot words
+__device__ __forceinline__ unsigned ws_error_bits(const unsigned* ctrl) {
+    unsigned e = ctrl[kStickyErrWord];
+    if (ctrl[kSlotBase + 15] | ctrl[kSlotBase + kSlotWords + 15]) e |= kErrVoxel;
+    if (ctrl[kSlotBase + 2 * kSlotWords + 15]) e |= kErrGrid;
+    e |= ctrl[kSlotBase + 3 * kSlotWords + 15] & kErrMergeMask;
+    return e;
+}
 // ------------------------------------------------------------------------------------------------------------
 // block-level helpers (256 threads)
 // ------------------------------------------------------------------------------------------------------------

@@ -1,0 +1,93 @@
+"""Capacity / overflow conditions must surface as PF_ERR_CAPACITY from the fused frame path, not as a silently degraded pose
+(the reference has no such limits: it prints and carries on, src/odomEstimationClass.cpp:276,423,430; ours are fixed at create
+time and documented in include/pfilter_b200.h)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _feat(rng, n, half):
+    a = np.zeros((n, 4), np.float32)
+    a[:, :3] = (rng.random((n, 3), dtype=np.float32) - 0.5) * 2 * np.asarray(half, np.float32)
+    return a
+
+
+def test_ring_capacity_reaches_the_fused_frame_path(pfb, capi):
+    """A ring with more points than max_ring_points is dropped whole by the extractor; pf_frame_process / pf_frame_wait must say so."""
+    p = pfb.synth.config("cfg2")
+    scans = [pfb.synth.scan(p, f) for f in range(3)]
+    ex = capi.Extractor(num_lines=64, max_points=131072, max_ring_points=1024)     # the synthetic rings hold ~1790 points
+    od = capi.Odometry(0.4, 0, 0.4, 75, max_map_points=1 << 19)
+    with pytest.raises(capi.PfError) as e:
+        capi.frame_process(ex, od, scans[0])
+    assert e.value.status == -3 and "ring" in str(e.value)
+    ex.close(); od.close()
+    # queued form: the error comes out of pf_frame_wait
+    ex = capi.Extractor(num_lines=64, max_points=131072, max_ring_points=1024)
+    od = capi.Odometry(0.4, 0, 0.4, 75, max_map_points=1 << 19)
+    ids = [capi.frame_submit(ex, od, s) for s in scans]
+    with pytest.raises(capi.PfError) as e:
+        capi.frame_wait(od, ids[1])
+    assert e.value.status == -3
+    # the stand-alone extraction call reports it as before
+    with pytest.raises(capi.PfError):
+        ex.run(scans[0])
+    ex.close(); od.close()
+    # the default capacity is fine
+    ex = capi.Extractor(num_lines=64, max_points=131072)
+    od = capi.Odometry(0.4, 0, 0.4, 75, max_map_points=1 << 19)
+    for s in scans:
+        capi.frame_process(ex, od, s)
+    ex.close(); od.close()
+
+
+def test_search_grid_overflow_is_reported(capi):
+    """First-frame maps are not cropped (:217-222): an extent beyond 2^23 cells of 1 m cannot be searched."""
+    rng = np.random.default_rng(5)
+    od = capi.Odometry(0.4, 0, 0.4, 75, max_map_points=1 << 19)
+    od.init_map(_feat(rng, 4000, (160, 160, 60)), _feat(rng, 20000, (160, 160, 60)))     # 321 x 321 x 121 cells > 2^23
+    with pytest.raises(capi.PfError) as e:
+        od.update(_feat(rng, 500, (20, 20, 2)), _feat(rng, 3000, (20, 20, 2)))
+    assert e.value.status == -3 and "grid" in str(e.value)
+    od.close()
+
+
+def test_voxel_index_overflow_is_reported(capi):
+    """pcl::VoxelGrid refuses index spaces beyond 2^31 ("leaf size too small"); the down-sampling kernels flag it."""
+    rng = np.random.default_rng(6)
+    od = capi.Odometry(0.4, 0, 0.4, 75, max_map_points=1 << 19)
+    od.init_map(_feat(rng, 4000, (30, 30, 3)), _feat(rng, 20000, (30, 30, 3)))
+    with pytest.raises(capi.PfError) as e:
+        od.update(_feat(rng, 500, (400, 400, 400)), _feat(rng, 3000, (20, 20, 2)))       # 2000^3 voxels of 0.4 m
+    assert e.value.status == -3
+    od.close()
+
+
+def test_outstanding_frame_limit_is_enforced(pfb, capi):
+    """At most 32 submitted frames may await pf_frame_wait: the 33rd submit is refused instead of overwriting a result slot."""
+    p = pfb.synth.config("cfg2")
+    scan = pfb.synth.scan(p, 0)
+    ex = capi.Extractor(num_lines=64, max_points=131072)
+    od = capi.Odometry(0.4, 0, 0.4, 75, max_map_points=1 << 19)
+    ids = [capi.frame_submit(ex, od, scan) for _ in range(32)]
+    with pytest.raises(capi.PfError) as e:
+        capi.frame_submit(ex, od, scan)
+    assert e.value.status == -4
+    capi.frame_wait(od, ids[0])
+    ids.append(capi.frame_submit(ex, od, scan))      # one slot is free again
+    for i in ids[1:]:
+        capi.frame_wait(od, i)
+    ex.close(); od.close()
+
+
+def test_pose_history_range_copy(pfb, capi):
+    p = pfb.synth.config("cfg2")
+    ex = capi.Extractor(num_lines=64, max_points=131072)
+    od = capi.Odometry(0.4, 0, 0.4, 75, max_map_points=1 << 19)
+    poses = [capi.frame_process(ex, od, pfb.synth.scan(p, f)) for f in range(6)]
+    import ctypes as C
+    hist = np.zeros((5, 7))
+    capi.check(capi.lib().pf_odom_get_pose_history(od.h, C.c_longlong(1), 5, hist.ctypes.data_as(C.c_void_p)))
+    assert hist.tobytes() == np.array(poses[1:]).tobytes()
+    ex.close(); od.close()
