@@ -222,6 +222,11 @@ int pf_associate(int device, int kind /*0 edge, 1 surf*/, pf_point* map, int m, 
  * H21 = upper triangle of sum J^T J (row-major), g6 = sum J^T r, cost = 1/2 sum rho. */
 int pf_eval_normal_eq(int device, const double pose[7], const double* edge9, int n_edge, const double* surf7, int n_surf,
                       double H21[21], double g6[6], double* cost);
+/* The same sums by the grid-wide streaming kernel that serves the map-size sweep of BASELINE.json configs[4] (10^6 .. 5 x 10^7
+ * residual blocks; pf_eval_normal_eq itself switches to it above 262144 blocks).  `reps` repetitions on the device (the first is a
+ * warm-up when reps > 1); ms_kernel = mean CUDA-event time of the kernel alone. */
+int pf_eval_normal_eq_timed(int device, const double pose[7], const double* edge9, int n_edge, const double* surf7, int n_surf,
+                            int reps, double H21[21], double g6[6], double* cost, float* ms_kernel);
 /* One ceres::Solve equivalent (src/odomEstimationClass.cpp:263-271) on fixed residuals. */
 int pf_lm_solve(int device, double pose_io[7], const double* edge9, int n_edge, const double* surf7, int n_surf,
                 int* iterations, double* final_cost);

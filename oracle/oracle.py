@@ -113,6 +113,17 @@ def knn5(map_pts, queries_xyz4, mode=1):
     return idx, d2
 
 
+def knn5_timed(map_pts, queries_xyz4):
+    """kd-tree (FLANN KDTreeSingleIndex-like, leaf 15) build and query timed separately: (idx, d2, s_build, s_query)."""
+    m = _pts(map_pts)
+    q = np.ascontiguousarray(queries_xyz4, np.float32)
+    idx = np.empty((len(q), 5), np.int32)
+    d2 = np.empty((len(q), 5), np.float32)
+    tb, tq = C.c_double(), C.c_double()
+    lib().pforacle_knn5_timed(_vp(m), len(m), _vp(q), len(q), _vp(idx), _vp(d2), C.byref(tb), C.byref(tq))
+    return idx, d2, tb.value, tq.value
+
+
 def associate(kind, map_pts, queries, pose, k_new, theta_p, theta_max):
     """Returns (map_after, queries_after, flag, geom8)."""
     m = _pts(map_pts).copy()

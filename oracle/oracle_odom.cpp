@@ -33,6 +33,7 @@
 #include <cstdio>
 #include <cstring>
 #include <limits>
+#include <chrono>
 #include <vector>
 
 namespace {
@@ -1025,6 +1026,29 @@ int pforacle_knn5(const OPoint* map, int m, const float* q4, int nq, int mode, i
             d2[5 * i + k] = ok ? nn.d[k] : std::numeric_limits<float>::infinity();
         }
     }
+    return 0;
+}
+
+// kd-tree build and query timed separately (CPU baseline of the map-size sweep); same results as pforacle_knn5(mode = 1)
+int pforacle_knn5_timed(const OPoint* map, int m, const float* q4, int nq, int32_t* idx, float* d2, double* s_build, double* s_query) {
+    std::vector<OPoint> M(map, map + m);
+    KdTree tree;
+    auto t0 = std::chrono::steady_clock::now();
+    tree.build(M);
+    auto t1 = std::chrono::steady_clock::now();
+    for (int i = 0; i < nq; ++i) {
+        float qf[3] = {q4[4 * i], q4[4 * i + 1], q4[4 * i + 2]};
+        Knn5 nn;
+        tree.search(qf, nn);
+        bool ok = nn.n == 5 && nn.d[4] < 1.0f;
+        for (int k = 0; k < 5; ++k) {
+            idx[5 * i + k] = ok ? nn.i[k] : -1;
+            d2[5 * i + k] = ok ? nn.d[k] : std::numeric_limits<float>::infinity();
+        }
+    }
+    auto t2 = std::chrono::steady_clock::now();
+    *s_build = std::chrono::duration<double>(t1 - t0).count();
+    *s_query = std::chrono::duration<double>(t2 - t1).count();
     return 0;
 }
 

@@ -8,7 +8,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpfilter_b200.so")
+# PFILTER_B200_LIB selects another build of the same library (kernel variants under build_variants/ while tuning)
+LIB_PATH = os.environ.get("PFILTER_B200_LIB") or os.path.join(_HERE, "libpfilter_b200.so")
 
 PF_OK = 0
 
@@ -261,6 +262,16 @@ def eval_normal_eq(pose, edge9, surf7, device=0):
     H = np.zeros(21); g = np.zeros(6); cost = C.c_double()
     check(lib().pf_eval_normal_eq(device, _vp(pose), _vp(e), len(e), _vp(s), len(s), _vp(H), _vp(g), C.byref(cost)))
     return H, g, cost.value
+
+
+def eval_normal_eq_timed(pose, edge9, surf7, reps=5, device=0):
+    """pf_eval_normal_eq_timed (grid-wide streaming kernel): returns (H21, g6, cost, ms_kernel)."""
+    pose = np.ascontiguousarray(pose, np.float64)
+    e = np.ascontiguousarray(edge9, np.float64).reshape(-1, 9)
+    s = np.ascontiguousarray(surf7, np.float64).reshape(-1, 7)
+    H = np.zeros(21); g = np.zeros(6); cost = C.c_double(); ms = C.c_float()
+    check(lib().pf_eval_normal_eq_timed(device, _vp(pose), _vp(e), len(e), _vp(s), len(s), reps, _vp(H), _vp(g), C.byref(cost), C.byref(ms)))
+    return H, g, cost.value, ms.value
 
 
 def lm_solve(pose, edge9, surf7, device=0):

@@ -400,6 +400,136 @@ int lm_solve(cudaStream_t stream, const LmParams& P, const double* pose_src, int
     return PF_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------------------------
+// K7 at map-sweep sizes (BASELINE.json configs[4]: 10^6 .. 5 x 10^7 residual blocks): the same residual / Jacobian / Huber / J^T J
+// arithmetic as one evaluation of k_lm_solve, as a grid-wide streaming kernel.  The per-frame solver is a 12-CTA cluster because a
+// frame has ~5 k residual blocks and needs five dependent evaluations; at 10^6 blocks one evaluation is an HBM stream of
+// 72 B (edge: p, a, b) / 56 B (surf: p, n, d) per block (src/lidarOptimization.cpp:12-78) and wants every SM.
+// Persistent CTAs, static round-robin over tiles of 256 blocks; a tile is one contiguous 18 KB / 14 KB run of the packed input,
+// brought into shared memory by ONE bulk (TMA) copy per tile into a 3-deep ring (mbarrier completion), so the loads of the next two
+// tiles are in flight while the CTA evaluates the current one; thread i reads block i from shared memory (stride 72 / 56 B:
+// conflict-free for 8-byte accesses), accumulates the 29 sums in fp64 registers; shuffle tree + shared memory per CTA, one partial
+// per CTA in global memory, and the last CTA to finish (ticket) adds the partials in CTA order -- deterministic.
+#ifndef PF_NE_STAGES
+#define PF_NE_STAGES 3
+#endif
+#ifndef PF_NE_CTAS
+#define PF_NE_CTAS 3
+#endif
+constexpr int kNeTile = 256, kNeStages = PF_NE_STAGES, kNeCtasPerSm = PF_NE_CTAS;
+constexpr int kNeStageBytes = kNeTile * 72;
+
+struct NeStreamParams {
+    const double* edge9; const double* surf7;
+    int n_edge, n_surf;
+    const double* pose;        // [7] device
+    double* partial;           // [grid][32]
+    unsigned* ticket;
+    double* out;               // [32]: H21, g6, cost, count
+};
+
+__global__ void __launch_bounds__(kNeTile, kNeCtasPerSm) k_normal_eq_stream(NeStreamParams P) {
+    extern __shared__ __align__(128) unsigned char s_stage[];      // [kNeStages][kNeStageBytes]
+    __shared__ __align__(8) unsigned long long s_bar[kNeStages];
+    __shared__ double s_red[kNeTile / 32][kAcc];
+    __shared__ int s_last;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int tiles_e = (P.n_edge + kNeTile - 1) / kNeTile, tiles_s = (P.n_surf + kNeTile - 1) / kNeTile, ntiles = tiles_e + tiles_s;
+    const int G = gridDim.x;
+    const int mine = (int)blockIdx.x < ntiles ? (ntiles - 1 - (int)blockIdx.x) / G + 1 : 0;
+    // tile j of this CTA -> (kind, first block, blocks)
+    auto desc = [&](int j, int& kind, const double*& src, int& cnt) {
+        const int t = (int)blockIdx.x + j * G;
+        if (t < tiles_e) { kind = 0; src = P.edge9 + (size_t)t * kNeTile * 9; cnt = min(kNeTile, P.n_edge - t * kNeTile); }
+        else { const int u = t - tiles_e; kind = 1; src = P.surf7 + (size_t)u * kNeTile * 7; cnt = min(kNeTile, P.n_surf - u * kNeTile); }
+    };
+    auto issue = [&](int j) {      // one thread; only full tiles travel by bulk copy (their byte count is a multiple of 16)
+        int kind, cnt; const double* src;
+        desc(j, kind, src, cnt);
+        if (cnt == kNeTile) bulk_load(s_stage + (size_t)(j % kNeStages) * kNeStageBytes, src, (unsigned)(kNeTile * (kind == 0 ? 72 : 56)), &s_bar[j % kNeStages]);
+    };
+    if (tid == 0) {
+        for (int b = 0; b < kNeStages; ++b) mbar_init(&s_bar[b], 1u);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        for (int j = 0; j < kNeStages - 1 && j < mine; ++j) issue(j);
+    }
+    double Rm[9], tv[3];
+    {
+        double x[7];
+#pragma unroll
+        for (int k = 0; k < 7; ++k) x[k] = P.pose[k];
+        quat_to_mat(x, Rm);
+        tv[0] = x[4]; tv[1] = x[5]; tv[2] = x[6];
+    }
+    double acc[kAcc];
+#pragma unroll
+    for (int k = 0; k < kAcc; ++k) acc[k] = 0.0;
+    __syncthreads();
+    for (int j = 0; j < mine; ++j) {
+        if (tid == 0 && j + kNeStages - 1 < mine) issue(j + kNeStages - 1);      // its buffer was released by the barrier below
+        int kind, cnt; const double* src;
+        desc(j, kind, src, cnt);
+        const int nd = kind == 0 ? 9 : 7;
+        double v[9];
+        if (cnt == kNeTile) {
+            mbar_wait(&s_bar[j % kNeStages], (unsigned)((j / kNeStages) & 1));
+            const double* sp = reinterpret_cast<const double*>(s_stage + (size_t)(j % kNeStages) * kNeStageBytes) + (size_t)tid * nd;
+#pragma unroll
+            for (int k = 0; k < 9; ++k) v[k] = k < nd ? sp[k] : 0.0;
+        } else if (tid < cnt) {      // the ragged last tile of a kind: plain loads
+#pragma unroll
+            for (int k = 0; k < 9; ++k) v[k] = k < nd ? src[(size_t)tid * nd + k] : 0.0;
+        }
+        if (tid < cnt) eval_one(kind, d3(v[0], v[1], v[2]), v + 3, Rm, tv, 0.0, acc);
+        __syncthreads();
+    }
+#pragma unroll
+    for (int k = 0; k < kAcc; ++k) {
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) acc[k] += __shfl_down_sync(0xffffffffu, acc[k], o);
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < kAcc; ++k) s_red[w][k] = acc[k];
+    }
+    __syncthreads();
+    if (tid < kAcc) {
+        double sum = 0;
+#pragma unroll
+        for (int k = 0; k < kNeTile / 32; ++k) sum += s_red[k][tid];
+        P.partial[(size_t)blockIdx.x * 32 + tid] = sum;
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = atomicAdd(P.ticket, 1u) == (unsigned)G - 1u;
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        if (tid < kAcc) {
+            double sum = 0;
+            for (int b = 0; b < G; ++b) sum += __ldcg(P.partial + (size_t)b * 32 + tid);      // CTA order: deterministic
+            P.out[tid] = sum;
+        }
+        if (tid == 0) *P.ticket = 0u;
+    }
+}
+
+int normal_eq_stream(cudaStream_t stream, const double* d_pose, const double* d_edge9, int n_edge, const double* d_surf7, int n_surf,
+                     double* d_partial, unsigned* d_ticket, double* d_out, int grid) {
+    static bool attr_set[64] = {};
+    int dev = 0;
+    PF_CUDA(cudaGetDevice(&dev));
+    if (!attr_set[dev & 63]) {
+        PF_CUDA(cudaFuncSetAttribute(k_normal_eq_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, kNeStages * kNeStageBytes));
+        attr_set[dev & 63] = true;
+    }
+    NeStreamParams P{d_edge9, d_surf7, n_edge, n_surf, d_pose, d_partial, d_ticket, d_out};
+    k_normal_eq_stream<<<grid, kNeTile, kNeStages * kNeStageBytes, stream>>>(P);
+    PF_CUDA(cudaGetLastError());
+    return PF_OK;
+}
+
 }  // namespace pf
 
 // ------------------------------------------------------------------------------------------------------------
@@ -407,7 +537,10 @@ int lm_solve(cudaStream_t stream, const LmParams& P, const double* pose_src, int
 // ------------------------------------------------------------------------------------------------------------
 using namespace pf;
 
+extern "C" int pf_eval_normal_eq_timed(int device, const double pose[7], const double* edge9, int n_edge, const double* surf7, int n_surf,
+                                       int reps, double H21[21], double g6[6], double* cost, float* ms_kernel);
 namespace {
+constexpr long long kLmTapMax = 262144;    // residual blocks up to which pf_eval_normal_eq runs the per-frame cluster kernel
 struct SolveTap {
     cudaStream_t stream = nullptr;
     double *d_p[2] = {nullptr, nullptr}, *d_geom[2] = {nullptr, nullptr};
@@ -467,6 +600,8 @@ int solve_tap_setup(SolveTap& t, int device, const double pose[7], const double*
 extern "C" int pf_eval_normal_eq(int device, const double pose[7], const double* edge9, int n_edge, const double* surf7, int n_surf,
                                  double H21[21], double g6[6], double* cost) {
     PF_REQUIRE(H21 && g6 && cost, "null output");
+    if ((long long)n_edge + n_surf > kLmTapMax)       // beyond the cluster kernel's shared-memory lists: the grid-wide kernel
+        return pf_eval_normal_eq_timed(device, pose, edge9, n_edge, surf7, n_surf, 1, H21, g6, cost, nullptr);
     SolveTap t;
     LmParams P{};
     PF_CHECK(solve_tap_setup(t, device, pose, edge9, n_edge, surf7, n_surf, P));
@@ -478,6 +613,55 @@ extern "C" int pf_eval_normal_eq(int device, const double pose[7], const double*
     memcpy(H21, S.last_H, sizeof(double) * 21);
     memcpy(g6, S.last_g, sizeof(double) * 6);
     *cost = S.last_cost;
+    return PF_OK;
+}
+
+
+// Grid-wide evaluation (k_normal_eq_stream): packed host arrays in, sums out; `reps` timed repetitions on the device (the first is a
+// warm-up when reps > 1), CUDA events on the tap's stream around the kernel alone.
+extern "C" int pf_eval_normal_eq_timed(int device, const double pose[7], const double* edge9, int n_edge, const double* surf7, int n_surf,
+                                       int reps, double H21[21], double g6[6], double* cost, float* ms_kernel) {
+    PF_REQUIRE(pose && H21 && g6 && cost && n_edge >= 0 && n_surf >= 0 && (edge9 || n_edge == 0) && (surf7 || n_surf == 0) && reps >= 1, "bad argument");
+    PF_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    PF_CUDA(cudaGetDeviceProperties(&prop, device));
+    PF_REQUIRE(prop.major == 10, "pfilter_b200 needs an sm_100a device, found sm_%d%d", prop.major, prop.minor);
+    struct Bufs {
+        cudaStream_t stream = nullptr; double *e = nullptr, *s = nullptr, *pose = nullptr, *partial = nullptr, *out = nullptr; unsigned* ticket = nullptr;
+        cudaEvent_t ev[2] = {nullptr, nullptr};
+        ~Bufs() { cudaFree(e); cudaFree(s); cudaFree(pose); cudaFree(partial); cudaFree(out); cudaFree(ticket);
+                  for (auto x : ev) if (x) cudaEventDestroy(x);
+                  if (stream) cudaStreamDestroy(stream); }
+    } b;
+    PF_CUDA(cudaStreamCreateWithFlags(&b.stream, cudaStreamNonBlocking));
+    const int grid = prop.multiProcessorCount * kNeCtasPerSm;
+    PF_CUDA(cudaMalloc(&b.e, sizeof(double) * 9 * (size_t)(n_edge > 0 ? n_edge : 1)));
+    PF_CUDA(cudaMalloc(&b.s, sizeof(double) * 7 * (size_t)(n_surf > 0 ? n_surf : 1)));
+    PF_CUDA(cudaMalloc(&b.pose, sizeof(double) * 7));
+    PF_CUDA(cudaMalloc(&b.partial, sizeof(double) * 32 * grid));
+    PF_CUDA(cudaMalloc(&b.out, sizeof(double) * 32));
+    PF_CUDA(cudaMalloc(&b.ticket, sizeof(unsigned)));
+    PF_CUDA(cudaMemsetAsync(b.ticket, 0, sizeof(unsigned), b.stream));
+    PF_CUDA(cudaMemcpyAsync(b.pose, pose, sizeof(double) * 7, cudaMemcpyHostToDevice, b.stream));
+    if (n_edge) PF_CUDA(cudaMemcpyAsync(b.e, edge9, sizeof(double) * 9 * (size_t)n_edge, cudaMemcpyHostToDevice, b.stream));
+    if (n_surf) PF_CUDA(cudaMemcpyAsync(b.s, surf7, sizeof(double) * 7 * (size_t)n_surf, cudaMemcpyHostToDevice, b.stream));
+    for (auto& x : b.ev) PF_CUDA(cudaEventCreate(&x));
+    float sum = 0.f;
+    for (int r = 0; r < reps; ++r) {
+        PF_CUDA(cudaEventRecord(b.ev[0], b.stream));
+        PF_CHECK(normal_eq_stream(b.stream, b.pose, b.e, n_edge, b.s, n_surf, b.partial, b.ticket, b.out, grid));
+        PF_CUDA(cudaEventRecord(b.ev[1], b.stream));
+        PF_CUDA(cudaStreamSynchronize(b.stream));
+        float ms = 0.f;
+        PF_CUDA(cudaEventElapsedTime(&ms, b.ev[0], b.ev[1]));
+        if (r > 0 || reps == 1) sum += ms;
+    }
+    double out[32];
+    PF_CUDA(cudaMemcpy(out, b.out, sizeof(out), cudaMemcpyDeviceToHost));
+    memcpy(H21, out, sizeof(double) * 21);
+    memcpy(g6, out + 21, sizeof(double) * 6);
+    *cost = out[27];
+    if (ms_kernel) *ms_kernel = sum / (reps > 1 ? reps - 1 : 1);
     return PF_OK;
 }
 

@@ -8,6 +8,7 @@
 //
 // Output layout: float4 {x, y, z, intensity}, ring-major, azimuth ascending, rays with no return
 // inside the range gate are dropped (like a real sensor).
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <cstring>
@@ -24,10 +25,14 @@ struct Rect {      // axis-aligned vertical rectangle: plane axis (0: x = c, 1: 
 struct Pole {      // vertical cylinder
     double x, y, r, z0, z1;
 };
+struct Volume {    // axis-aligned box of scattering medium (foliage): a ray ends at an exponentially distributed depth inside it
+    double lo[3], hi[3], density;   // density = expected returns per metre of path
+};
 struct Scene {
     double ground_z;
     std::vector<Rect> rects;
     std::vector<Pole> poles;
+    std::vector<Volume> volumes;
 };
 
 inline uint64_t splitmix64(uint64_t x) {
@@ -109,6 +114,22 @@ Scene build_campus(uint64_t seed, double half) {
     return sc;
 }
 
+// "dense campus": the campus plus volumetric scatter (tree crowns, hedges) so that almost every return opens a new voxel -- the
+// scene that makes the persistent local map of BASELINE.json configs[3] grow into the millions when the filter keeps the points.
+Scene build_campus_dense(uint64_t seed, double half) {
+    Scene sc = build_campus(seed, half);
+    Rng rng(seed * 15485863ull + 11);
+    for (int i = 0; i < 900; ++i) {
+        double cx = rng.uni(-half, half), cy = rng.uni(-half, half);
+        double r = std::sqrt(cx * cx + cy * cy);
+        if (r > 56.0 && r < 64.0) continue;
+        double sx = rng.uni(2.0, 9.0), sy = rng.uni(2.0, 9.0), z0 = sc.ground_z + rng.uni(0.0, 3.0), h = rng.uni(2.0, 10.0);
+        Volume v{{cx - sx / 2, cy - sy / 2, z0}, {cx + sx / 2, cy + sy / 2, z0 + h}, rng.uni(0.15, 0.6)};
+        sc.volumes.push_back(v);
+    }
+    return sc;
+}
+
 struct Pose2 { double x, y, z, yaw; };
 
 Pose2 trajectory(const pf_synth_params& p, int k) {
@@ -144,7 +165,8 @@ Cache g_cache;
 
 const Scene& scene_for(const pf_synth_params& p) {
     if (!g_cache.valid || g_cache.key.seed != p.seed || g_cache.key.scene != p.scene) {
-        g_cache.scene = p.scene == PF_SYNTH_SCENE_STREET ? build_street(p.seed, -60.0, 1200.0) : build_campus(p.seed, 110.0);
+        g_cache.scene = p.scene == PF_SYNTH_SCENE_STREET ? build_street(p.seed, -60.0, 1200.0)
+                      : p.scene == PF_SYNTH_SCENE_CAMPUS ? build_campus(p.seed, 110.0) : build_campus_dense(p.seed, 110.0);
         g_cache.key = p;
         g_cache.valid = true;
     }
@@ -189,6 +211,56 @@ extern "C" int pf_synth_scan(const pf_synth_params* p, int frame, float* out_xyz
     }
     for (const Pole& c : sc.poles)
         if (std::hypot(c.x - pose.x, c.y - pose.y) < reach) poles.push_back(c);
+    std::vector<Volume> vols;
+    for (const Volume& v : sc.volumes)
+        if (std::hypot(0.5 * (v.lo[0] + v.hi[0]) - pose.x, 0.5 * (v.lo[1] + v.hi[1]) - pose.y) < reach) vols.push_back(v);
+
+    // Azimuth bins around the sensor: a ray only meets primitives whose subtended azimuth interval (one bin of margin either side)
+    // contains its own azimuth.  Pure culling: the surviving hit set, and therefore every output bit, is unchanged.
+    constexpr int kBins = 720;
+    std::vector<std::vector<int>> brect(kBins), bpole(kBins), bvol(kBins);
+    auto add_arc = [&](std::vector<std::vector<int>>& bins, int id, double centre, double half_width) {
+        if (half_width >= M_PI - 0.02) { for (int b = 0; b < kBins; ++b) bins[b].push_back(id); return; }
+        const double w = 2.0 * M_PI / kBins;
+        const int b0 = (int)std::floor((centre - half_width + M_PI) / w) - 1, b1 = (int)std::floor((centre + half_width + M_PI) / w) + 1;
+        for (int b = b0; b <= b1; ++b) bins[((b % kBins) + kBins) % kBins].push_back(id);
+    };
+    auto arc_of_points = [&](const double (*pts)[2], int np, double& centre, double& half_width) {
+        double mx = 0, my = 0;
+        for (int i = 0; i < np; ++i) { mx += pts[i][0] - pose.x; my += pts[i][1] - pose.y; }
+        centre = std::atan2(my, mx);
+        half_width = 0;
+        for (int i = 0; i < np; ++i) {
+            double d = std::atan2(pts[i][1] - pose.y, pts[i][0] - pose.x) - centre;
+            while (d > M_PI) d -= 2 * M_PI;
+            while (d < -M_PI) d += 2 * M_PI;
+            half_width = std::max(half_width, std::fabs(d));
+        }
+    };
+    for (size_t i = 0; i < rects.size(); ++i) {
+        const Rect& r = rects[i];
+        const double pts[2][2] = {{r.axis == 0 ? r.c : r.lo, r.axis == 0 ? r.lo : r.c}, {r.axis == 0 ? r.c : r.hi, r.axis == 0 ? r.hi : r.c}};
+        // distance from the sensor to the segment: very close segments subtend almost pi and the mean direction is ill-defined
+        const double along = r.axis == 0 ? pose.y : pose.x, across = std::fabs((r.axis == 0 ? pose.x : pose.y) - r.c);
+        if (across < 0.5 && along > r.lo - 0.5 && along < r.hi + 0.5) { add_arc(brect, (int)i, 0, M_PI); continue; }
+        double c, hw;
+        arc_of_points(pts, 2, c, hw);
+        add_arc(brect, (int)i, c, hw);
+    }
+    for (size_t i = 0; i < poles.size(); ++i) {
+        const Pole& c = poles[i];
+        const double d = std::hypot(c.x - pose.x, c.y - pose.y);
+        if (d <= c.r * 1.5) { add_arc(bpole, (int)i, 0, M_PI); continue; }
+        add_arc(bpole, (int)i, std::atan2(c.y - pose.y, c.x - pose.x), std::asin(std::min(1.0, c.r / d)));
+    }
+    for (size_t i = 0; i < vols.size(); ++i) {
+        const Volume& v = vols[i];
+        if (pose.x > v.lo[0] - 0.5 && pose.x < v.hi[0] + 0.5 && pose.y > v.lo[1] - 0.5 && pose.y < v.hi[1] + 0.5) { add_arc(bvol, (int)i, 0, M_PI); continue; }
+        const double pts[4][2] = {{v.lo[0], v.lo[1]}, {v.lo[0], v.hi[1]}, {v.hi[0], v.lo[1]}, {v.hi[0], v.hi[1]}};
+        double c, hw;
+        arc_of_points(pts, 4, c, hw);
+        add_arc(bvol, (int)i, c, hw);
+    }
 
     int n = 0;
     for (int ring = 0; ring < p->sensor_lines; ++ring) {
@@ -204,11 +276,14 @@ extern "C" int pf_synth_scan(const pf_synth_params* p, int frame, float* out_xyz
             double dx = cy * dxs - sy * dys, dy = sy * dxs + cy * dys;
             double ox = pose.x, oy = pose.y, oz = pose.z;
             double tbest = 1e30;
+            int bin = (int)std::floor((std::atan2(dy, dx) + M_PI) / (2.0 * M_PI / kBins));
+            bin = bin < 0 ? 0 : (bin >= kBins ? kBins - 1 : bin);
             if (dz < -1e-9) {
                 double t = (sc.ground_z - oz) / dz;
                 if (t > 0 && t < tbest) tbest = t;
             }
-            for (const Rect& r : rects) {
+            for (int ri : brect[bin]) {
+                const Rect& r = rects[ri];
                 double d = r.axis == 0 ? dx : dy, o = r.axis == 0 ? ox : oy;
                 if (std::fabs(d) < 1e-12) continue;
                 double t = (r.c - o) / d;
@@ -216,7 +291,8 @@ extern "C" int pf_synth_scan(const pf_synth_params* p, int frame, float* out_xyz
                 double u = r.axis == 0 ? oy + t * dy : ox + t * dx, z = oz + t * dz;
                 if (u >= r.lo && u <= r.hi && z >= r.z0 && z <= r.z1) tbest = t;
             }
-            for (const Pole& c : poles) {
+            for (int ci : bpole[bin]) {
+                const Pole& c = poles[ci];
                 double fx = ox - c.x, fy = oy - c.y;
                 double A = dx * dx + dy * dy, B = fx * dx + fy * dy, C = fx * fx + fy * fy - c.r * c.r;
                 double disc = B * B - A * C;
@@ -225,6 +301,21 @@ extern "C" int pf_synth_scan(const pf_synth_params* p, int frame, float* out_xyz
                 if (t <= 0 || t >= tbest) continue;
                 double z = oz + t * dz;
                 if (z >= c.z0 && z <= c.z1) tbest = t;
+            }
+            for (int vi : bvol[bin]) {      // slab test, then an exponential free path inside the medium
+                const Volume& v = vols[vi];
+                const double d3[3] = {dx, dy, dz}, o3[3] = {ox, oy, oz};
+                double t0 = 0.0, t1 = tbest;
+                for (int a = 0; a < 3 && t0 < t1; ++a) {
+                    if (std::fabs(d3[a]) < 1e-12) { if (o3[a] < v.lo[a] || o3[a] > v.hi[a]) t1 = -1.0; continue; }
+                    double ta = (v.lo[a] - o3[a]) / d3[a], tb = (v.hi[a] - o3[a]) / d3[a];
+                    if (ta > tb) std::swap(ta, tb);
+                    if (ta > t0) t0 = ta;
+                    if (tb < t1) t1 = tb;
+                }
+                if (!(t0 < t1)) continue;
+                const double depth = -std::log(u01(splitmix64(h ^ (0xA24BAED4963EE407ull * (vi + 1))))) / v.density;
+                if (t0 + depth < t1) tbest = t0 + depth;
             }
             if (tbest > 1e29) continue;
             // Box-Muller range noise along the ray (also breaks exact curvature ties)
