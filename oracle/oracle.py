@@ -153,6 +153,21 @@ def lm_solve(pose, edge9, surf7):
     return x, it.value, cost.value
 
 
+def lm_solve_ex(pose, edge9, surf7, max_iter=200, ftol=1e-15):
+    """The oracle's LM state machine run to convergence (iteration cap and function tolerance opened up)."""
+    x = np.array(pose, np.float64)
+    e = np.ascontiguousarray(edge9, np.float64).reshape(-1, 9)
+    s = np.ascontiguousarray(surf7, np.float64).reshape(-1, 7)
+    it = C.c_int(); cost = C.c_double()
+    lib().pforacle_lm_solve_ex(_vp(x), _vp(e), len(e), _vp(s), len(s), max_iter, C.c_double(ftol), C.byref(it), C.byref(cost))
+    return x, it.value, cost.value
+
+
+def set_sort_mode(literal):
+    """0: stable voxel sort (convention shared with the GPU kernels); 1: the reference's literal (unstable) std::sort.  Returns the old mode."""
+    return lib().pforacle_set_sort_mode(int(literal))
+
+
 def se3_plus(x, d):
     x = np.ascontiguousarray(x, np.float64); d = np.ascontiguousarray(d, np.float64)
     out = np.zeros(7)

@@ -259,7 +259,18 @@ void colpiv_qr_solve(const double* A_in, const double* b_in, int rows, double x[
 // ---------------------------------------------------------------------------------------------------------
 // PCL restatements
 // ---------------------------------------------------------------------------------------------------------
-struct KeyIdx { unsigned key; unsigned idx; };
+struct KeyIdx { unsigned key; unsigned idx; };   // same layout as pcl's cloud_point_index_idx {idx, cloud_point_index}
+
+// Order of the points inside a voxel = order of the centroid's float sums.  The reference sorts (voxel, point) pairs with std::sort
+// on the voxel index alone (src/odomEstimationClass.cpp:74, pcl/filters/impl/voxel_grid.hpp), which is not stable: the order is
+// whatever libstdc++'s introsort leaves.  Mode 0 (default, the convention shared with the GPU kernels): stable, ascending
+// input index.  Mode 1 ("literal"): the reference's own call, std::sort with the comparator on the voxel index only -- with the same
+// libstdc++ algorithm this is the reference's summation order; used to measure how far the convention moves the trajectory.
+static int g_sort_literal = 0;
+static void sort_voxel_pairs(std::vector<KeyIdx>& iv) {
+    if (g_sort_literal) std::sort(iv.begin(), iv.end(), [](const KeyIdx& a, const KeyIdx& b) { return a.key < b.key; });
+    else std::stable_sort(iv.begin(), iv.end(), [](const KeyIdx& a, const KeyIdx& b) { return a.key < b.key; });
+}
 
 // pcl::VoxelGrid<PointXYZRGB>::applyFilter, downsample_all_data = true, no filter field, dense input
 // (called through downSamplingToMap, src/odomEstimationClass.cpp:176-180).
@@ -289,7 +300,7 @@ void voxel_grid_pcl(const std::vector<OPoint>& in, float leaf, std::vector<OPoin
         int i2 = (int)(std::floor(in[i].z * inv) - (float)minb[2]);
         iv[i] = {(unsigned)(i0 * mul[0] + i1 * mul[1] + i2 * mul[2]), (unsigned)i};
     }
-    std::stable_sort(iv.begin(), iv.end(), [](const KeyIdx& a, const KeyIdx& b) { return a.key < b.key; });
+    sort_voxel_pairs(iv);
     for (size_t s = 0; s < iv.size();) {
         size_t e = s + 1;
         while (e < iv.size() && iv[e].key == iv[s].key) ++e;
@@ -332,7 +343,7 @@ void rgbds(const std::vector<OPoint>& in, float leaf, std::vector<OPoint>& out) 
         int i2 = (int)(std::floor(in[i].z / leaf) - (float)minb[2]);
         iv[i] = {(unsigned)(i0 * mul[0] + i1 * mul[1] + i2 * mul[2]), (unsigned)i};
     }
-    std::stable_sort(iv.begin(), iv.end(), [](const KeyIdx& a, const KeyIdx& b) { return a.key < b.key; });   // :74
+    sort_voxel_pairs(iv);   // :74
     for (size_t s = 0; s < iv.size();) {   // :86-131 (min_points_per_voxel_ = 0)
         size_t e = s + 1;
         while (e < iv.size() && iv[e].key == iv[s].key) ++e;
@@ -626,7 +637,9 @@ struct LmInfo { int iterations; double final_cost; int successful; };
 // ceres::Solve with the options at src/odomEstimationClass.cpp:263-271 (TRUST_REGION, LEVENBERG_MARQUARDT, DENSE_QR,
 // max_num_iterations 4, jacobi_scaling, function_tolerance 1e-6, gradient_tolerance 1e-10, parameter_tolerance 1e-8,
 // initial radius 1e4, max radius 1e16, min_relative_decrease 1e-3, min/max_lm_diagonal 1e-6 / 1e32).
-LmInfo lm_solve(const std::vector<Residual>& res, double x[7]) {
+// max_iter / ftol: the reference's values are 4 and 1e-6 (:265 and the Ceres default); the parity-pinning test runs the same
+// state machine to convergence (large max_iter, tiny ftol) against an independent minimiser of the same cost.
+LmInfo lm_solve(const std::vector<Residual>& res, double x[7], int max_iter = 4, double ftol = 1e-6) {
     LmInfo info{0, 0.0, 0};
     const int n = (int)res.size();
     if (n == 0) return info;   // no residual blocks: Ceres returns at once, parameters untouched
@@ -659,7 +672,7 @@ LmInfo lm_solve(const std::vector<Residual>& res, double x[7]) {
     double x_norm = 0;
     for (int k = 0; k < 7; ++k) x_norm += x[k] * x[k];
     x_norm = std::sqrt(x_norm);
-    for (int iter = 1; iter <= 4; ++iter) {
+    for (int iter = 1; iter <= max_iter; ++iter) {
         info.iterations = iter;
         if (!reuse_diag) {
             for (int k = 0; k < 6; ++k) {
@@ -697,7 +710,7 @@ LmInfo lm_solve(const std::vector<Residual>& res, double x[7]) {
         for (int k = 0; k < 7; ++k) sn += (x[k] - xc[k]) * (x[k] - xc[k]);
         if (std::sqrt(sn) <= 1e-8 * (x_norm + 1e-8)) break;            // parameter tolerance (candidate not applied)
         double cost_change = cost - cand;
-        if (std::fabs(cost_change) <= 1e-6 * cost) break;              // function tolerance (candidate not applied)
+        if (std::fabs(cost_change) <= ftol * cost) break;              // function tolerance (candidate not applied)
         double rel = cost_change / model_cost_change;
         if (rel > 1e-3) {
             std::memcpy(x, xc, sizeof(double) * 7);
@@ -1106,6 +1119,19 @@ int pforacle_lm_solve(double pose_io[7], const double* edge9, int ne, const doub
     *final_cost = li.final_cost;
     return 0;
 }
+
+// the same state machine with the iteration cap and the function tolerance opened up (pinning tests)
+int pforacle_lm_solve_ex(double pose_io[7], const double* edge9, int ne, const double* surf7, int ns, int max_iter, double ftol,
+                         int* iterations, double* final_cost) {
+    std::vector<Residual> res = pack_residuals(edge9, ne, surf7, ns);
+    LmInfo li = lm_solve(res, pose_io, max_iter, ftol);
+    *iterations = li.iterations;
+    *final_cost = li.final_cost;
+    return 0;
+}
+
+// 0: stable voxel sort (convention shared with the GPU), 1: the reference's literal std::sort (see sort_voxel_pairs)
+int pforacle_set_sort_mode(int literal) { const int old = g_sort_literal; g_sort_literal = literal ? 1 : 0; return old; }
 
 void pforacle_se3_plus(const double x[7], const double d[6], double out[7]) { se3_plus(x, d, out); }
 void pforacle_eig3(const double A[9], double w[3], double V[9]) { eig3_sym(A, w, V); }
