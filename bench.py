@@ -28,7 +28,8 @@ sys.path.insert(0, ROOT)
 
 METRIC = "scans/sec at 64-ring ~120k-pt shape (extract+match+filter)"
 UNIT = "scans/s"
-WORKLOAD = "configs[1]: 100-frame synthetic KITTI-shaped sequence (64 rings x 1800, planes+poles street), PFilter 0/0.4/75"
+WORKLOAD = ("configs[1]: 100-frame synthetic KITTI-shaped sequence (64 rings x 1800, planes+poles street), PFilter 0/0.4/75; "
+            "rank r runs the sequence with seed 3000 + r (the configs[4] family) at every world size")
 PFILTER = (0, 0.4, 75)
 MAX_POINTS = 115200
 
@@ -82,6 +83,26 @@ class ClockSampler(threading.Thread):
         reasons = sorted({names[i] for r in self.rows for i in range(4) if len(r) > 2 + i and r[2 + i].lower().startswith("active")})
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
                 "samples": len(self.rows)}
+
+
+def _host():
+    model = ""
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("model name"):
+                    model = line.split(":", 1)[1].strip()
+                    break
+    except Exception:
+        pass
+    return {"nproc": os.cpu_count(), "cpu_model": model}
+
+
+def _config(world, K, scans):
+    """The workload description: identical in both arms (the driver compares them)."""
+    return {"workload": WORKLOAD, "frames_per_gpu": K, "points_per_scan": int(np.mean([len(s) for s in scans])),
+            "l2": "every frame streams a new 1.8 MB scan; map state is the live working set (no replay of cached inputs)",
+            "parallelism": f"replicas x{world}, no collective"}
 
 
 def _sequence(pfb, cfg, nframes):
@@ -150,24 +171,40 @@ def cpu_pipeline(scans, pipelined):
 
 
 def run_reference(args):
+    """The reference's CPU path on this box's host cores: one 2-thread pipeline (the reference's two ROS nodes) per sequence,
+    `--gpus` sequences side by side -- the same sequences our arm's ranks run.  Rank 0 alone works and prints."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     from pf_loader import pfb
-    p, scans, gt = _sequence(pfb, "cfg2", args.steps)
+    from pfilter_noetic_b200 import shard
+    world = max(1, args.gpus)
+    seqs = [_sequence(pfb, shard.sequence_for_rank(r, world), args.steps) for r in range(world)]
     for _ in range(min(args.warmup, 1)):
-        cpu_pipeline(scans[:3], True)
-    sps, dt, poses, kind = cpu_pipeline(scans, True)
+        cpu_pipeline(seqs[0][1][:3], True)
+    results = [None] * world
+
+    def work(r):
+        results[r] = cpu_pipeline(seqs[r][1], True)
+    t0 = time.perf_counter()
+    ths = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    dt = time.perf_counter() - t0                     # all pipelines done = max over pipelines
+    sps = world * args.steps / dt
+    kind = results[0][3]
     line = {
         "impl": "reference", "metric": METRIC, "value": sps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64",
-        "data": "synthetic", "config": {"workload": WORKLOAD},
-        "cpu_baseline": {"value": sps, "unit": UNIT, "cores": 2, "kind": "port",
-                         "sample": f"{args.steps} frames of the same sequence; extraction = the reference's own laserProcessingClass.cpp "
-                                   f"({'compiled in place' if kind == 'reference' else 'restated'}), odometry = oracle restatement "
-                                   "(PCL/FLANN/Ceres cannot be built here); 2 threads = the reference's 2 ROS nodes"},
+        "data": "synthetic", "config": _config(world, args.steps, seqs[0][1]),
+        "cpu_baseline": {"value": sps, "unit": UNIT, "cores": 2 * world, "kind": "port",
+                         "sample": f"{world} x {args.steps} frames (the sequences of our arm's ranks), one pipeline per sequence side by side; extraction = "
+                                   f"the reference's own laserProcessingClass.cpp ({'compiled in place' if kind == 'reference' else 'restated'}), odometry = "
+                                   "oracle restatement (PCL/FLANN/Ceres cannot be built here); 2 threads per pipeline = the reference's 2 ROS nodes"},
         "e2e": {"value": sps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "ate_m": _ate(poses, gt),
+        "ate_m": [_ate(results[r][2], seqs[r][2]) for r in range(world)], "host": _host(),
     }
     print(json.dumps(line))
 
@@ -284,6 +321,59 @@ def extra_kernel_legs(capi, dev_index):
     return {"k9_map_merge": k9, "k4_knn": k4, "k10_global_map": k10}
 
 
+def multi_sequence_leg(pfb, capi, torch, names, K, local, barrier, reduce_max):
+    """configs[4] as a fixed job of 8 sequences: this rank runs `names` CONCURRENTLY on its GPU -- one (extractor, odometry) handle
+    pair, stream set and host thread per sequence, host pinned scans in and poses out (pf_frame_submit / pf_frame_wait).
+    Returns (whole-rank wall ms, per-sequence poses)."""
+    from concurrent.futures import ThreadPoolExecutor
+    seqs = []
+    for name in names:
+        p = pfb.synth.config(name)
+        pfb.synth.scan(p, 0)
+        with ThreadPoolExecutor(min(16, os.cpu_count() or 4)) as tp:
+            scans = list(tp.map(lambda f: pfb.synth.scan(p, f), range(K)))
+        pinned = []
+        for sc in scans:
+            a, ptr = capi.pinned_array((len(sc), 4), np.float32)
+            a[:] = sc
+            pinned.append((a, ptr))
+        seqs.append(pinned)
+    handles = [(capi.Extractor(num_lines=64, max_points=MAX_POINTS, device=local),
+                capi.Odometry(0.4, *PFILTER, max_map_points=1 << 19, max_features=MAX_POINTS, device=local)) for _ in names]
+    poses = [None] * len(names)
+    gate = threading.Barrier(len(names) + 1)
+
+    def work(i):
+        ex, od = handles[i]
+        pin = seqs[i]
+        out = []
+        gate.wait()
+        prev = capi.frame_submit(ex, od, pin[0][0])
+        for k in range(1, K):
+            fid = capi.frame_submit(ex, od, pin[k][0])
+            out.append(capi.frame_wait(od, prev))
+            prev = fid
+        out.append(capi.frame_wait(od, prev))
+        poses[i] = np.array(out)
+    ths = [threading.Thread(target=work, args=(i,)) for i in range(len(names))]
+    for t in ths:
+        t.start()
+    barrier()
+    t0 = time.perf_counter()
+    gate.wait()
+    for t in ths:
+        t.join()
+    torch.cuda.synchronize()
+    ms = 1e3 * (time.perf_counter() - t0)
+    barrier()
+    for ex, od in handles:
+        ex.close(); od.close()
+    for pinned in seqs:
+        for _, ptr in pinned:
+            capi.host_free(ptr)
+    return reduce_max(ms), poses
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -298,6 +388,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device(f"cuda:{local}")
     K, W = args.steps, max(args.warmup, 3)
+    REPS = max(1, int(os.environ.get("PF_BENCH_REPS", "5")))
     from pfilter_noetic_b200 import shard
     cfg = shard.sequence_for_rank(rank, world)
     p, scans, gt = _sequence(pfb, cfg, K)
@@ -312,13 +403,21 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # pinned host copies (e2e leg) and device-resident copies (value leg)
+    def reduce_max(x):
+        t = torch.tensor([float(x)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0])
+
+    # pinned host copies (e2e legs) and device-resident copies (value leg)
     pinned = []
     for s in scans:
         a, ptr = capi.pinned_array((len(s), 4), np.float32)
         a[:] = s
         pinned.append((a, ptr))
     dscans = [torch.from_numpy(s).to(dev) for s in scans]
+    lib = capi.lib()
+    import ctypes as C
 
     # warm-up: W untimed frames on throw-away handles (module load, allocator, clocks)
     ex, od = handles()
@@ -326,99 +425,145 @@ def run_ours(args):
         capi.frame_process(ex, od, pinned[k][0])
     ex.close(); od.close()
 
-    # ---- value: scans resident in HBM, frames queued back to back, CUDA events ----------------------------------
-    ex, od = handles()
-    s_ex, s_od = torch.cuda.ExternalStream(ex.stream), torch.cuda.ExternalStream(od.stream)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    l0 = ex.launches + od.launches
+    # Every leg below is one timed region of EXACTLY K frames on fresh handles (frame 0 = map initialisation included), bracketed
+    # by barrier + synchronize; it is repeated REPS times and the median of the max-over-ranks times is reported, so that a 9 ms
+    # region is not a single sample.
+    def leg_value():
+        """scans resident in HBM, frames queued back to back, CUDA events on the library's streams"""
+        ex, od = handles()
+        s_ex, s_od = torch.cuda.ExternalStream(ex.stream), torch.cuda.ExternalStream(od.stream)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = ex.launches + od.launches
+        barrier()
+        e0.record(s_ex)
+        for k in range(K):
+            capi.check(lib.pf_frame_process_device(ex.h, od.h, C.c_void_p(dscans[k].data_ptr()), len(scans[k]), None))
+        e1.record(s_od)
+        capi.check(lib.pf_odom_sync(od.h))
+        barrier()
+        ms = e0.elapsed_time(e1)
+        launches = ex.launches + od.launches - l0
+        hist = np.zeros((K - 1, 7))
+        capi.check(lib.pf_odom_get_pose_history(od.h, C.c_longlong(1), K - 1, hist.ctypes.data_as(C.c_void_p)))
+        poses_dev = np.concatenate([np.array([[0, 0, 0, 1, 0, 0, 0.0]]), hist])
+        stats = od.stats()
+        stats["graph_captures"] = od.graph_captures
+        ex.close(); od.close()
+        return reduce_max(ms), launches, poses_dev, stats
+
+    def leg_sync():
+        """one blocking pf_frame_process per frame from pinned host memory"""
+        ex, od = handles()
+        out = []
+        barrier()
+        t0 = time.perf_counter()
+        for k in range(K):
+            out.append(capi.frame_process(ex, od, pinned[k][0]))
+        torch.cuda.synchronize()
+        ms = 1e3 * (time.perf_counter() - t0)
+        barrier()
+        ex.close(); od.close()
+        return reduce_max(ms), np.array(out)
+
+    def leg_e2e():
+        """the same host scans through pf_frame_submit / pf_frame_wait, one frame in flight ahead of the one whose pose is read back:
+        every step still uploads its scan from pinned host memory and reads its pose back"""
+        ex, od = handles()
+        out = []
+        barrier()
+        t0 = time.perf_counter()
+        fid_prev = capi.frame_submit(ex, od, pinned[0][0])
+        for k in range(1, K):
+            fid = capi.frame_submit(ex, od, pinned[k][0])
+            out.append(capi.frame_wait(od, fid_prev))
+            fid_prev = fid
+        out.append(capi.frame_wait(od, fid_prev))
+        torch.cuda.synchronize()
+        ms = 1e3 * (time.perf_counter() - t0)
+        barrier()
+        ex.close(); od.close()
+        return reduce_max(ms), np.array(out)
+
     sampler = ClockSampler(local)
-    barrier()
     sampler.start()
-    e0.record(s_ex)
-    lib = capi.lib()
-    import ctypes as C
-    for k in range(K):
-        capi.check(lib.pf_frame_process_device(ex.h, od.h, C.c_void_p(dscans[k].data_ptr()), len(scans[k]), None))
-    e1.record(s_od)
-    capi.check(lib.pf_odom_sync(od.h))
-    barrier()
+    vals = [leg_value() for _ in range(REPS)]
     clocks = sampler.stop()
-    ms_dev = e0.elapsed_time(e1)
-    launches = ex.launches + od.launches - l0
-    hist = np.zeros((K - 1, 7))
-    capi.check(lib.pf_odom_get_pose_history(od.h, C.c_longlong(1), K - 1, hist.ctypes.data_as(C.c_void_p)))
-    poses_dev = np.concatenate([np.array([[0, 0, 0, 1, 0, 0, 0.0]]), hist])
-    stats = od.stats()
-    stats["graph_captures"] = od.graph_captures
-    ex.close(); od.close()
-
-    # ---- e2e (synchronous): one pf_frame_process per frame from pinned host memory ---------------------------------
-    ex, od = handles()
-    poses = []
-    barrier()
-    t0 = time.perf_counter()
-    for k in range(K):
-        poses.append(capi.frame_process(ex, od, pinned[k][0]))
-    torch.cuda.synchronize()
-    t_e2e_sync = time.perf_counter() - t0
-    barrier()
-    poses = np.array(poses)
-    ex.close(); od.close()
-
-    # ---- e2e (headline): the same host scans through pf_frame_submit / pf_frame_wait, one frame in flight ahead of the one
-    # whose pose is read back: every step still uploads its scan from pinned host memory and reads its pose back.
-    ex, od = handles()
-    poses_p = []
-    barrier()
-    t0 = time.perf_counter()
-    fid_prev = capi.frame_submit(ex, od, pinned[0][0])
-    for k in range(1, K):
-        fid = capi.frame_submit(ex, od, pinned[k][0])
-        poses_p.append(capi.frame_wait(od, fid_prev))
-        fid_prev = fid
-    poses_p.append(capi.frame_wait(od, fid_prev))
-    torch.cuda.synchronize()
-    t_e2e = time.perf_counter() - t0
-    barrier()
-    poses_p = np.array(poses_p)
-    assert poses_p.tobytes() == poses.tobytes(), "pipelined and synchronous frame calls disagree"
-    ex.close(); od.close()
-
-    t = torch.tensor([ms_dev, t_e2e * 1e3, t_e2e_sync * 1e3], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_dev_max, ms_e2e_max, ms_e2e_sync_max = float(t[0]), float(t[1]), float(t[2])
+    syncs = [leg_sync() for _ in range(REPS)]
+    e2es = [leg_e2e() for _ in range(REPS)]
+    ms_dev = float(np.median([v[0] for v in vals]))
+    ms_sync = float(np.median([v[0] for v in syncs]))
+    ms_e2e = float(np.median([v[0] for v in e2es]))
+    launches, poses_dev, stats = vals[-1][1], vals[-1][2], vals[-1][3]
+    poses = syncs[-1][1]
+    for v in vals:
+        assert v[2].tobytes() == poses_dev.tobytes(), "repetitions of the device-resident leg disagree"
+    for v in e2es + syncs:
+        assert v[1].tobytes() == poses.tobytes(), "pipelined and synchronous frame calls disagree"
     h2d = int(np.mean([len(s) for s in scans]) * 16)
+
+    # configs[4] as a fixed 8-sequence job: 8 / world sequences run concurrently on every GPU
+    multi = None
+    if os.environ.get("PF_BENCH_MULTI", "1") != "0":
+        names = shard.sequences_for_rank(rank, world)
+        ms_multi, mposes = multi_sequence_leg(pfb, capi, torch, names, K, local, barrier, reduce_max)
+        own = names.index(cfg) if cfg in names else -1
+        multi = {"sequences_total": shard.N_SEQUENCES, "sequences_per_gpu": len(names), "frames_per_sequence": K,
+                 "value": shard.N_SEQUENCES * K / (ms_multi * 1e-3), "unit": UNIT, "ms_whole_job": ms_multi,
+                 "scans_per_s_per_gpu": len(names) * K / (ms_multi * 1e-3),
+                 "api": "one (extractor, odometry) handle pair + host thread per sequence; pf_frame_submit / pf_frame_wait from pinned host scans",
+                 "poses_bit_identical_to_single_sequence_run": bool(own >= 0 and mposes[own].tobytes() == poses.tobytes())}
+        if world == 1 and rank == 0:       # how one GPU's throughput grows with the number of concurrent sequences
+            per = {}
+            for S in (1, 2, 4):
+                ms_s, _ = multi_sequence_leg(pfb, capi, torch, names[:S], K, local, barrier, reduce_max)
+                per[str(S)] = S * K / (ms_s * 1e-3)
+            per[str(len(names))] = multi["scans_per_s_per_gpu"]
+            multi["scans_per_s_on_one_gpu_vs_concurrent_sequences"] = per
 
     if rank == 0:
         roof = roofline_leg(pfb, capi, torch, scans[:8], dev)
         extra = extra_kernel_legs(capi, local)
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import oracle as O
+        if os.environ.get("PF_BENCH_SWEEP", "1") != "0":
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import sweep
+            sizes = tuple(float(x) for x in os.environ.get("PF_BENCH_SWEEP_SIZES", "1,2,5,10,20,50").split(","))
+            extra["sweep"] = sweep.run_sweep(capi, sizes, device=local, oracle=O)
         ncpu = min(K, 40)
         cpu_sps, cpu_dt, cpu_poses, kind = cpu_pipeline(scans[:ncpu], False)
+        cpu_knn = None
+        if "sweep" in extra:
+            for row in extra["sweep"]["rows"]:
+                if "cpu_kdtree" in row:
+                    cpu_knn = {"map_points": row["map_points"], **row["cpu_kdtree"], "gpu_queries_per_s_same_map": row["k4_queries_per_s_voxel_order"]}
+                    break
         line = {
-            "metric": METRIC, "value": world * K / (ms_dev_max * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms_dev_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64",
-            "data": "synthetic",
-            "config": {"workload": WORKLOAD if world == 1 else "configs[4]: independent 64-ring sequences (seeds 3000+rank), one per GPU",
-                       "frames_per_gpu": K, "points_per_scan": int(np.mean([len(s) for s in scans])),
-                       "l2": "every frame streams a new 1.8 MB scan; map state is the live working set (no replay of cached inputs)",
-                       "parallelism": f"replicas x{world}, no collective"},
-            "e2e": {"value": world * K / (ms_e2e_max * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(capi.lib().pf_odom_result_bytes()),
-                    "ms_per_step": ms_e2e_max / K,
+            "metric": METRIC, "value": world * K / (ms_dev * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64",
+            "data": "synthetic", "config": _config(world, K, scans),
+            "repetitions": {"timed_regions": REPS, "statistic": "median of the max-over-ranks times; every region is K frames on fresh handles",
+                            "value_ms": [v[0] for v in vals], "e2e_ms": [v[0] for v in e2es], "e2e_synchronous_ms": [v[0] for v in syncs]},
+            "e2e": {"value": world * K / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(capi.lib().pf_odom_result_bytes()),
+                    "ms_per_step": ms_e2e / K,
                     "api": "pf_frame_submit + pf_frame_wait (host pinned scan in, pose out; frame k+1 is submitted before the pose of frame k is read)",
-                    "synchronous": {"value": world * K / (ms_e2e_sync_max * 1e-3), "ms_per_step": ms_e2e_sync_max / K,
+                    "synchronous": {"value": world * K / (ms_sync * 1e-3), "ms_per_step": ms_sync / K,
                                     "api": "pf_frame_process (one blocking call per frame)"}},
             "gpu_launches": int(launches), "gpu_launches_per_step": launches / K,
             "roofline": roof,
             "knn_queries_per_s": extra["k4_knn"]["queries_per_s"],
+            "cpu_knn_queries_per_s": cpu_knn,
+            "multi_sequence": multi,
             "extra_kernels": extra,
             "cpu_baseline": {"value": cpu_sps, "unit": UNIT, "cores": 1, "kind": "port",
                              "sample": f"first {ncpu} frames of the same sequence, serial on one core: extraction = the reference's own "
                                        f"laserProcessingClass.cpp ({'compiled in place, oracle/_ref' if kind == 'reference' else 'restated'}), "
                                        "odometry/filter/map = oracle restatement (PCL/FLANN/Ceres are not buildable in this image)"},
+            "host": _host(),
             "clocks": clocks,
-            "accuracy": {"ate_vs_ground_truth_m": _ate(poses, gt), "ate_vs_ground_truth_m_device_leg": _ate(poses_dev, gt),
-                         "cpu_oracle_ate_m": _ate(cpu_poses, gt[:ncpu]),
+            "accuracy": {"frames_compared": ncpu,
+                         "ate_vs_ground_truth_m_first_frames": _ate(poses[:ncpu], gt[:ncpu]), "cpu_oracle_ate_m_first_frames": _ate(cpu_poses, gt[:ncpu]),
+                         "ate_vs_ground_truth_m_all_frames": _ate(poses, gt), "ate_vs_ground_truth_m_all_frames_device_leg": _ate(poses_dev, gt),
                          "max_abs_translation_diff_vs_cpu_oracle_m": float(np.abs(poses[:ncpu, 4:] - cpu_poses[:, 4:]).max())},
             "odom_stats_last_frame": stats,
         }

@@ -12,4 +12,11 @@ struct PointCloud {
     void push_back(const PointT& p) { points.push_back(p); width = (unsigned)points.size(); }
     std::size_t size() const { return points.size(); }
 };
+// pcl::copyPointCloud between point types: copies the fields both types have (x, y, z here), the rest keep their defaults
+template <class A, class B>
+void copyPointCloud(const PointCloud<A>& in, PointCloud<B>& out) {
+    out.points.resize(in.points.size());
+    for (std::size_t i = 0; i < in.points.size(); ++i) { B q; q.x = in.points[i].x; q.y = in.points[i].y; q.z = in.points[i].z; out.points[i] = q; }
+    out.width = (unsigned)out.points.size();
+}
 }  // namespace pcl

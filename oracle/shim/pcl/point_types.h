@@ -17,4 +17,10 @@ struct alignas(16) PointXYZI {
     float x = 0.f, y = 0.f, z = 0.f, w_ = 1.f;
     float intensity = 0.f, pad_[3] = {0.f, 0.f, 0.f};
 };
+// 32-byte layout of pcl::PointXYZRGB (xyz + padding, then b g r a packed in one word); used by the typed-adapter compile test only
+struct alignas(16) PointXYZRGB {
+    float x = 0.f, y = 0.f, z = 0.f, w_ = 1.f;
+    unsigned char b = 0, g = 0, r = 0, a = 255;
+    float pad_[3] = {0.f, 0.f, 0.f};
+};
 }  // namespace pcl

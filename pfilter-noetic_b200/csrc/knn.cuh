@@ -67,12 +67,10 @@ __device__ __forceinline__ bool knn5_warp(const KnnGrid& g, float qx, float qy, 
         if (yy >= 0 && yy < dy && zz >= 0 && zz < dz) {
             const long long x0 = cx - 1 < 0 ? 0 : cx - 1, x1 = cx + 1 >= dx ? dx - 1 : cx + 1;
             if (x0 <= x1) {
+                // the cell sort is a counting sort: cell c holds [cell_start[c], cell_end[c]) and cell_end[c] == cell_start[c + 1], so
+                // the three x-adjacent cells of a row are the one range [cell_start[first], cell_end[last]) -- two loads, not six
                 const long long base = (zz * dy + yy) * dx;
-                int s = 0x7fffffff, e = 0;
-                for (long long x = x0; x <= x1; ++x) {
-                    const int cs = g.cell_start[base + x], ce = g.cell_end[base + x];
-                    if (ce > cs) { s = min(s, cs); e = max(e, ce); }
-                }
+                const int s = __ldg(g.cell_start + base + x0), e = __ldg(g.cell_end + base + x1);
                 if (e > s) { rs = s; re = e; }
             }
         }

@@ -466,6 +466,9 @@ __global__ void __launch_bounds__(kNeTile, kNeCtasPerSm) k_normal_eq_stream(NeSt
 #pragma unroll
     for (int k = 0; k < kAcc; ++k) acc[k] = 0.0;
     __syncthreads();
+    unsigned phases = 0u;      // bit b: parity the next wait on stage b expects.  Only FULL tiles travel through a stage's barrier (a ragged
+                               // tile -- the last edge tile may sit in the middle of a CTA's sequence -- neither arrives nor waits), so the
+                               // parity is counted per completed wait, not derived from the tile number
     for (int j = 0; j < mine; ++j) {
         if (tid == 0 && j + kNeStages - 1 < mine) issue(j + kNeStages - 1);      // its buffer was released by the barrier below
         int kind, cnt; const double* src;
@@ -473,7 +476,9 @@ __global__ void __launch_bounds__(kNeTile, kNeCtasPerSm) k_normal_eq_stream(NeSt
         const int nd = kind == 0 ? 9 : 7;
         double v[9];
         if (cnt == kNeTile) {
-            mbar_wait(&s_bar[j % kNeStages], (unsigned)((j / kNeStages) & 1));
+            const int st = j % kNeStages;
+            mbar_wait(&s_bar[st], (phases >> st) & 1u);
+            phases ^= 1u << st;
             const double* sp = reinterpret_cast<const double*>(s_stage + (size_t)(j % kNeStages) * kNeStageBytes) + (size_t)tid * nd;
 #pragma unroll
             for (int k = 0; k < 9; ++k) v[k] = k < nd ? sp[k] : 0.0;

@@ -9,13 +9,22 @@ import torch
 import torch.distributed as dist
 
 
+N_SEQUENCES = 8     # BASELINE.json configs[4]: 8 independent sequences, seeds 3000..3007
+
+
 def sequence_for_rank(rank, world_size):
-    """Name of the synthetic sequence a rank processes (BASELINE.json configs[4]: seeds 3000..3007, one per GPU)."""
-    if world_size == 1:
-        return "cfg2"
+    """Name of the synthetic sequence a rank processes.  The same family at every world size (a 64-ring street sequence of the
+    configs[1] shape, seed 3000 + rank), so that the 1 / 2 / 4 / 8-GPU numbers compare like for like."""
     if not 0 <= rank < world_size:
         raise ValueError(f"rank {rank} outside world of {world_size}")
-    return f"cfg5.{rank % 8}"
+    return f"cfg5.{rank % N_SEQUENCES}"
+
+
+def sequences_for_rank(rank, world_size, total=N_SEQUENCES):
+    """configs[4] as a fixed job of `total` sequences: the ones this rank runs (concurrently on its GPU) at this world size."""
+    if not 0 <= rank < world_size:
+        raise ValueError(f"rank {rank} outside world of {world_size}")
+    return [f"cfg5.{k}" for k in range(total) if k % world_size == rank]
 
 
 def aggregate_throughput(frames_this_rank, elapsed_ms_this_rank, device=None):

@@ -55,3 +55,14 @@ def test_cpp_class_wrappers_compile():
     r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), "-x", "c++", "-"], input=src, text=True,
                        stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
     assert r.returncode == 0, r.stdout
+
+
+def test_typed_adapter_compiles_against_the_reference_call_sequence():
+    """include/pfilter_b200/compat_eigen_pcl.h: the node call sequences typed as the reference types them (pcl::PointCloud<...>::Ptr,
+    Eigen::Isometry3d, public members odom / laserCloudCornerMap / laserCloudSurfMap) compile and link against the C ABI.  Eigen and
+    PCL are the stand-ins under oracle/shim (neither exists in this image)."""
+    r = subprocess.run(["g++", "-std=c++17", "-O1", "-Wall", "-I", os.path.join(ROOT, "oracle", "shim"), "-I", os.path.join(ROOT, "include"),
+                        os.path.join(ROOT, "tests", "compat", "node_sequence.cpp"), "-o", os.path.join(ROOT, "tests", "compat", "node_sequence"),
+                        os.path.join(ROOT, "pfilter-noetic_b200", "libpfilter_b200.so"), os.path.join(ROOT, "pfilter-noetic_b200", "libpf_synth.so"),
+                        "-Wl,-rpath," + os.path.join(ROOT, "pfilter-noetic_b200")], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout

@@ -17,3 +17,38 @@ def test_cpp_harness_runs():
     print(r.stdout)
     assert r.returncode == 0, r.stdout
     assert "14 frames" in r.stdout
+
+
+def test_typed_adapter_sequence_matches_the_c_abi(pfb, capi):
+    """tests/compat/node_sequence.cpp (reference-typed calls through compat_eigen_pcl.h) gives the poses and map sizes of the same frames
+    through the plain C ABI."""
+    import numpy as np
+    exe = os.path.join(ROOT, "tests", "compat", "node_sequence")
+    if not os.path.exists(exe):      # built by __graft_entry__.build() / the CPU compile test
+        r = subprocess.run(["g++", "-std=c++17", "-O1", "-I", os.path.join(ROOT, "oracle", "shim"), "-I", os.path.join(ROOT, "include"),
+                            os.path.join(ROOT, "tests", "compat", "node_sequence.cpp"), "-o", exe,
+                            os.path.join(ROOT, "pfilter-noetic_b200", "libpfilter_b200.so"), os.path.join(ROOT, "pfilter-noetic_b200", "libpf_synth.so"),
+                            "-Wl,-rpath," + os.path.join(ROOT, "pfilter-noetic_b200")], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        assert r.returncode == 0, r.stdout
+    n = 6
+    r = subprocess.run([exe, str(n)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout
+    rows = [l.split() for l in r.stdout.splitlines() if l.startswith("frame")]
+    assert len(rows) == n
+    p = pfb.synth.config("cfg2")
+    ex = capi.Extractor(num_lines=64, max_points=262144)
+    od = capi.Odometry(0.4, 0, 0.4, 75)
+    for f in range(n):
+        s = pfb.synth.scan(p, f)
+        e, u, _ = ex.run(s, want_label=False)
+        if f == 0:
+            od.init_map(e, u)
+            pose = np.array([0, 0, 0, 1, 0, 0, 0.0])
+        else:
+            pose = od.update(e, u)
+        got = np.array([float(x) for x in rows[f][3:10]])
+        # the adapter hands the pose out as an Isometry3d and the test reads it back through Quaterniond(rotation()): 1e-12
+        assert np.abs(got - pose).max() < 1e-8, (f, got, pose)
+        assert int(rows[f][11]) == len(e) and int(rows[f][13]) == len(u)
+        assert int(rows[f][15]) == len(od.map_part(0)) and int(rows[f][17]) == len(od.map_part(1))
+    ex.close(); od.close()

@@ -49,6 +49,11 @@ def test_single_rank_passthrough():
     sys.path.insert(0, ROOT)
     from pf_loader import pfb  # noqa: F401
     from pfilter_noetic_b200 import shard
-    assert shard.sequence_for_rank(0, 1) == "cfg2"
+    assert shard.sequence_for_rank(0, 1) == "cfg5.0"          # the same sequence family at every world size
+    # configs[4] as a fixed 8-sequence job: every sequence is run exactly once at every world size
+    for world in (1, 2, 4, 8):
+        owned = [shard.sequences_for_rank(r, world) for r in range(world)]
+        assert sorted(sum(owned, [])) == [f"cfg5.{k}" for k in range(8)]
+        assert all(len(o) == 8 // world for o in owned)
     sps, ms, total = shard.aggregate_throughput(100, 50.0)
     assert total == 100 and ms == 50.0 and abs(sps - 2000.0) < 1e-9
