@@ -55,6 +55,25 @@ int pf_host_alloc(void** p, uint64_t bytes);
 int pf_host_free(void* p);
 
 /* ------------------------------------------------------------------------------------------------
+ * Scan packing (host side of the boundary): the float4 layout above from the forms the reference's callers hold a scan in.
+ * xyzi_out is any host buffer of cap_points x 16 bytes -- normally one from pf_host_alloc, so that the packed scan is what the
+ * H2D copy of pf_frame_process / pf_frame_submit reads.
+ * ---------------------------------------------------------------------------------------------- */
+/* sensor_msgs/PointCloud2 as the nodes receive it and pcl::fromROSMsg turns it into PointXYZI (src/laserProcessingNode.cpp:52-63):
+ * offsets and sensor_msgs/PointField datatype codes (1 INT8 .. 7 FLOAT32, 8 FLOAT64) of the x, y, z, intensity fields;
+ * off_intensity < 0 = no such field (intensity 0, as fromROSMsg leaves it); row_step 0 = point_step x width. */
+typedef struct pf_pc2_layout {
+    uint32_t point_step, row_step, width, height;
+    int32_t off_x, off_y, off_z, off_intensity;
+    uint8_t type_x, type_y, type_z, type_intensity;
+    uint8_t is_bigendian;     /* must be 0 */
+} pf_pc2_layout;
+int pf_pack_pointcloud2(const uint8_t* data, uint64_t data_bytes, const pf_pc2_layout* layout, float* xyzi_out, int cap_points, int* n_points);
+/* KITTI odometry velodyne/NNNNNN.bin (little-endian float32 x, y, z, reflectance): PF_ERR_CAPACITY when the file holds more points */
+int pf_read_kitti_bin(const char* path, float* xyzi_out, int cap_points, int* n_points);
+int pf_write_kitti_bin(const char* path, const float* xyzi, int n_points);
+
+/* ------------------------------------------------------------------------------------------------
  * Feature extraction  --  replaces LaserProcessingClass (include/laserProcessingClass.h:32-41)
  * ---------------------------------------------------------------------------------------------- */
 typedef struct pf_extract pf_extract;

@@ -102,6 +102,40 @@ def pinned_array(shape, dtype):
     return arr, p
 
 
+class Pc2Layout(C.Structure):
+    _fields_ = [("point_step", C.c_uint32), ("row_step", C.c_uint32), ("width", C.c_uint32), ("height", C.c_uint32),
+                ("off_x", C.c_int32), ("off_y", C.c_int32), ("off_z", C.c_int32), ("off_intensity", C.c_int32),
+                ("type_x", C.c_uint8), ("type_y", C.c_uint8), ("type_z", C.c_uint8), ("type_intensity", C.c_uint8), ("is_bigendian", C.c_uint8)]
+
+
+def pack_pointcloud2(data, point_step, fields, width, height=1, row_step=0, out=None):
+    """pf_pack_pointcloud2: PointCloud2 payload -> float32 [n, 4].  fields: {name: (offset, PointField datatype)}; `out` may be a pinned
+    [cap, 4] float32 array (pinned_array) -- the scan is packed straight into the buffer the H2D copy reads."""
+    buf = np.frombuffer(data, dtype=np.uint8)
+    n = int(width) * int(height)
+    res = out if out is not None else np.empty((max(n, 1), 4), np.float32)
+    assert res.dtype == np.float32 and res.ndim == 2 and res.shape[1] == 4 and res.flags["C_CONTIGUOUS"]
+    get = lambda k: fields.get(k, (-1, 7))
+    L = Pc2Layout(point_step, row_step, width, height, get("x")[0], get("y")[0], get("z")[0], get("intensity")[0],
+                  get("x")[1], get("y")[1], get("z")[1], get("intensity")[1], 0)
+    m = C.c_int()
+    check(lib().pf_pack_pointcloud2(_vp(buf), C.c_uint64(buf.size), C.byref(L), _vp(res), len(res), C.byref(m)))
+    return res[:m.value]
+
+
+def read_kitti_bin(path, out=None, cap_points=262144):
+    """pf_read_kitti_bin: velodyne .bin -> float32 [n, 4] (into `out`, e.g. a pinned array, when given)."""
+    res = out if out is not None else np.empty((cap_points, 4), np.float32)
+    m = C.c_int()
+    check(lib().pf_read_kitti_bin(os.fsencode(str(path)), _vp(res), len(res), C.byref(m)))
+    return res[:m.value]
+
+
+def write_kitti_bin(path, xyzi):
+    a = as_points(xyzi)
+    check(lib().pf_write_kitti_bin(os.fsencode(str(path)), _vp(a), len(a)))
+
+
 class Extractor:
     """Handle of pf_extract_* (replaces LaserProcessingClass)."""
 

@@ -52,3 +52,31 @@ def test_typed_adapter_sequence_matches_the_c_abi(pfb, capi):
         assert int(rows[f][11]) == len(e) and int(rows[f][13]) == len(u)
         assert int(rows[f][15]) == len(od.map_part(0)) and int(rows[f][17]) == len(od.map_part(1))
     ex.close(); od.close()
+
+
+def test_packed_scans_through_the_frame_pipeline(pfb, capi, tmp_path):
+    """F4 on the boundary's side: scan -> KITTI .bin -> pf_read_kitti_bin into a pinned buffer -> pf_frame_process, and scan ->
+    PointCloud2 payload -> pf_pack_pointcloud2 -> pf_frame_process, give the poses of the direct call, bit for bit."""
+    import numpy as np
+    io = __import__("pfilter_noetic_b200.io", fromlist=["io"])
+    p = pfb.synth.config("cfg2")
+    scans = [pfb.synth.scan(p, f) for f in range(5)]
+
+    def run(feed):
+        ex = capi.Extractor(num_lines=64, max_points=131072)
+        od = capi.Odometry(0.4, 0, 0.4, 75, max_map_points=1 << 19)
+        out = np.array([capi.frame_process(ex, od, feed(k)) for k in range(len(scans))])
+        ex.close(); od.close()
+        return out
+    direct = run(lambda k: scans[k])
+    pin, ptr = capi.pinned_array((131072, 4), np.float32)
+    for k, s in enumerate(scans):
+        capi.write_kitti_bin(tmp_path / f"{k:06d}.bin", s)
+    via_bin = run(lambda k: capi.read_kitti_bin(tmp_path / f"{k:06d}.bin", out=pin))
+    assert via_bin.tobytes() == direct.tobytes()
+
+    def via_msg(k):
+        data, step, fields = io.xyzi_to_pointcloud2(scans[k])
+        return capi.pack_pointcloud2(data, step, fields, len(scans[k]), out=pin)
+    assert run(via_msg).tobytes() == direct.tobytes()
+    capi.host_free(ptr)
