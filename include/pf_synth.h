@@ -8,7 +8,7 @@
 extern "C" {
 #endif
 
-enum { PF_SYNTH_SCENE_STREET = 0, PF_SYNTH_SCENE_CAMPUS = 1, PF_SYNTH_SCENE_CAMPUS_DENSE = 2 };
+enum { PF_SYNTH_SCENE_STREET = 0, PF_SYNTH_SCENE_CAMPUS = 1, PF_SYNTH_SCENE_CAMPUS_DENSE = 2, PF_SYNTH_SCENE_STREET_DENSE = 3 };
 enum { PF_SYNTH_TRAJ_STREET = 0, PF_SYNTH_TRAJ_LOOP = 1 };
 
 typedef struct pf_synth_params {

@@ -63,6 +63,9 @@ __global__ void k_grid_geom(GridBuild G) {
         geom[3 + a] = (int)(d > 0x7fffffff ? 0x7fffffff : d);
         prod = (d > (1ll << 40) || prod > (1ll << 40)) ? (1ll << 41) : prod * d;
     }
+    // a non-positive extent can only come from non-finite coordinates (a diverged pose turns the appended points into NaN / inf):
+    // treated like an extent beyond the capacity -- the grid is void and the frame reports it
+    if (geom[3] <= 0 || geom[4] <= 0 || geom[5] <= 0) prod = (1ll << 41);
     if (prod > kGridCellCap) {   // map extent larger than the search grid capacity
         atomicOr(&G.state[15], 1u);
         for (int a = 0; a < 3; ++a) geom[3 + a] = 0;
@@ -95,6 +98,11 @@ __global__ void __launch_bounds__(256) k_grid_count(GridBuild G, uint32_t* __res
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const Pt p = m[i];
         const int cx = (int)floorf(p.x) - ox, cy = (int)floorf(p.y) - oy, cz = (int)floorf(p.z) - oz;
+        if ((unsigned)cx >= (unsigned)dx || (unsigned)cy >= (unsigned)dy || (unsigned)cz >= (unsigned)dz) {     // NaN coordinate: not in any cell
+            keys[base + i] = 0xffffffffu;
+            atomicOr(&G.state[15], 2u);
+            continue;
+        }
         const unsigned cell = (unsigned)(cx + (cy + cz * dy) * dx);
         keys[base + i] = cell;
         atomicAdd(&cs[cell], 1);
@@ -159,6 +167,7 @@ __global__ void __launch_bounds__(256) k_grid_scatter(GridBuild G, const uint32_
     int* ce = G.cell_end[kind];
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const Pt v = m[i];
+        if (keys[base + i] == 0xffffffffu) continue;
         const int pos = atomicAdd(&ce[keys[base + i]], 1);
         G.pts[kind][pos] = make_float4(v.x, v.y, v.z, __int_as_float(i));
     }

@@ -110,6 +110,9 @@ __global__ void __launch_bounds__(256) k_append(AppendParams A) {
         if (tot > A.map_cap) { atomicOr(&A.sh->err, 1); tot = A.map_cap; }
         A.sh->n_app[A.slot[kind]] = tot;
         if (kind == 0 && A.write_pose) {
+            bool finite = true;
+            for (int i = 0; i < 7; ++i) finite = finite && isfinite(s_pose[i]);
+            if (!finite) atomicOr(&A.sh->err, (int)kErrPose);
             quat_to_mat(s_pose, A.sh->odom.R);
             for (int i = 0; i < 3; ++i) A.sh->odom.t[i] = s_pose[4 + i];
             const int hist_slot = (int)((A.sh->frame + 1) % kPoseHist);      // this update is frame (last finished + 1)
@@ -646,6 +649,11 @@ int enqueue_update(pf_odom* h, const float4* const feat_in[kKinds], const int* c
 // device error bits of a frame -> status + text
 int decode_frame_error(const pf_odom* h, int err) {
     if (err == 0) return PF_OK;
+    if (err & (int)kErrPose) {
+        // the reference has no such check: once the maps run empty its constant-velocity prediction (:235-240) doubles every frame
+        set_error("the pose is no longer finite: tracking was lost (the reference would go on publishing NaN here)");
+        return PF_ERR_STATE;
+    }
     if (err & 1) set_error("local map exceeded max_map_points = %d", h->mcap);
     else if (err & (int)kErrMergeMask)
         set_error("map update failed (bits %d: 2 = voxel coordinates outside the key range, 4 = more than %d centroids left their voxel, 8 / 16 = internal)",

@@ -27,6 +27,7 @@ constexpr unsigned kErrMergeMask = 30u;   // map update: 2 voxel coordinate rang
 constexpr unsigned kErrGrid = 32u;        // map extent exceeds the search grid (kGridCellCap cells of 1 m)
 constexpr unsigned kErrVoxel = 64u;       // VoxelGrid index space exceeds 31 bits (pcl::VoxelGrid's "leaf size too small" case)
 constexpr unsigned kErrRing = 128u;       // a scan ring exceeded the extractor's max_ring_points (the ring was dropped)
+constexpr unsigned kErrPose = 256u;       // the solved pose is not finite: tracking was lost and the prediction ran away
 
 struct Workspace {
     cudaStream_t stream = nullptr;

@@ -100,8 +100,11 @@ Scene build_campus(uint64_t seed, double half) {
     for (int i = 0; i < nb; ++i) {
         double cx = rng.uni(-half, half), cy = rng.uni(-half, half);
         double r = std::sqrt(cx * cx + cy * cy);
-        if (r > 52.0 && r < 68.0) continue;          // keep the driving loop (radius 60 m) free
         double lx = rng.uni(2.0, 14.0), ly = rng.uni(2.0, 14.0), h = rng.uni(2.0, 9.0);
+        // keep the driving loop (radius 60 m about the origin) free: no part of a box within 4 m of it -- a box CENTRE outside the
+        // band is not enough, the sensor would drive through the corner of a large box and lose every return inside the range gate
+        const double half_diag = 0.5 * std::sqrt(lx * lx + ly * ly);
+        if (r - half_diag < 64.0 && r + half_diag > 56.0) continue;
         add_box(sc, cx - lx / 2, cx + lx / 2, cy - ly / 2, cy + ly / 2, sc.ground_z, sc.ground_z + h);
     }
     for (int i = 0; i < 400; ++i) {
@@ -125,6 +128,23 @@ Scene build_campus_dense(uint64_t seed, double half) {
         if (r > 56.0 && r < 64.0) continue;
         double sx = rng.uni(2.0, 9.0), sy = rng.uni(2.0, 9.0), z0 = sc.ground_z + rng.uni(0.0, 3.0), h = rng.uni(2.0, 10.0);
         Volume v{{cx - sx / 2, cy - sy / 2, z0}, {cx + sx / 2, cy + sy / 2, z0 + h}, rng.uni(0.15, 0.6)};
+        sc.volumes.push_back(v);
+    }
+    return sc;
+}
+
+// "dense street": the planes+poles street with volumetric scatter (hedges, tree crowns) on both sides of the lane -- the odometry keeps
+// tracking here for thousands of frames (the campus loop does not: the reference algorithm's yaw diverges after ~540 frames), and
+// almost every scatter return opens a new voxel, which is what makes a persistent local map grow.
+Scene build_street_dense(uint64_t seed, double x_begin, double x_end) {
+    Scene sc = build_street(seed, x_begin, x_end);
+    Rng rng(seed * 32452843ull + 5);
+    const int nvol = (int)((x_end - x_begin) / 1.5);
+    for (int i = 0; i < nvol; ++i) {
+        const double cx = rng.uni(x_begin, x_end), side = rng.uni() < 0.5 ? -1.0 : 1.0;
+        const double sx = rng.uni(1.5, 6.0), sy = rng.uni(1.0, 4.0), z0 = sc.ground_z + rng.uni(0.0, 3.0), h = rng.uni(1.5, 6.0);
+        const double cy = side * rng.uni(4.0 + sy / 2, 11.0);       // clear of the lane (the trajectory weaves within |y| < 1.5)
+        Volume v{{cx - sx / 2, cy - sy / 2, z0}, {cx + sx / 2, cy + sy / 2, z0 + h}, rng.uni(0.1, 0.5)};
         sc.volumes.push_back(v);
     }
     return sc;
@@ -166,7 +186,8 @@ Cache g_cache;
 const Scene& scene_for(const pf_synth_params& p) {
     if (!g_cache.valid || g_cache.key.seed != p.seed || g_cache.key.scene != p.scene) {
         g_cache.scene = p.scene == PF_SYNTH_SCENE_STREET ? build_street(p.seed, -60.0, 1200.0)
-                      : p.scene == PF_SYNTH_SCENE_CAMPUS ? build_campus(p.seed, 110.0) : build_campus_dense(p.seed, 110.0);
+                      : p.scene == PF_SYNTH_SCENE_CAMPUS ? build_campus(p.seed, 110.0)
+                      : p.scene == PF_SYNTH_SCENE_CAMPUS_DENSE ? build_campus_dense(p.seed, 110.0) : build_street_dense(p.seed, -60.0, 1200.0);
         g_cache.key = p;
         g_cache.valid = true;
     }

@@ -5,7 +5,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SCENE_STREET, SCENE_CAMPUS, SCENE_CAMPUS_DENSE = 0, 1, 2
+SCENE_STREET, SCENE_CAMPUS, SCENE_CAMPUS_DENSE, SCENE_STREET_DENSE = 0, 1, 2, 3
 TRAJ_STREET, TRAJ_LOOP = 0, 1
 
 
@@ -66,6 +66,10 @@ def config(name):
         return params(sensor_lines=64, seed=2022)
     if name == "cfg4":                       # 32-ring slow campus loop
         return params(sensor_lines=32, seed=2023, scene=SCENE_CAMPUS, trajectory=TRAJ_LOOP, speed=0.15)
+    if name == "cfg4s":                      # 32-ring, low speed, along the planes+poles street (tracks for thousands of frames)
+        return params(sensor_lines=32, seed=2023, speed=0.15)
+    if name == "cfg4sd":                     # the same with volumetric scatter beside the lane: map-growth stress (filter off)
+        return params(sensor_lines=32, seed=2023, scene=SCENE_STREET_DENSE, speed=0.15)
     if name == "cfg4d":                      # the same loop through the campus with volumetric scatter (foliage): map-growth stress
         return params(sensor_lines=32, seed=2023, scene=SCENE_CAMPUS_DENSE, trajectory=TRAJ_LOOP, speed=0.15)
     if name.startswith("cfg5."):             # 8 independent 64-ring sequences, seeds 3000..3007

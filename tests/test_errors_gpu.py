@@ -91,3 +91,47 @@ def test_pose_history_range_copy(pfb, capi):
     capi.check(capi.lib().pf_odom_get_pose_history(od.h, C.c_longlong(1), 5, hist.ctypes.data_as(C.c_void_p)))
     assert hist.tobytes() == np.array(poses[1:]).tobytes()
     ex.close(); od.close()
+
+
+def test_non_finite_map_points_are_an_error_not_a_crash(capi):
+    """A diverged pose turns appended points into inf / NaN; the search-grid build must flag them, not index with them."""
+    rng = np.random.default_rng(8)
+    xyz = (rng.random((20000, 3), dtype=np.float32) - 0.5) * np.array([60, 60, 6], np.float32)
+    q = np.zeros((100, 4), np.float32)
+    q[:, :3] = xyz[:100] + 0.05
+    for bad in (np.inf, -np.inf, np.nan):
+        m = xyz.copy()
+        m[777, 1] = bad
+        with pytest.raises(capi.PfError) as e:
+            capi.knn5(capi.make_points(m), q)
+        assert e.value.status == -3
+    idx, d2 = capi.knn5(capi.make_points(xyz), q)          # the device is still healthy
+    assert (idx[:, 0] == np.arange(100)).all()
+
+
+def test_tracking_loss_is_reported(pfb, capi):
+    """The campus loop (cfg4) is where the reference algorithm itself loses its yaw estimate after ~540 frames; its constant-velocity
+    prediction then doubles every frame until the pose is inf / NaN.  The GPU path must end that run with an error status."""
+    from concurrent.futures import ThreadPoolExecutor
+    p = pfb.synth.config("cfg4")
+    pfb.synth.scan(p, 0)
+    with ThreadPoolExecutor(8) as tp:
+        scans = list(tp.map(lambda f: pfb.synth.scan(p, f), range(900)))
+    ex = capi.Extractor(num_lines=32, max_points=57600)
+    od = capi.Odometry(0.4, 0, 1.0, 200, max_map_points=1 << 20, max_features=57600)
+    status = None
+    for k, s in enumerate(scans):
+        try:
+            pose = capi.frame_process(ex, od, s)
+        except capi.PfError as e:
+            status = e.status
+            break
+        if not np.isfinite(pose).all():
+            status = "nan pose returned"
+            break
+    # either the run survives (tracking kept) or it ends with a status -- never a CUDA fault (-2) and never a silent NaN
+    assert status in (None, -3, -4), status
+    ex.close(); od.close()
+    ex = capi.Extractor(num_lines=32, max_points=57600)      # and the device is still usable
+    ex.run(scans[0])
+    ex.close()

