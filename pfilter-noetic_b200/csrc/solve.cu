@@ -40,6 +40,10 @@ __device__ __forceinline__ double residual_weight(int weight_type, double obs, d
 
 // `weight` scales the RESIDUAL only, never the Jacobian, and only when the functor's own test passes: the edge functor
 // wants exactly 1, 2 or 12 (src/lidarOptimization.cpp:25-28), the surf functor anything but 0 (:62-63).
+// kFma: accumulate J^T J and J^T r with fused multiply-adds (the library is built with -fmad=false so that every product rounds like
+// the CPU reference; the map-sweep kernel, whose sums are compared at 1e-10 and whose fp64 issue rate matters, may fuse the 27
+// accumulations -- PF_NE_FMA)
+template <bool kFma = false>
 __device__ __forceinline__ void eval_one(int kind, D3 p, const double* ge, const double* Rm, const double* tv, double weight, double acc[kAcc]) {
     const D3 lp = d3(Rm[0] * p.x + Rm[1] * p.y + Rm[2] * p.z + tv[0], Rm[3] * p.x + Rm[4] * p.y + Rm[5] * p.z + tv[1],
                      Rm[6] * p.x + Rm[7] * p.y + Rm[8] * p.z + tv[2]);
@@ -80,10 +84,10 @@ __device__ __forceinline__ void eval_one(int kind, D3 p, const double* ge, const
 #pragma unroll
     for (int a = 0; a < 6; ++a) {
 #pragma unroll
-        for (int b = a; b < 6; ++b) acc[t++] += J[a] * J[b];
+        for (int b = a; b < 6; ++b) { acc[t] = kFma ? fma(J[a], J[b], acc[t]) : acc[t] + J[a] * J[b]; ++t; }
     }
 #pragma unroll
-    for (int a = 0; a < 6; ++a) acc[21 + a] += J[a] * r;
+    for (int a = 0; a < 6; ++a) acc[21 + a] = kFma ? fma(J[a], r, acc[21 + a]) : acc[21 + a] + J[a] * r;
     acc[27] += 0.5 * rho0;
     acc[28] += 1.0;
 }
@@ -412,10 +416,10 @@ int lm_solve(cudaStream_t stream, const LmParams& P, const double* pose_src, int
 // conflict-free for 8-byte accesses), accumulates the 29 sums in fp64 registers; shuffle tree + shared memory per CTA, one partial
 // per CTA in global memory, and the last CTA to finish (ticket) adds the partials in CTA order -- deterministic.
 #ifndef PF_NE_STAGES
-#define PF_NE_STAGES 3
+#define PF_NE_STAGES 4
 #endif
 #ifndef PF_NE_CTAS
-#define PF_NE_CTAS 3
+#define PF_NE_CTAS 2
 #endif
 constexpr int kNeTile = 256, kNeStages = PF_NE_STAGES, kNeCtasPerSm = PF_NE_CTAS;
 constexpr int kNeStageBytes = kNeTile * 72;
@@ -486,7 +490,11 @@ __global__ void __launch_bounds__(kNeTile, kNeCtasPerSm) k_normal_eq_stream(NeSt
 #pragma unroll
             for (int k = 0; k < 9; ++k) v[k] = k < nd ? src[(size_t)tid * nd + k] : 0.0;
         }
-        if (tid < cnt) eval_one(kind, d3(v[0], v[1], v[2]), v + 3, Rm, tv, 0.0, acc);
+#ifdef PF_NE_FMA
+        if (tid < cnt) eval_one<true>(kind, d3(v[0], v[1], v[2]), v + 3, Rm, tv, 0.0, acc);
+#else
+        if (tid < cnt) eval_one<false>(kind, d3(v[0], v[1], v[2]), v + 3, Rm, tv, 0.0, acc);
+#endif
         __syncthreads();
     }
 #pragma unroll
