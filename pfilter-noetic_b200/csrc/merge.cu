@@ -431,189 +431,6 @@ __global__ void __launch_bounds__(256, 8) k_mm_write(MapMergeParams P) {
     }
 }
 
-// ---- single-pass variant (opt-in, PF_MM_VARIANT=1; slower than the two passes -- see DESIGN.md "K9 single pass") --------------
-// One streaming pass with a decoupled look-back: tiles of 1024 map points are handed out by ticket in ascending order, a tile
-// is bulk-copied into shared memory (cp.async.bulk + mbarrier), counted, its count published, its output offset found by
-// looking back over its predecessors' counts, and written from shared memory.  Traffic: 16 B read per map point + 16 B
-// written per surviving voxel (the two-pass form reads the map twice).
-constexpr int kSingleCtas = 6;      // resident CTAs per SM (2 x 16 KB buffers each)
-
-__global__ void __launch_bounds__(256, kSingleCtas) k_mm_single(MapMergeParams P, unsigned long long* status, unsigned* ctrl) {
-    PF_PDL_ENTRY();
-    const int cloud = blockIdx.y;
-    const MapMergeCloud& c = P.c[cloud];
-    __shared__ __align__(128) Pt s_buf[2][kMergeTile];
-    __shared__ __align__(8) unsigned long long s_bar[2];
-    __shared__ unsigned s_mask[2][32];          // kept ballots of the 32 rows (warp w: rows 4 w .. 4 w + 3)
-    __shared__ int s_cnt[2][8];                 // kept per warp
-    __shared__ int s_segpre[33];                // crowded tiles only: exclusive kept-prefix of the rows, [32] = kept in the tile
-    __shared__ int s_next[2];
-    __shared__ unsigned s_excl;
-    const int mA = *c.n_sorted;
-    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-    const int lbase = cloud * P.s.cap;
-    const int ni_all = (int)P.state[6 + cloud];
-    if (mA == 0) {       // first update after initMapWithPoints: everything is an insert, already in key order
-        for (int e = blockIdx.x * 256 + tid; e < ni_all; e += gridDim.x * 256) c.out[e] = P.s.i_pt[lbase + e];
-        if (blockIdx.x == 0 && tid == 0) *c.n_sorted_out = ni_all;
-        return;
-    }
-    const int ntiles = mA / kMergeTile + 1;     // the last tile also takes the inserts behind the last map point
-    const int* m_ra = P.s.m_ra + lbase;
-    const int* i_ra = P.s.i_ra + lbase;
-    const int* tm = P.s.tile_m + (size_t)cloud * P.s.tile_cap;
-    const int* ti = P.s.tile_i + (size_t)cloud * P.s.tile_cap;
-    const CropBox box = crop_of(P.center);
-    const unsigned long long ep = ((unsigned long long)(((ctrl[0] << 3) | 4u) & 0x3fffffffu)) << 34;
-    status += (size_t)cloud * P.s.tile_cap;
-    const unsigned full = 0xffffffffu;
-    auto issue = [&](int t, int b) {            // thread 0: start the copy of tile t into buffer b
-        const int n = min(kMergeTile, mA - t * kMergeTile);
-        if (n > 0) bulk_load(&s_buf[b][0], c.buf + (size_t)t * kMergeTile, (unsigned)n * 16u, &s_bar[b]);
-    };
-    int held = 0;                               // thread 0: the ticket behind the tile in flight
-    if (tid == 0) {
-        mbar_init(&s_bar[0], 1u);
-        mbar_init(&s_bar[1], 1u);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        held = (int)atomicAdd(&ctrl[7 + cloud], 1u);
-    }
-    __syncthreads();
-    int tile = 0;
-    unsigned phases = 0u;                       // bit b: parity the next wait on buffer b expects
-    for (int par = 0;; par ^= 1) {
-        if (tid == 0) {
-            // the ticket was taken behind the previous tile's look-back (its latency hides behind the stores); buffer par and
-            // the small arrays of the tile before the previous one are free: every thread passed two barriers since
-            s_next[par] = held;
-            if (held < ntiles) issue(held, par);
-        }
-        __syncthreads();
-        tile = s_next[par];
-        if (tile >= ntiles) break;
-        const int base = tile * kMergeTile;
-        const int nload = min(kMergeTile, mA - base);
-        Pt* buf = &s_buf[par][0];
-        const int wrow = w * 128;               // first slot of this warp's four rows
-        const int mLo = tm[tile], mHi = tm[tile + 1], iLo = ti[tile], iHi = ti[tile + 1];
-        const int nm = mHi - mLo, ni = iHi - iLo;
-        // the few matched voxels / inserts of the tile sit one per lane (ascending map index); longer lists: binary search
-        const int m_slot = lane < nm ? m_ra[mLo + lane] - base : 0x7fffffff;
-        const int i_slot = lane < ni ? i_ra[iLo + lane] - base : 0x7fffffff;
-        if (nload > 0) { mbar_wait(&s_bar[par], (phases >> par) & 1u); phases ^= 1u << par; }    // the lists travel while the tile does
-        int wkept = 0;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int row = wrow + k * 32;
-            const int i = base + row + lane;
-            unsigned mm = 0u;                   // lanes of this row whose slot may hold a matched voxel
-            if (nm > 0) mm = nm > 32 ? full : __reduce_or_sync(full, (unsigned)(m_slot - row) < 32u ? 1u << ((m_slot - row) & 31) : 0u);
-            bool keep = false;
-            if (i < mA) {
-                Pt p = buf[row + lane];
-                if (in_box(box, p)) {
-                    int h = mHi;
-                    if (mm >> lane & 1u) { h = lower_bound_i(m_ra, mLo, mHi, i); if (h < mHi && m_ra[h] != i) h = mHi; }
-                    if (h == mHi) {     // the voxel keeps its single point: x / 1 = x, counters from the point itself
-                        keep = single_point_kept(P, p.rgba);
-                        const unsigned r = pt_r(p.rgba);
-                        buf[row + lane].rgba = pack_rgba(r > 250u ? 255u : r + 2u, pt_g(p.rgba), 0u, 255u);
-                    } else {            // finished in k_mm_heads
-                        p = P.s.m_pt[lbase + h];
-                        keep = (p.rgba >> 24) != 0u;
-                        buf[row + lane] = p;
-                    }
-                }
-            }
-            const unsigned mk = __ballot_sync(full, keep);
-            wkept += __popc(mk);
-            if (lane == 0) s_mask[par][w * 4 + k] = mk;
-        }
-        if (lane == 0) s_cnt[par][w] = wkept;
-        __syncthreads();
-        const int cw = lane < 8 ? s_cnt[par][lane] : 0;
-        const int kept = __reduce_add_sync(full, cw);
-        if (w == 0) {       // this tile's output offset: decoupled look-back over 32 predecessors at a time
-            const unsigned aggregate = (unsigned)(kept + ni);
-            if (lane == 0) st_relaxed_u64(status + tile, ep | ((tile == 0 ? 2ull : 1ull) << 32) | aggregate);
-            unsigned excl = 0;
-            for (int look = tile - 1; look >= 0; look -= 32) {
-                const int t = look - lane;
-                unsigned flag = 2u, val = 0u;          // virtual tiles in front of tile 0: inclusive prefix 0
-                if (t >= 0) {
-                    unsigned long long v;
-                    do { v = ld_relaxed_u64(status + t); } while ((v >> 34) != (ep >> 34) || ((v >> 32) & 3ull) == 0);
-                    flag = (unsigned)((v >> 32) & 3ull);
-                    val = (unsigned)v;
-                }
-                const unsigned pmask = __ballot_sync(full, flag == 2u);
-                const int first_p = __ffs(pmask) - 1;  // nearest predecessor holding an inclusive prefix
-                excl += __reduce_add_sync(full, (pmask == 0u || lane <= first_p) ? val : 0u);
-                if (pmask) break;
-            }
-            if (lane == 0) {
-                if (tile != 0) st_relaxed_u64(status + tile, ep | (2ull << 32) | (excl + aggregate));
-                if (tile == ntiles - 1) *c.n_sorted_out = (int)(excl + aggregate);
-                s_excl = excl;
-            }
-        }
-        __syncthreads();
-        const int gbase = (int)s_excl;
-        if (tid == 0) held = (int)atomicAdd(&ctrl[7 + cloud], 1u);     // next tile's ticket: its latency hides behind the stores
-        int rowpre = gbase + __reduce_add_sync(full, lane < w ? cw : 0);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int row = wrow + k * 32;
-            int ins_before = 0;                 // inserts in front of every kept point of this row, if no insert falls inside it
-            bool ins_search = false;
-            if (ni > 0) {
-                if (ni > 32) {
-                    ins_search = true;
-                } else {
-                    ins_before = __popc(__ballot_sync(full, i_slot < row));
-                    ins_search = ins_before != __popc(__ballot_sync(full, i_slot < row + 32));
-                }
-            }
-            const unsigned mk = s_mask[par][w * 4 + k];
-            if (mk >> lane & 1u) {
-                int pos = rowpre + __popc(mk & lanemask_lt());
-                pos += ins_search ? lower_bound_i(i_ra, iLo, iHi, base + row + lane + 1) - iLo : ins_before;      // inserts in front of this point
-                *reinterpret_cast<float4*>(c.out + pos) = *reinterpret_cast<const float4*>(&buf[row + lane]);
-            }
-            rowpre += __popc(mk);
-        }
-        if (ni > 64) {          // crowded tile (CTA-uniform): one thread per insert over a shared prefix table
-            if (w == 0) {
-                const int cnt = __popc(s_mask[par][lane]);
-                int x = cnt;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const int y = __shfl_up_sync(full, x, o);
-                    if (lane >= o) x += y;
-                }
-                s_segpre[lane] = x - cnt;
-                if (lane == 31) s_segpre[32] = x;
-            }
-            __syncthreads();
-            for (int e = iLo + tid; e < iHi; e += 256) {
-                const int s = i_ra[e] - base;      // the insert goes in front of slot s; s >= 1024: behind the last map point
-                const int before = s >= kMergeTile ? kept : s_segpre[s >> 5] + __popc(s_mask[par][s >> 5] & ((1u << (s & 31)) - 1u));
-                c.out[gbase + before + (e - iLo)] = P.s.i_pt[lbase + e];
-            }
-        } else if (ni > 0) {    // a few inserts: one warp each
-            const unsigned mw = s_mask[par][lane];
-            const int cm = __popc(mw);
-            for (int e = iLo + w; e < iHi; e += 8) {
-                const int s = i_ra[e] - base;
-                const int seg = s >> 5;            // 32: behind the last map point
-                const int part = lane < seg ? cm : (lane == seg ? __popc(mw & ((1u << (s & 31)) - 1u)) : 0);
-                const int before = __reduce_add_sync(full, part);
-                if (lane == 0) c.out[gbase + before + (e - iLo)] = P.s.i_pt[lbase + e];
-            }
-        }
-    }
-}
-
 __global__ void __launch_bounds__(256) k_mm_finish(MapMergeParams P) {
     PF_PDL_ENTRY();
     const int cloud = blockIdx.x;
@@ -630,12 +447,6 @@ __global__ void __launch_bounds__(256) k_mm_finish(MapMergeParams P) {
 
 }  // namespace
 
-// PF_MM_VARIANT (read once): 0 = count pass + write pass (default), 1 = single pass (k_mm_single)
-static int merge_variant() {
-    static const int v = [] { const char* e = getenv("PF_MM_VARIANT"); return e ? atoi(e) : 0; }();
-    return v;
-}
-
 int map_merge_scratch_create(MapMergeScratch& s, int cap_b, int exc_cap, int cap_a) {
     s.cap = cap_b;
     s.exc_cap = exc_cap;
@@ -644,8 +455,6 @@ int map_merge_scratch_create(MapMergeScratch& s, int cap_b, int exc_cap, int cap
     PF_CUDA(cudaMalloc(&s.tile_i, sizeof(int) * 2 * (size_t)s.tile_cap));
     PF_CUDA(cudaMalloc(&s.tile_agg, sizeof(int) * 2 * (size_t)s.tile_cap));
     PF_CUDA(cudaMalloc(&s.cta_sum, sizeof(int) * 2 * kMergeMaxGrid));
-    PF_CUDA(cudaMalloc(&s.fstatus, sizeof(unsigned long long) * 2 * (size_t)s.tile_cap));
-    PF_CUDA(cudaMemset(s.fstatus, 0, sizeof(unsigned long long) * 2 * (size_t)s.tile_cap));
     const size_t n = (size_t)2 * cap_b;
     PF_CUDA(cudaMalloc(&s.m_ra, sizeof(int) * n));
     PF_CUDA(cudaMalloc(&s.m_pt, sizeof(Pt) * n));
@@ -658,7 +467,7 @@ int map_merge_scratch_create(MapMergeScratch& s, int cap_b, int exc_cap, int cap
 
 void map_merge_scratch_destroy(MapMergeScratch& s) {
     cudaFree(s.m_ra); cudaFree(s.m_pt); cudaFree(s.m_delta); cudaFree(s.i_ra); cudaFree(s.i_pt); cudaFree(s.exc);
-    cudaFree(s.tile_m); cudaFree(s.tile_i); cudaFree(s.tile_agg); cudaFree(s.cta_sum); cudaFree(s.fstatus);
+    cudaFree(s.tile_m); cudaFree(s.tile_i); cudaFree(s.tile_agg); cudaFree(s.cta_sum);
     s = MapMergeScratch();
 }
 
@@ -691,12 +500,7 @@ int map_merge(Workspace& ws, const MapMergeParams& P_in, int capB0, int capB1, i
     if (grid > kMergeMaxGrid) grid = kMergeMaxGrid;
 
     if (ws.ev_a) cudaEventRecord(ws.ev_a, ws.stream);
-    if (merge_variant() == 1) {
-        // single streaming pass: persistent CTAs, tiles by ticket
-        const int fgrid = mtiles_all < kSingleCtas * kSMs ? mtiles_all : kSingleCtas * kSMs;
-        PF_CUDA(launch_pdl(k_mm_single, dim3(fgrid, 2), dim3(256), 0, ws.stream, P, P.s.fstatus, ws.ctrl));
-        ws.launches += 4;
-    } else {
+    {
         // count pass: 8 CTAs per SM at 32 registers without a register prefetch measured 3 % faster than 5 CTAs with one
         // (PF_MM_COUNT=0 selects the prefetching form)
         static const int count_variant = [] { const char* e = getenv("PF_MM_COUNT"); return e ? atoi(e) : 1; }();

@@ -39,7 +39,6 @@ struct MapMergeScratch {     // sized by the capacity of B (both clouds together
     int cap;                                      // entries per list and cloud half: cloud c uses [c * cap, (c + 1) * cap)
     int* tile_m;  int* tile_i;   int tile_cap;    // [2][tile_cap] first matched head / insert of every 1024-point map tile
     int* tile_agg; int* cta_sum;                  // [2][tile_cap] points a tile emits; [2][kMergeMaxGrid] per CTA of the count pass
-    unsigned long long* fstatus;                  // [2][tile_cap] look-back words of the single-pass variant (epoch | flag | count)
 };
 
 struct MapMergeParams {

@@ -152,17 +152,6 @@ def test_merge_adversarial_small_inputs(capi, oracle, seed):
     _check(capi, oracle, m0s, np.concatenate([exc, extra]), center1, leaf, prm)
 
 
-def test_merge_single_pass_variant():
-    """PF_MM_VARIANT=1 (k_mm_single: one streaming pass with a decoupled look-back) must produce the same maps as the default
-    count pass + write pass.  The switch is read once per process, so the parity tests of this file run again in a child."""
-    env = dict(os.environ, PF_MM_VARIANT="1")
-    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-m", "gpu", "-p", "no:cacheprovider",
-                        "-k", "matches_full or chain_of or large_map or adversarial_small or unsorted_start or empty_inputs"],
-                       env=env, capture_output=True, text=True, timeout=900, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-1000:]
-    assert " passed" in r.stdout
-
-
 @pytest.mark.parametrize("seed", range(4))
 def test_voxel_downsample_adversarial(capi, oracle, seed):
     rng = np.random.default_rng(200 + seed)
