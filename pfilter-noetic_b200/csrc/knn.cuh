@@ -75,31 +75,58 @@ __device__ __forceinline__ bool knn5_warp(const KnnGrid& g, float qx, float qy, 
             }
         }
     }
-    // exclusive prefix of the row lengths over lanes 0..8
-    const int len = re - rs;
-    int incl = len;
-#pragma unroll
-    for (int o = 1; o < 16; o <<= 1) {
-        int y = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += y;
+    // Every point of a row with cell offsets (ry, rz) is at least my / mz away from the query in y / z, where my, mz are the
+    // distances to the cell faces -- exact in float (|q - floor(q)| < 1), and rounding is monotone, so
+    // lower = fl(fl(my my) + fl(mz mz)) bounds the float distance the search computes for any point of the row from below.
+    // Pass A scans the centre row (offsets 0, 0); `upper` = the fifth smallest of the lanes' best distances so far is an upper bound
+    // of the final fifth distance; pass B scans the other rows and skips those with lower > upper (strictly: a skipped point can
+    // neither enter the result nor tie with it).  On dense maps this drops most corner rows; the result is unchanged.
+    float lower = 0.f;
+    if (lane < 9) {
+        const int ry = (int)(lane % 3) - 1, rz = (int)(lane / 3) - 1;      // the row's cell offsets in y and z
+        const float my = ry == 0 ? 0.f : (ry < 0 ? __fsub_rn(qy, fy) : __fsub_rn(__fadd_rn(fy, 1.0f), qy));
+        const float mz = rz == 0 ? 0.f : (rz < 0 ? __fsub_rn(qz, fz) : __fsub_rn(__fadd_rn(fz, 1.0f), qz));
+        lower = __fadd_rn(__fmul_rn(my, my), __fmul_rn(mz, mz));
     }
-    const int total = __shfl_sync(0xffffffffu, incl, 8);
-    const int excl = incl - len;
     Top5 t;
     top5_init(t);
-    for (int i = lane; i < ((total + 31) & ~31); i += 32) {
-        // row r with excl[r] <= i < excl[r] + len[r]
-        int r = 0;
+    auto scan = [&](int len) {      // len: this lane's row length (lanes >= 9: 0); rows with len == 0 are skipped
+        int incl = len;
 #pragma unroll
-        for (int k = 1; k < 9; ++k) r += (i >= __shfl_sync(0xffffffffu, excl, k)) ? 1 : 0;
-        const int rbase = __shfl_sync(0xffffffffu, rs, r), rex = __shfl_sync(0xffffffffu, excl, r);
-        if (i < total) {
-            const float4 p = __ldg(g.pts + rbase + (i - rex));
-            const float ddx = __fsub_rn(qx, p.x), ddy = __fsub_rn(qy, p.y), ddz = __fsub_rn(qz, p.z);
-            const float d = __fadd_rn(__fadd_rn(__fmul_rn(ddx, ddx), __fmul_rn(ddy, ddy)), __fmul_rn(ddz, ddz));
-            top5_insert(t, ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)__float_as_int(p.w));
+        for (int o = 1; o < 16; o <<= 1) {
+            int y = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += y;
         }
+        const int total = __shfl_sync(0xffffffffu, incl, 8);
+        const int excl = incl - len;
+        for (int i = lane; i < ((total + 31) & ~31); i += 32) {
+            // row r with excl[r] <= i < excl[r] + len[r]
+            int r = 0;
+#pragma unroll
+            for (int k = 1; k < 9; ++k) r += (i >= __shfl_sync(0xffffffffu, excl, k)) ? 1 : 0;
+            const int rbase = __shfl_sync(0xffffffffu, rs, r), rex = __shfl_sync(0xffffffffu, excl, r);
+            if (i < total) {
+                const float4 p = __ldg(g.pts + rbase + (i - rex));
+                const float ddx = __fsub_rn(qx, p.x), ddy = __fsub_rn(qy, p.y), ddz = __fsub_rn(qz, p.z);
+                const float d = __fadd_rn(__fadd_rn(__fmul_rn(ddx, ddx), __fmul_rn(ddy, ddy)), __fmul_rn(ddz, ddz));
+                top5_insert(t, ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)__float_as_int(p.w));
+            }
+        }
+    };
+    const int len = (lane < 9) ? re - rs : 0;
+    scan(lane == 4 ? len : 0);                                  // pass A: the centre row
+    unsigned upper = 0x7f800000u;                               // +inf: fewer than five lanes hold a candidate, nothing is skipped
+    {
+        unsigned best = (unsigned)(t.k[0] >> 32);               // float bits of non-negative distances order like unsigned; empty = ~0
+        unsigned u = 0u;
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+            u = __reduce_min_sync(0xffffffffu, best);
+            if (best == u) best = 0xffffffffu;                  // ties drop several lanes at once: the bound only gets weaker
+        }
+        if (u < 0x7f800000u) upper = u;
     }
+    scan((lane != 4 && __float_as_uint(lower) <= upper) ? len : 0);      // pass B
     // merge the 32 sorted lists: five rounds of warp arg-min on (d2, index)
 #pragma unroll
     for (int k = 0; k < 5; ++k) {

@@ -73,3 +73,27 @@ def test_normal_eq_stream_linearity_at_full_size(capi):
     assert abs(c5 - k * c1) <= 1e-11 * c5
     H5b, g5b, c5b, _ = capi.eval_normal_eq_timed(sweep.SWEEP_POSE, e5, s5, reps=1)
     assert H5.tobytes() == H5b.tobytes() and g5.tobytes() == g5b.tobytes() and c5 == c5b
+
+
+@pytest.mark.parametrize("kind", ["dense", "lattice", "faces"])
+def test_knn5_row_pruning_is_exact(capi, oracle, kind):
+    """The search skips rows of cells whose lower distance bound exceeds the running fifth distance (knn.cuh).  Dense maps make it
+    skip most; lattice maps make every distance tie; queries ON cell faces make the bounds zero -- results must stay FLANN's."""
+    rng = np.random.default_rng({"dense": 1, "lattice": 2, "faces": 3}[kind])
+    n, nq = 300_000, 30_000
+    xyz = (rng.random((n, 3), dtype=np.float32) - 0.5) * np.array([40, 40, 10], np.float32)        # ~19 points per 1 m cell
+    if kind == "lattice":
+        xyz = np.round(xyz * 4) / 4                                                              # 0.25 m lattice: masses of exact ties
+    q = np.zeros((nq, 4), np.float32)
+    q[:, :3] = xyz[rng.integers(0, n, nq)] + rng.normal(0, 0.15, (nq, 3)).astype(np.float32)
+    if kind == "faces":
+        q[: nq // 2, rng.integers(0, 3)] = np.round(q[: nq // 2, 0])                             # integer coordinates: on a cell face
+        q[nq // 2:, :3] = np.round(q[nq // 2:, :3])
+    if kind == "lattice":
+        q[:, :3] = np.round(q[:, :3] * 8) / 8
+    pts = capi.make_points(xyz.astype(np.float32))
+    gi, gd = capi.knn5(pts, q)
+    ci, cd, _, _ = oracle.knn5_timed(pts, q)
+    assert np.array_equal(gi, ci)
+    assert gd.tobytes() == cd.tobytes()
+    assert (gi[:, 4] >= 0).mean() > 0.95
