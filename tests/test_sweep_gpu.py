@@ -87,7 +87,8 @@ def test_knn5_row_pruning_is_exact(capi, oracle, kind):
     q = np.zeros((nq, 4), np.float32)
     q[:, :3] = xyz[rng.integers(0, n, nq)] + rng.normal(0, 0.15, (nq, 3)).astype(np.float32)
     if kind == "faces":
-        q[: nq // 2, rng.integers(0, 3)] = np.round(q[: nq // 2, 0])                             # integer coordinates: on a cell face
+        c = int(rng.integers(0, 3))
+        q[: nq // 2, c] = np.round(q[: nq // 2, c])                                              # integer coordinate: on a cell face
         q[nq // 2:, :3] = np.round(q[nq // 2:, :3])
     if kind == "lattice":
         q[:, :3] = np.round(q[:, :3] * 8) / 8
