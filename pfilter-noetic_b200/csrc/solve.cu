@@ -42,7 +42,7 @@ __device__ __forceinline__ double residual_weight(int weight_type, double obs, d
 // wants exactly 1, 2 or 12 (src/lidarOptimization.cpp:25-28), the surf functor anything but 0 (:62-63).
 // kFma: accumulate J^T J and J^T r with fused multiply-adds (the library is built with -fmad=false so that every product rounds like
 // the CPU reference; the map-sweep kernel, whose sums are compared at 1e-10 and whose fp64 issue rate matters, may fuse the 27
-// accumulations -- PF_NE_FMA)
+// accumulations -- the default there, -DPF_NE_NOFMA builds it without)
 template <bool kFma = false>
 __device__ __forceinline__ void eval_one(int kind, D3 p, const double* ge, const double* Rm, const double* tv, double weight, double acc[kAcc]) {
     const D3 lp = d3(Rm[0] * p.x + Rm[1] * p.y + Rm[2] * p.z + tv[0], Rm[3] * p.x + Rm[4] * p.y + Rm[5] * p.z + tv[1],
@@ -416,7 +416,7 @@ int lm_solve(cudaStream_t stream, const LmParams& P, const double* pose_src, int
 // conflict-free for 8-byte accesses), accumulates the 29 sums in fp64 registers; shuffle tree + shared memory per CTA, one partial
 // per CTA in global memory, and the last CTA to finish (ticket) adds the partials in CTA order -- deterministic.
 #ifndef PF_NE_STAGES
-#define PF_NE_STAGES 4
+#define PF_NE_STAGES 5
 #endif
 #ifndef PF_NE_CTAS
 #define PF_NE_CTAS 2
@@ -490,10 +490,10 @@ __global__ void __launch_bounds__(kNeTile, kNeCtasPerSm) k_normal_eq_stream(NeSt
 #pragma unroll
             for (int k = 0; k < 9; ++k) v[k] = k < nd ? src[(size_t)tid * nd + k] : 0.0;
         }
-#ifdef PF_NE_FMA
-        if (tid < cnt) eval_one<true>(kind, d3(v[0], v[1], v[2]), v + 3, Rm, tv, 0.0, acc);
-#else
+#ifdef PF_NE_NOFMA
         if (tid < cnt) eval_one<false>(kind, d3(v[0], v[1], v[2]), v + 3, Rm, tv, 0.0, acc);
+#else       // fused accumulation of the 27 sums: 71 % of the measured HBM peak against 65 % without (profiles/k7_stream_variants_r2.txt)
+        if (tid < cnt) eval_one<true>(kind, d3(v[0], v[1], v[2]), v + 3, Rm, tv, 0.0, acc);
 #endif
         __syncthreads();
     }
