@@ -194,18 +194,24 @@ int build_grids(Workspace& ws, const GridBuild& G_in, int slot, int cap0, int ca
     return PF_OK;
 }
 
-__global__ void __launch_bounds__(256) k_knn5_tap(KnnGrid g, const float4* __restrict__ q, int nq, int* __restrict__ idx_out,
+// Two queries per warp (a half warp each): a query is a chain of dependent memory round trips (cell table, centre row, other rows),
+// so the number of queries in flight sets the throughput; the ~10-70 candidates of a query keep 16 lanes busy.
+#ifndef PF_KNN_TAP_GROUP
+#define PF_KNN_TAP_GROUP 16
+#endif
+constexpr int kTapGroup = PF_KNN_TAP_GROUP;
+__global__ void __launch_bounds__(256, 8) k_knn5_tap(KnnGrid g, const float4* __restrict__ q, int nq, int* __restrict__ idx_out,
                                                   float* __restrict__ d2_out) {
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (warp >= nq) return;
-    const float4 p = q[warp];
+    const int qi = (blockIdx.x * blockDim.x + threadIdx.x) / kTapGroup;
+    if (qi >= nq) return;          // uniform within a group
+    const float4 p = q[qi];
     int idx[5];
     float d2[5];
-    const bool ok = knn5_warp(g, p.x, p.y, p.z, idx, d2);
-    const unsigned lane = lane_id();
+    const bool ok = knn5_group<kTapGroup>(g, p.x, p.y, p.z, idx, d2);
+    const unsigned lane = lane_id() & (kTapGroup - 1);
     if (lane < 5) {
-        idx_out[5 * warp + lane] = ok ? idx[lane] : -1;
-        d2_out[5 * warp + lane] = ok ? d2[lane] : __int_as_float(0x7f800000);
+        idx_out[5 * qi + lane] = ok ? idx[lane] : -1;
+        d2_out[5 * qi + lane] = ok ? d2[lane] : __int_as_float(0x7f800000);
     }
 }
 
@@ -267,7 +273,7 @@ static int knn5_tap(int device, const pf_point* map, int m, const float* queries
         PF_CHECK(workspace_begin_step(t.ws));
         PF_CHECK(build_grids(t.ws, G, 0, mc, 0));
         PF_CUDA(cudaEventRecord(ev[1], t.stream));
-        if (q) k_knn5_tap<<<div_up(q, 8), 256, 0, t.stream>>>(g, t.d_q, q, t.d_idx, t.d_d2);
+        if (q) k_knn5_tap<<<div_up(q, 256 / kTapGroup), 256, 0, t.stream>>>(g, t.d_q, q, t.d_idx, t.d_d2);
         PF_CUDA(cudaEventRecord(ev[2], t.stream));
         PF_CUDA(cudaStreamSynchronize(t.stream));
         float a = 0.f, b = 0.f;

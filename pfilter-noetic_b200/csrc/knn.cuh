@@ -51,10 +51,15 @@ __device__ __forceinline__ void top5_insert(Top5& t, unsigned long long key) {
     }
 }
 
-// Whole warp cooperates on one query; every lane returns the same 5 results (ascending).  Returns true when the
-// result is usable under the reference's contract (5 neighbours found and d2[4] < 1).
-__device__ __forceinline__ bool knn5_warp(const KnnGrid& g, float qx, float qy, float qz, int idx[5], float d2[5]) {
-    const unsigned lane = lane_id();
+// A group of W lanes (a whole warp, or a half warp so that a warp works on two queries at once: the search is a chain of three or
+// four dependent memory round trips, so queries in flight are what sets the throughput) cooperates on one query; every lane of
+// the group returns the same 5 results (ascending).  Returns true when the result is usable under the reference's contract
+// (5 neighbours found and d2[4] < 1).  All W lanes of the group must call it together.
+template <int W>
+__device__ __forceinline__ bool knn5_group(const KnnGrid& g, float qx, float qy, float qz, int idx[5], float d2[5]) {
+    static_assert(W == 32 || W == 16, "group of 16 or 32 lanes");
+    const unsigned lane = lane_id() & (unsigned)(W - 1);                               // lane within the group
+    const unsigned gm = W == 32 ? 0xffffffffu : (0xffffu << (lane_id() & 16u));       // the group's lanes
     const int ox = g.geom[0], oy = g.geom[1], oz = g.geom[2], dx = g.geom[3], dy = g.geom[4], dz = g.geom[5];
     // floor() of the float coordinate is the exact cell; clamp far-away queries so the int conversion cannot overflow
     const float fx = fminf(fmaxf(floorf(qx), -1.0e9f), 1.0e9f), fy = fminf(fmaxf(floorf(qy), -1.0e9f), 1.0e9f),
@@ -94,17 +99,17 @@ __device__ __forceinline__ bool knn5_warp(const KnnGrid& g, float qx, float qy, 
         int incl = len;
 #pragma unroll
         for (int o = 1; o < 16; o <<= 1) {
-            int y = __shfl_up_sync(0xffffffffu, incl, o);
+            int y = __shfl_up_sync(gm, incl, o, W);
             if (lane >= o) incl += y;
         }
-        const int total = __shfl_sync(0xffffffffu, incl, 8);
+        const int total = __shfl_sync(gm, incl, 8, W);
         const int excl = incl - len;
-        for (int i = lane; i < ((total + 31) & ~31); i += 32) {
+        for (int i = (int)lane; i < ((total + W - 1) & ~(W - 1)); i += W) {
             // row r with excl[r] <= i < excl[r] + len[r]
             int r = 0;
 #pragma unroll
-            for (int k = 1; k < 9; ++k) r += (i >= __shfl_sync(0xffffffffu, excl, k)) ? 1 : 0;
-            const int rbase = __shfl_sync(0xffffffffu, rs, r), rex = __shfl_sync(0xffffffffu, excl, r);
+            for (int k = 1; k < 9; ++k) r += (i >= __shfl_sync(gm, excl, k, W)) ? 1 : 0;
+            const int rbase = __shfl_sync(gm, rs, r, W), rex = __shfl_sync(gm, excl, r, W);
             if (i < total) {
                 const float4 p = __ldg(g.pts + rbase + (i - rex));
                 const float ddx = __fsub_rn(qx, p.x), ddy = __fsub_rn(qy, p.y), ddz = __fsub_rn(qz, p.z);
@@ -121,7 +126,7 @@ __device__ __forceinline__ bool knn5_warp(const KnnGrid& g, float qx, float qy, 
         unsigned u = 0u;
 #pragma unroll
         for (int k = 0; k < 5; ++k) {
-            u = __reduce_min_sync(0xffffffffu, best);
+            u = __reduce_min_sync(gm, best);
             if (best == u) best = 0xffffffffu;                  // ties drop several lanes at once: the bound only gets weaker
         }
         if (u < 0x7f800000u) upper = u;
@@ -131,8 +136,8 @@ __device__ __forceinline__ bool knn5_warp(const KnnGrid& g, float qx, float qy, 
 #pragma unroll
     for (int k = 0; k < 5; ++k) {
         const unsigned hi = (unsigned)(t.k[0] >> 32), lo = (unsigned)t.k[0];
-        const unsigned hmin = __reduce_min_sync(0xffffffffu, hi);
-        const unsigned lmin = __reduce_min_sync(0xffffffffu, hi == hmin ? lo : 0xffffffffu);
+        const unsigned hmin = __reduce_min_sync(gm, hi);
+        const unsigned lmin = __reduce_min_sync(gm, hi == hmin ? lo : 0xffffffffu);
         if (hi == hmin && lo == lmin && t.k[0] != ~0ull) {   // unique winner pops its head
             t.k[0] = t.k[1]; t.k[1] = t.k[2]; t.k[2] = t.k[3]; t.k[3] = t.k[4]; t.k[4] = ~0ull;
         }
@@ -141,6 +146,10 @@ __device__ __forceinline__ bool knn5_warp(const KnnGrid& g, float qx, float qy, 
     }
     const bool ok = (idx[4] != -1) && (d2[4] < 1.0f);
     return ok;
+}
+// the whole warp on one query
+__device__ __forceinline__ bool knn5_warp(const KnnGrid& g, float qx, float qy, float qz, int idx[5], float d2[5]) {
+    return knn5_group<32>(g, qx, qy, qz, idx, d2);
 }
 #endif
 
