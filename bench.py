@@ -25,6 +25,9 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# more hardware work queues than the default 8: the multi-sequence leg runs 8 sequences x 4 streams side by side, and streams that
+# share a queue serialise (measured: 6.5 k -> 7.5 k scans/s with 8 sequences on one GPU).  Must be set before the CUDA context exists.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 METRIC = "scans/sec at 64-ring ~120k-pt shape (extract+match+filter)"
 UNIT = "scans/s"
@@ -276,7 +279,8 @@ def extra_kernel_legs(capi, dev_index):
     raw = capi.make_points(xyz, r=0, g=200, b=0, a=255)
     m0 = capi.map_update(raw, (0, 0, 0), 0.4, 0, 0.4, 75, device=dev_index)        # sorted, one point per voxel
     del raw
-    add = capi.make_points((rng.random((20000, 3), dtype=np.float32) - 0.5) * np.array([120, 120, 12], np.float32), r=0, g=1)
+    # one frame's worth of new points: the frame loop appends n_edge_ds + n_surf_ds ~ 7 k down-sampled features per update
+    add = capi.make_points((rng.random((7000, 3), dtype=np.float32) - 0.5) * np.array([120, 120, 12], np.float32), r=0, g=1)
     t = capi.map_merge_timed(m0, add, (0.3, 0.1, 0.0), 0.4, 0, 0.4, 75, reps=6, device=dev_index)
     bytes_k9 = 16.0 * (len(m0) + len(add)) + 16.0 * t["n_out"]
     k9 = {"bound": "hbm", "kernel": "k_mm_count + k_mm_write (K9 streaming map update: CropBox + voxel merge + PFilter delete + r update)",

@@ -36,25 +36,32 @@ __global__ void __launch_bounds__(256) k_assoc_match(AssocParams P) {
     for (int q0 = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * kAssocBatch; q0 < nq; q0 += nwarps * kAssocBatch) {
         int my_idx[5] = {-1, -1, -1, -1, -1};
         bool my_found = false;
+        // Batch entry b is searched by half warp (b & 1) in round (b >> 1) -- two searches side by side: a search is a chain of dependent
+        // memory round trips, not a throughput problem -- and fitted by lane fit_lane(b) = 16 (b & 1) + (b >> 1) of that half warp.
+        const int half = (int)(lane >> 4), hl = (int)(lane & 15u);
+        const int my_b = 2 * hl + half;                      // the batch entry this lane fits (if < kAssocBatch)
         if (guard) {
 #pragma unroll 1
-            for (int g = 0; g < kAssocBatch; ++g) {
-                const int q = q0 + g;
-                if (q >= nq) break;
-                const Pt qp = c.queries[q];
-                const D3 pw = pose_apply(P.pose, d3((double)qp.x, (double)qp.y, (double)qp.z));
-                int idx[5];
-                float d2[5];
-                const bool found = knn5_warp(c.grid, (float)pw.x, (float)pw.y, (float)pw.z, idx, d2);   // :299-300 / :447-451
-                if ((int)lane == g) {
-                    my_found = found;
+            for (int rnd = 0; rnd < (kAssocBatch + 1) / 2; ++rnd) {
+                const int b = 2 * rnd + half;
+                const int q = q0 + b;
+                if (b < kAssocBatch && q < nq) {             // uniform within the half warp
+                    const Pt qp = c.queries[q];
+                    const D3 pw = pose_apply(P.pose, d3((double)qp.x, (double)qp.y, (double)qp.z));
+                    int idx[5];
+                    float d2[5];
+                    const bool found = knn5_group<16>(c.grid, (float)pw.x, (float)pw.y, (float)pw.z, idx, d2);   // :299-300 / :447-451
+                    if (hl == rnd) {
+                        my_found = found;
 #pragma unroll
-                    for (int j = 0; j < 5; ++j) my_idx[j] = idx[j];
+                        for (int j = 0; j < 5; ++j) my_idx[j] = idx[j];
+                    }
                 }
             }
         }
-        const int q = q0 + (int)lane;
-        if ((int)lane < kAssocBatch && q < nq) {
+        __syncwarp();
+        const int q = q0 + my_b;
+        if (my_b < kAssocBatch && q < nq) {
             unsigned flag = 0;
             if (my_found) {
                 D3 nb[5];
@@ -123,19 +130,35 @@ __global__ void __launch_bounds__(128) k_assoc_persist(AssocParams P) {
     const int nq = *c.n_q;
     for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += gridDim.x * blockDim.x) {
     if (c.flag[q] != 1) continue;
-    int m[5], g0[5], len[5];
+    int m[5], g0[5], len[5], rank[5], h[5];
     int sg = 0, sr = 0;
 #pragma unroll
+    for (int j = 0; j < 5; ++j) m[j] = c.nn_idx[5 * q + j];
+#pragma unroll
     for (int j = 0; j < 5; ++j) {
-        m[j] = c.nn_idx[5 * q + j];
         const unsigned rgba = c.map[m[j]].rgba;
         g0[j] = (int)pt_g(rgba);
-        int rank = 0, n = 0;
-        for (int h = c.head[m[j]]; h >= 0; h = c.next[h]) { rank += (h / 5 < q) ? 1 : 0; ++n; }
-        len[j] = n;
-        sg += min(255, g0[j] + rank);          // the counter value the serial loop would have read (:332-336)
         sr += (int)pt_r(rgba);
+        h[j] = c.head[m[j]];
+        rank[j] = 0; len[j] = 0;
     }
+    // the five hit lists are walked side by side: one hop of each per round, so the pointer chases overlap (a list is as long as the
+    // number of valid queries that hit the map point in this pass; walking them one after the other was most of the kernel's time)
+    while (true) {
+        bool any = false;
+#pragma unroll
+        for (int j = 0; j < 5; ++j) {
+            if (h[j] >= 0) {
+                rank[j] += (h[j] / 5 < q) ? 1 : 0;
+                len[j] += 1;
+                h[j] = c.next[h[j]];
+                any = true;
+            }
+        }
+        if (!any) break;
+    }
+#pragma unroll
+    for (int j = 0; j < 5; ++j) sg += min(255, g0[j] + rank[j]);          // the counter value the serial loop would have read (:332-336)
     float observe = (float)((double)sg / 5.0 + 1);                           // :332-338
     const float round = (float)((double)sr / 5.0);                           // :339-344
     if (__fdiv_rn(observe, round) > 5) observe = 255;                        // :348-349 (round == 0 -> inf)
