@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define PF_VERSION 100
+#define PF_VERSION 101
 
 typedef enum pf_status {
     PF_OK = 0,
@@ -84,6 +84,9 @@ typedef struct pf_extract_config {
     int32_t max_ring_points;   /* capacity of one ring; sizes the per-warp shared memory (a sector of the ring) and so the
                                   occupancy of the extract kernel: set it to the sensor's points per ring plus a margin;
                                   0 = default 2304, maximum 3040 */
+    int32_t surf_order;        /* order of the surf points inside a sector: 0 = ascending ring position (default, fastest), 1 = the
+                                  reference's: ascending curvature, the order of its sorted walk (src/laserProcessingClass.cpp:101-104,
+                                  :198-205; equal curvatures: lower ring position first).  The SETS are identical either way. */
 } pf_extract_config;
 
 /* LaserProcessingClass::init, src/laserProcessingClass.cpp:4-8 */
@@ -92,8 +95,8 @@ int pf_extract_destroy(pf_extract* h);
 
 /* LaserProcessingClass::featureExtraction, src/laserProcessingClass.cpp:10-96 (+ :99-209).
  * xyzi: n host points (float4).  edge/surf receive the selected points (16 B each, same float4 layout) in
- * emission order ring -> sector -> {edges by descending curvature; surf by ascending ring position}; the
- * SETS equal the reference's, the reference emits surf by ascending curvature inside a sector.
+ * emission order ring -> sector -> {edges by descending curvature; surf by ascending ring position, or -- with
+ * pf_extract_config.surf_order = 1 -- by ascending curvature as the reference emits them}; the SETS equal the reference's.
  * label (optional, n bytes): 0 = neither, 1 = edge, 2 = surf, per input index.
  * Capacities: edge needs 120 * num_lines points, surf needs n points. */
 int pf_extract_run(pf_extract* h, const float* xyzi, int n, float* edge, int* n_edge, float* surf, int* n_surf,

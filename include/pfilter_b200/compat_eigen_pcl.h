@@ -67,7 +67,7 @@ class LaserProcessingClass {
         lidar_param = lidar_param_in;
         if (h_) { pf_extract_destroy(h_); h_ = nullptr; }
         pf_lidar_params lp = lidar_param.c_params();
-        pf_extract_config cfg{262144, 1, 0};
+        pf_extract_config cfg{262144, 1, 0, 1};     // surf_order 1: the reference's emission order (ascending curvature in a sector)
         status_ = pf_extract_create(&lp, &cfg, 0, &h_);
         if (status_ != PF_OK) std::fprintf(stderr, "LaserProcessingClass::init: %s\n", pf_last_error());
     }

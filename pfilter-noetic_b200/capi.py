@@ -26,7 +26,7 @@ class LidarParams(C.Structure):
 
 
 class ExtractConfig(C.Structure):
-    _fields_ = [("max_points", C.c_int32), ("max_batch", C.c_int32), ("max_ring_points", C.c_int32)]
+    _fields_ = [("max_points", C.c_int32), ("max_batch", C.c_int32), ("max_ring_points", C.c_int32), ("surf_order", C.c_int32)]
 
 
 class OdomParams(C.Structure):
@@ -140,9 +140,9 @@ class Extractor:
     """Handle of pf_extract_* (replaces LaserProcessingClass)."""
 
     def __init__(self, num_lines=64, min_distance=3.0, max_distance=90.0, max_points=131072, max_batch=1,
-                 max_ring_points=0, device=0):
+                 max_ring_points=0, device=0, surf_order=0):
         self.lidar = LidarParams(num_lines, min_distance, max_distance, 0.1)
-        self.cfg = ExtractConfig(max_points, max_batch, max_ring_points)
+        self.cfg = ExtractConfig(max_points, max_batch, max_ring_points, surf_order)
         self.h = C.c_void_p()
         check(lib().pf_extract_create(C.byref(self.lidar), C.byref(self.cfg), device, C.byref(self.h)))
         self.num_lines = num_lines

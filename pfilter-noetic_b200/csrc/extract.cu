@@ -61,6 +61,7 @@ struct ExtractParams {
     unsigned int* ctrl;       // [0] ticket, [1] epoch, [2] error bits
     int stride, tiles, edge_stride, batch;
     int num_lines, rcap, scap, warp_smem;
+    int sval_off;             // byte offset of the exact-curvature array inside a warp's shared memory (reference surf order only)
     double min_d, max_d;
 };
 
@@ -526,8 +527,13 @@ __device__ __noinline__ int sector_pick_large(const float4* sp, unsigned* scand,
 // compacted by ballot; greedy pick (sector_pick); surf = unflagged (:198-205).  Output offsets: every sector publishes
 // (epoch | edges | surfs), the last sector of a ring to finish publishes the ring's sum, and a sector's offset is the sum of
 // the earlier rings' words plus the earlier sectors of its own ring: the compacted clouds are written once, from shared memory.
-template <bool kLabel>
-__global__ void __launch_bounds__(kSecWarps * 32, 14) k_sector_extract(ExtractParams P) {
+// kRefOrder: surf points leave in the reference's order -- ascending exact curvature inside the sector, the order its sorted walk at
+// :198-205 produces (equal values: lower ring position first; std::sort leaves that case open) -- instead of ring position.  The
+// exact doubles of all positions are kept in shared memory and every surf point counts the surf points in front of it: O(n^2 / 32)
+// per lane, about five times the cost of the default order, for callers that want pcl::VoxelGrid downstream to see the very point
+// order the reference's extraction would have handed it.
+template <bool kLabel, bool kRefOrder>
+__global__ void __launch_bounds__(kSecWarps * 32, kRefOrder ? 8 : 14) k_sector_extract(ExtractParams P) {
     PF_PDL_ENTRY();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
@@ -539,6 +545,7 @@ __global__ void __launch_bounds__(kSecWarps * 32, 14) k_sector_extract(ExtractPa
     unsigned* slink = scand + S;                                         // [S / 32 + 2] link bits: bit q = short step q -> q+1
     unsigned* sflagw = slink + S / 32 + 2;                               // [18] flag bits of the sector (picked / suppressed)
     int* ssrc = reinterpret_cast<int*>(sflagw + 18);                     // [S] source index (label output only)
+    double* sval = reinterpret_cast<double*>(wsm + P.sval_off);          // [S] exact curvature per sector position (kRefOrder only)
 
     const unsigned epoch = *reinterpret_cast<volatile unsigned int*>(&P.ctrl[1]);
     const int nsec = P.batch * P.num_lines * kSectors;       // < 2^23 (host): the float division below is exact
@@ -668,6 +675,7 @@ __global__ void __launch_bounds__(kSecWarps * 32, 14) k_sector_extract(ExtractPa
                         const double dx = (double)sxy.x, dy = (double)sxy.y, dz = (double)szw.x;
                         const double val = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
                         const int rel = qh + j - 5;
+                        if (kRefOrder && act && rel < Ls) sval[rel] = val;
                         const bool isc = act && rel < Ls && val > 0.1;
                         const unsigned cm = __ballot_sync(kFull, isc);
                         if (isc) {
@@ -771,6 +779,23 @@ __global__ void __launch_bounds__(kSecWarps * 32, 14) k_sector_extract(ExtractPa
                 if (kLabel) label[ssrc[myedge + 5]] = 1;
             }
             float4* surf = P.surf + (size_t)s * P.stride + su;
+            if (kRefOrder) {
+                __syncwarp();
+                if (lane < 16) sflagw[lane] = flagw;
+                __syncwarp();
+                for (int rel = lane; rel < Ls; rel += 32) {
+                    if ((sflagw[rel >> 5] >> (rel & 31)) & 1u) continue;         // picked or suppressed: not a surf point
+                    const double v = sval[rel];
+                    int rank = 0;
+                    for (int j = 0; j < Ls; ++j) {                               // same j in every lane: broadcast reads
+                        const double u = sval[j];
+                        const bool surf_j = ((sflagw[j >> 5] >> (j & 31)) & 1u) == 0u;
+                        rank += (surf_j && (u < v || (u == v && j < rel))) ? 1 : 0;
+                    }
+                    st_stream_f4(surf + rank, sp[rel + 5]);
+                    if (kLabel) label[ssrc[rel + 5]] = 2;
+                }
+            } else
             for (int row = 0; row * 32 < Ls; ++row) {
                 const unsigned kw = __shfl_sync(kFull, keep, row);
                 const int bw = __shfl_sync(kFull, sbase, row);
@@ -796,6 +821,8 @@ struct pf_extract {
     int stride = 0, tiles = 0, max_batch = 0, rcap = 0, scap = 0, edge_stride = 0;
     int warp_smem = 0, warp_smem_label = 0;   // bytes of shared memory per warp of k_sector_extract (without / with label output)
     int ctas = 0, ctas_label = 0;             // resident CTAs of the persistent kernel on the whole device
+    int ref_order = 0;                        // surf emission order: 0 ring position, 1 the reference's (ascending curvature)
+    int sval_off = 0;
     int group = 1;
     // device
     float4* d_pts = nullptr;
@@ -931,13 +958,19 @@ static int extract_launch(pf_extract* h, const float4* d_xyzi, const int* d_n, i
         }
         launch_pdl(k_ring_index, dim3(div_up(nb * h->lidar.num_lines, 8)), dim3(256), 0, h->stream, P);
         const int want = div_up(nb * h->lidar.num_lines * kSectors, kSecWarps);
-        if (d_label) {
-            P.warp_smem = h->warp_smem_label;
-            launch_pdl(k_sector_extract<true>, dim3(want < h->ctas_label ? want : h->ctas_label), dim3(kSecWarps * 32), (size_t)kSecWarps * h->warp_smem_label,
-                       h->stream, P);
-        } else {
-            P.warp_smem = h->warp_smem;
-            launch_pdl(k_sector_extract<false>, dim3(want < h->ctas ? want : h->ctas), dim3(kSecWarps * 32), (size_t)kSecWarps * h->warp_smem, h->stream, P);
+        P.sval_off = h->sval_off;
+        {
+            const int wsm = d_label ? h->warp_smem_label : h->warp_smem, ctas = d_label ? h->ctas_label : h->ctas;
+            P.warp_smem = wsm;
+            const dim3 grid(want < ctas ? want : ctas), block(kSecWarps * 32);
+            const size_t smem = (size_t)kSecWarps * wsm;
+            if (h->ref_order) {
+                if (d_label) launch_pdl(k_sector_extract<true, true>, grid, block, smem, h->stream, P);
+                else launch_pdl(k_sector_extract<false, true>, grid, block, smem, h->stream, P);
+            } else {
+                if (d_label) launch_pdl(k_sector_extract<true, false>, grid, block, smem, h->stream, P);
+                else launch_pdl(k_sector_extract<false, false>, grid, block, smem, h->stream, P);
+            }
         }
         h->launches += 3;
     }
@@ -967,6 +1000,7 @@ extern "C" int pf_extract_create(const pf_lidar_params* lidar, const pf_extract_
                "num_lines must be 16, 32 or 64 (src/laserProcessingClass.cpp:30-61), got %d", lidar->num_lines);
     PF_REQUIRE(cfg->max_points > 0 && cfg->max_batch > 0, "max_points and max_batch must be positive");
     PF_REQUIRE(cfg->max_batch <= 16384, "max_batch %d > 16384", cfg->max_batch);   // sectors per launch stay below 2^23
+    PF_REQUIRE(cfg->surf_order == 0 || cfg->surf_order == 1, "surf_order %d: 0 (ring position) or 1 (the reference's: ascending curvature)", cfg->surf_order);
     int ndev = 0;
     PF_CUDA(cudaGetDeviceCount(&ndev));
     PF_REQUIRE(device >= 0 && device < ndev, "device %d not available (%d devices)", device, ndev);
@@ -993,25 +1027,38 @@ extern "C" int pf_extract_create(const pf_lidar_params* lidar, const pf_extract_
     // the register windows), candidate words, link bits, suppressed ranges (+ source indices for the label output)
     h->scap = div_up((h->rcap - 10) / kSectors + 14, 32) * 32;
     if (h->scap < 256) h->scap = 256;     // sector_pick hands up to 256 live words back through the candidate array
+    h->ref_order = cfg->surf_order;
     h->warp_smem = (h->scap + 24) * 16 + h->scap * 4 + (h->scap / 32 + 2 + 18) * 4;
     h->warp_smem = div_up(h->warp_smem, 16) * 16;
     h->warp_smem_label = h->warp_smem + h->scap * 4;
+    if (h->ref_order) {                        // + the exact curvature of every sector position (behind the label array's place)
+        h->sval_off = h->warp_smem_label;
+        h->warp_smem = h->warp_smem_label = h->sval_off + h->scap * 8;
+    }
     if ((size_t)kSecWarps * h->warp_smem_label > (size_t)prop.sharedMemPerBlockOptin) {
         set_error("max_ring_points %d needs %d B shared memory (> %zu)", h->rcap, kSecWarps * h->warp_smem_label,
                   (size_t)prop.sharedMemPerBlockOptin);
         delete h;
         return PF_ERR_INVALID;
     }
-    PF_CUDA(cudaFuncSetAttribute(k_sector_extract<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSecWarps * h->warp_smem));
-    PF_CUDA(cudaFuncSetAttribute(k_sector_extract<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSecWarps * h->warp_smem_label));
     {
-        int occ = 0, occ_label = 0;
-        PF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sector_extract<false>, kSecWarps * 32, (size_t)kSecWarps * h->warp_smem));
-        PF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_label, k_sector_extract<true>, kSecWarps * 32,
-                                                              (size_t)kSecWarps * h->warp_smem_label));
-        PF_REQUIRE(occ >= 1 && occ_label >= 1, "k_sector_extract does not fit on an SM");
-        h->ctas = occ * prop.multiProcessorCount;
-        h->ctas_label = occ_label * prop.multiProcessorCount;
+        auto setup = [&](auto kern, int wsm, int* ctas) -> int {
+            PF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSecWarps * wsm));
+            int occ = 0;
+            PF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kSecWarps * 32, (size_t)kSecWarps * wsm));
+            PF_REQUIRE(occ >= 1, "k_sector_extract does not fit on an SM");
+            *ctas = occ * prop.multiProcessorCount;
+            return PF_OK;
+        };
+        int rc;
+        if (h->ref_order) {
+            rc = setup(k_sector_extract<false, true>, h->warp_smem, &h->ctas);
+            if (rc == PF_OK) rc = setup(k_sector_extract<true, true>, h->warp_smem_label, &h->ctas_label);
+        } else {
+            rc = setup(k_sector_extract<false, false>, h->warp_smem, &h->ctas);
+            if (rc == PF_OK) rc = setup(k_sector_extract<true, false>, h->warp_smem_label, &h->ctas_label);
+        }
+        if (rc != PF_OK) { delete h; return rc; }
     }
     // fp32 range gate strictly inside [min_distance, max_distance]: everything else takes the exact double comparison
     h->gate_lo = (float)lidar->min_distance;

@@ -22,7 +22,7 @@ def test_library_exports_every_declared_symbol(pfb):
     lib = C.CDLL(pfb.capi.LIB_PATH)
     missing = [n for n in names if not hasattr(lib, n)]
     assert not missing, missing
-    assert lib.pf_version() == 100
+    assert lib.pf_version() == 101
 
 
 def test_synth_library_exports(pfb):

@@ -132,3 +132,40 @@ def test_extract_random_elevations_and_nonfinite(capi, oracle):
         ref = oracle.extract(s, num_lines=lines, order=1)
         assert (ref["label"] > 0).sum() > n // 10
         _check(s, ex.run(s), ref)
+
+
+def test_extract_reference_surf_order(capi, oracle, pfb, cfg2_scans):
+    """pf_extract_config.surf_order = 1: surf points leave in the reference's order (ascending curvature inside a sector,
+    src/laserProcessingClass.cpp:101-104, :198-205) -- the same SEQUENCE as the reference's own compiled source, not only the same set."""
+    _, scans = cfg2_scans
+    ex = capi.Extractor(num_lines=64, max_points=131072, surf_order=1)
+    ex0 = capi.Extractor(num_lines=64, max_points=131072)
+    for s in scans[:3]:
+        edge, surf, label = ex.run(s)
+        ref = oracle.extract(s, order=0)
+        assert np.array_equal(label, ref["label"])
+        assert np.array_equal(edge, s[ref["edge_idx"]])
+        assert np.array_equal(surf, s[ref["surf_idx"]])
+        if oracle.have_ref():                    # the real reference (std::sort: the noise of the generator leaves no exact ties)
+            e, f = oracle.ref_extract(s)
+            assert np.array_equal(edge, s[e]) and np.array_equal(surf, s[f])
+        e0, s0, l0 = ex0.run(s)                  # the default order: same sets, different sequence
+        assert np.array_equal(l0, label) and np.array_equal(e0, edge) and not np.array_equal(s0, surf)
+        assert np.array_equal(np.sort(s0.view(np.uint32), axis=0), np.sort(surf.view(np.uint32), axis=0))
+    # 32 lines, ragged batch, label output and the fused frame path use the same kernel
+    p = pfb.synth.params(sensor_lines=32, seed=77)
+    s = pfb.synth.scan(p, 3)
+    ex32 = capi.Extractor(num_lines=32, max_points=65536, max_batch=4, surf_order=1)
+    ref = oracle.extract(s, num_lines=32, order=0)
+    for out in ex32.run_batch([s, s[:30000], s[:100]]):
+        pass
+    o = ex32.run_batch([s, s[:30000]])
+    assert np.array_equal(o[0][1], s[ref["surf_idx"]]) and np.array_equal(o[0][2], ref["label"])
+    r2 = oracle.extract(s[:30000], num_lines=32, order=0)
+    assert np.array_equal(o[1][1], s[:30000][r2["surf_idx"]])
+    # exact ties (quantised coordinates): lower ring position first, as the oracle's order 0 has it
+    q = scans[2].copy()
+    q[:, :3] = np.round(q[:, :3] * 32.0) / 32.0
+    edge, surf, label = ex.run(q)
+    rq = oracle.extract(q, order=0)
+    assert np.array_equal(label, rq["label"]) and np.array_equal(surf, q[rq["surf_idx"]])

@@ -36,7 +36,7 @@ def test_typed_adapter_sequence_matches_the_c_abi(pfb, capi):
     rows = [l.split() for l in r.stdout.splitlines() if l.startswith("frame")]
     assert len(rows) == n
     p = pfb.synth.config("cfg2")
-    ex = capi.Extractor(num_lines=64, max_points=262144)
+    ex = capi.Extractor(num_lines=64, max_points=262144, surf_order=1)     # the adapter emits surf in the reference's order
     od = capi.Odometry(0.4, 0, 0.4, 75)
     for f in range(n):
         s = pfb.synth.scan(p, f)
