@@ -596,10 +596,15 @@ __global__ void __launch_bounds__(kSecWarps * 32, kRefOrder ? 8 : 14) k_sector_e
                             if (kLabel) ssrc[pos - p0] = tbase + (pos - beg);
                         }
                     } else {
+                        // the ring ids of the lane's eight rows first: one load latency per tile instead of eight in a row
+                        unsigned long long rb = 0ull;
+#pragma unroll
+                        for (int row = 0; row < kTile / 32; ++row)
+                            rb |= (unsigned long long)rid[tbase + row * 32 + lane] << (8 * row);
                         int run = beg;
                         for (int row = 0; row < kTile / 32 && run < p1; ++row) {
                             const int i = tbase + row * 32 + lane;
-                            const bool mt = rid[i] == r;
+                            const bool mt = (int)((rb >> (8 * row)) & 0xffull) == r;
                             const unsigned mm = __ballot_sync(kFull, mt);
                             const int pos = run + __popc(mm & lt);
                             if (mt && pos >= p0 && pos < p1) {
@@ -730,13 +735,15 @@ __global__ void __launch_bounds__(kSecWarps * 32, kRefOrder ? 8 : 14) k_sector_e
         {
             unsigned long long v = 0ull;
             bool ok = lane >= k;
+            unsigned nap = 100u;        // polls were 12 % of the kernel's instructions at a fixed 200 ns: back off
             while (true) {
                 if (!ok) {
                     v = ld_relaxed_u64(dsec + lane);
                     ok = (unsigned)(v >> 32) == epoch;
                 }
                 if (__all_sync(kFull, ok)) break;
-                __nanosleep(200);
+                __nanosleep(nap);
+                if (nap < 1600u) nap <<= 1;
             }
             if (lane < k) {
                 e_in = (int)((v >> 20) & 0xfffu);
@@ -752,6 +759,7 @@ __global__ void __launch_bounds__(kSecWarps * 32, kRefOrder ? 8 : 14) k_sector_e
         {
             unsigned long long v0 = 0ull, v1 = 0ull;      // r <= 63: at most two ring words per lane
             bool ok0 = lane >= r, ok1 = lane + 32 >= r;
+            unsigned nap = 100u;
             while (true) {
                 if (!ok0) {
                     v0 = ld_relaxed_u64(dring + lane);
@@ -762,7 +770,8 @@ __global__ void __launch_bounds__(kSecWarps * 32, kRefOrder ? 8 : 14) k_sector_e
                     ok1 = (unsigned)(v1 >> 32) == epoch;
                 }
                 if (__all_sync(kFull, ok0 && ok1)) break;
-                __nanosleep(200);
+                __nanosleep(nap);
+                if (nap < 1600u) nap <<= 1;
             }
             if (lane < r) { e += (int)((v0 >> 20) & 0xfffu); su += (int)(v0 & 0xfffffu); }
             if (lane + 32 < r) { e += (int)((v1 >> 20) & 0xfffu); su += (int)(v1 & 0xfffffu); }

@@ -169,3 +169,58 @@ def test_extract_reference_surf_order(capi, oracle, pfb, cfg2_scans):
     edge, surf, label = ex.run(q)
     rq = oracle.extract(q, order=0)
     assert np.array_equal(label, rq["label"]) and np.array_equal(surf, q[rq["surf_idx"]])
+
+
+def _check_points(scan, out, ref):
+    edge, surf, _ = out
+    assert np.array_equal(edge, scan[ref["edge_idx"]])
+    assert np.array_equal(surf, scan[ref["surf_idx"]])
+
+
+def test_extract_large_mixed_batches(capi, oracle, pfb, cfg2_scans):
+    """Batches of 24 - 32 scans without label output: ragged / empty / truncated scans, interleaved point order, lattice ties,
+    scans with many dropped points; the same handle twice with different content (state left behind by a launch -- look-back
+    words, tile tables -- must not leak into the next)."""
+    _, scans = cfg2_scans
+    p = pfb.synth.config("cfg2")
+    batch = [pfb.synth.scan(p, f) for f in range(10, 22)]
+    batch.append(batch[0][:50000])
+    batch.append(batch[1][:100])
+    batch.append(np.zeros((0, 4), np.float32))
+    s = scans[0]
+    ring = oracle.extract(s)["ring"]
+    pos = np.zeros(len(s), np.int64)
+    for r in range(64):
+        idx = np.nonzero(ring == r)[0]
+        pos[idx] = np.arange(len(idx))
+    batch.append(np.ascontiguousarray(s[np.lexsort((ring, pos))]))          # azimuth-major interleave
+    for q in (32.0, 8.0):
+        t = scans[2].copy()
+        t[:, :3] = np.round(t[:, :3] * q) / q
+        batch.append(t)
+    rng = np.random.default_rng(12)
+    n = 100000
+    el = np.deg2rad(rng.uniform(-27.0, 4.0, n)); az = np.sort(rng.uniform(-np.pi, np.pi, n)); rho = rng.uniform(2.5, 95.0, n)
+    t = np.stack([rho * np.cos(el) * np.cos(az), rho * np.cos(el) * np.sin(az), rho * np.sin(el), rng.uniform(0, 1, n)], 1)
+    batch.append(np.ascontiguousarray(t.astype(np.float32)))
+    # ring-major scan with every 7th point out of range (dropped): no tile of it is pure
+    t = scans[1].copy()
+    t[::7, :3] *= 40.0
+    batch.append(t)
+    assert len(batch) >= 16
+    ex = capi.Extractor(num_lines=64, max_points=131072, max_batch=32, max_ring_points=3040)
+    refs = [oracle.extract(b, order=1) for b in batch]
+    for _ in range(2):
+        outs = ex.run_batch(batch, want_label=False)
+        for b, o, ref in zip(batch, outs, refs):
+            _check_points(b, o, ref)
+    rev = batch[::-1] + batch[:8]
+    outs = ex.run_batch(rev, want_label=False)
+    for b, o, ref in zip(rev, outs, refs[::-1] + refs[:8]):
+        _check_points(b, o, ref)
+    # 32-line sensor, 16 scans
+    p32 = pfb.synth.params(sensor_lines=32, seed=78)
+    b32 = [pfb.synth.scan(p32, f) for f in range(16)]
+    ex32 = capi.Extractor(num_lines=32, max_points=65536, max_batch=16)
+    for b, o in zip(b32, ex32.run_batch(b32, want_label=False)):
+        _check_points(b, o, oracle.extract(b, num_lines=32, order=1))
