@@ -62,6 +62,7 @@ inline int div_up(int a, int b) { return (a + b - 1) / b; }
 // of every link (also inside the captured CUDA graph, where it becomes a programmatic edge).  Every kernel launched this way MUST
 // start with PF_PDL_ENTRY(); kernels without it in front of one (cooperative sort, memcpy, events) behave as ordinary predecessors.
 bool pdl_enabled();
+void odom_handles_changed(int delta);   // odometry handles alive in this process (pdl_enabled's default looks at it)
 inline int64_t div_up64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 #ifdef __CUDACC__

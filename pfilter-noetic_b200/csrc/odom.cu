@@ -36,6 +36,7 @@ struct OdomShared {   // small device-resident block
     int guard;             // the maps hold enough points to associate (:247 / BPF :720)
     int n_map[4];          // map sizes after the last update (read back with the pose: tight launch bounds for the next frame)
     long long frame;       // frame index this block describes
+    int n_ds[4];           // down-sampled feature counts of the last update (read back with the pose: launch geometry of the next frames)
 };
 
 constexpr int kKinds = 4;     // kind slots of a handle: ES uses 0 (edge) 1 (surf); BPF 0 (beam) 1 (pillar) 2 (facade); slot 3 stays empty
@@ -46,7 +47,7 @@ __global__ void k_odom_reset(OdomShared* sh, LmState* S) {
     for (int i = 0; i < 3; ++i) { sh->odom.t[i] = 0; sh->last_odom.t[i] = 0; }
     const double id[7] = {0, 0, 0, 1, 0, 0, 0};
     for (int i = 0; i < 7; ++i) { sh->pose[i] = id[i]; S->x[i] = id[i]; }
-    for (int k = 0; k < 4; ++k) { sh->n_app[k] = 0; sh->n_map[k] = 0; }
+    for (int k = 0; k < 4; ++k) { sh->n_app[k] = 0; sh->n_map[k] = 0; sh->n_ds[k] = 0; }
     sh->err = 0;
     sh->guard = 0;
 }
@@ -109,6 +110,7 @@ __global__ void __launch_bounds__(256) k_append(AppendParams A) {
         int tot = m + n;
         if (tot > A.map_cap) { atomicOr(&A.sh->err, 1); tot = A.map_cap; }
         A.sh->n_app[A.slot[kind]] = tot;
+        A.sh->n_ds[A.slot[kind]] = n;
         if (kind == 0 && A.write_pose) {
             bool finite = true;
             for (int i = 0; i < 7; ++i) finite = finite && isfinite(s_pose[i]);
@@ -257,6 +259,8 @@ struct pf_odom {
     bool graph_overlap[2] = {false, false};   // whether the graph was captured without the down-sampling (it ran on the second stream)
     int graph_captures = 0;
     int map_exact[kKinds] = {};          // last exactly known map sizes (read-backs); map_ub may run ahead of them when frames are queued
+    int nds_known[kKinds] = {};          // down-sampled feature counts of the newest frame read back (0: none yet): launch geometry hint
+    int graph_q[2][kKinds] = {};         // query-count hints the graph was sized for
     // optional phase timing (PF_ODOM_TIMING=1): CUDA events at the phase boundaries of the last update
     bool timing = false;
     cudaEvent_t tev[8] = {};
@@ -369,6 +373,7 @@ void ring_refresh(pf_odom* h) {
             for (int k = 0; k < kKinds; ++k) ub[k] += h->ring_add[sj][k];
         }
         for (int k = 0; k < kKinds; ++k) { h->map_ub[k] = ub[k] < h->bufcap ? ub[k] : h->bufcap; h->map_exact[k] = h->h_ring[slot].n_map[k]; }
+        if (h->ring_frame[slot] > 0) for (int k = 0; k < kKinds; ++k) h->nds_known[k] = h->h_ring[slot].n_ds[k];
         h->known_frame = h->ring_frame[slot];
         break;
     }
@@ -423,8 +428,12 @@ int record_downsample(pf_odom* h, Workspace& w, const float4* const feat[kKinds]
 
 // The launch sequence of one update, enqueued on h->stream (directly, or into a stream capture).  ub / mub: upper bounds of the
 // feature and map counts (launch geometry only: every kernel is grid-stride or persistent and reads the exact device counts).
+// qh: how many down-sampled query points to expect per kind (from the read-backs of the last frames; <= ub): sizes the grids of the
+// kernels that walk the query clouds.  ub is the only bound the host has when it enqueues (the raw feature count, 10 - 30 x the
+// down-sampled one); grids sized by it are mostly CTAs that find nothing to do -- harmless for one sequence, but with several
+// sequences on one GPU they take the slots other sequences' kernels could run in.
 int record_update(pf_odom* h, const float4* const feat[kKinds], const int* const n_feat[kKinds], const int ub[kKinds], const int mub[kKinds],
-                  int passes, bool sorted_known, int app[kKinds], bool overlap) {
+                  const int qh[kKinds], int passes, bool sorted_known, int app[kKinds], bool overlap) {
     Workspace& ws = h->ws;
     const int cur = h->cur, nxt = cur ^ 1;
     auto mark = [&](int i) { if (h->timing) cudaEventRecord(h->tev[i], h->stream); };
@@ -495,7 +504,7 @@ int record_update(pf_odom* h, const float4* const feat[kKinds], const int* const
     L.state = h->d_state; L.iter_poses = h->d_iter_poses; L.eval_only = 0;
     L.weight_type = (int)h->prm.weight_type;
     for (int it = 0; it < passes; ++it) {
-        for (int p = 0; p < h->npairs; ++p) PF_CHECK(associate_pass(h->stream, A[p], ub[h->pair[p][0]], ub[h->pair[p][1]], &ws.launches));
+        for (int p = 0; p < h->npairs; ++p) PF_CHECK(associate_pass(h->stream, A[p], qh[h->pair[p][0]], qh[h->pair[p][1]], &ws.launches));
         if (it == passes - 1) mark(3);
         PF_CHECK(lm_solve(h->stream, L, nullptr, it == 0, &ws.launches, ub_src));
     }
@@ -512,7 +521,9 @@ int record_update(pf_odom* h, const float4* const feat[kKinds], const int* const
         P.write_pose = p == 0;
         P.sh = h->d_sh; P.S = h->d_state; P.map_cap = h->bufcap;
         P.pose_hist = h->d_pose_hist;
-        PF_CUDA(launch_pdl(k_append, dim3(kSMs, 2), dim3(256), 0, h->stream, P));
+        const int qmax = qh[h->pair[p][0]] > qh[h->pair[p][1]] ? qh[h->pair[p][0]] : qh[h->pair[p][1]];
+        const int ablk = div_up(qmax > 0 ? qmax : 1, 256);
+        PF_CUDA(launch_pdl(k_append, dim3(ablk < kSMs ? ablk : kSMs, 2), dim3(256), 0, h->stream, P));
         ws.launches += 1;
     }
     for (int p = 0; p < h->npairs; ++p) {
@@ -532,7 +543,7 @@ int record_update(pf_odom* h, const float4* const feat[kKinds], const int* const
             const int k = h->pair[p][j];
             app[k] = mub[k] + ub[k] < h->bufcap ? mub[k] + ub[k] : h->bufcap;
             // unsorted part: everything on the first update (raw first-frame maps), later last update's exceptions + this frame's points
-            capb[j] = sorted_known ? (kMergeExcCap + ub[k] < app[k] ? kMergeExcCap + ub[k] : app[k]) : app[k];
+            capb[j] = sorted_known ? (kMergeExcCap + qh[k] < app[k] ? kMergeExcCap + qh[k] : app[k]) : app[k];   // launch geometry only
             if (k == kNull) capb[j] = 0;
             capa[j] = mub[k];
         }
@@ -570,6 +581,11 @@ int enqueue_update(pf_odom* h, const float4* const feat_in[kKinds], const int* c
         if (live && ub[k] < 1) ub[k] = 1;
         mub[k] = live ? (h->map_ub[k] > 1 ? h->map_ub[k] : 1) : 0;
     }
+    int qh[kKinds];
+    for (int k = 0; k < kKinds; ++k) {
+        const int seen = h->nds_known[k];
+        qh[k] = seen > 0 && seen + seen / 4 + 512 < ub[k] ? seen + seen / 4 + 512 : ub[k];
+    }
     const int passes = h->optimization_count;
     h->last_passes = passes;
     const int cur = h->cur;
@@ -593,12 +609,14 @@ int enqueue_update(pf_odom* h, const float4* const feat_in[kKinds], const int* c
         bool fits = h->graph_exec[cur] != nullptr && h->graph_overlap[cur] == overlap;
         for (int k = 0; k < kKinds && fits; ++k)
             fits = h->graph_feat[cur][k] == feat[k] && h->graph_nfeat[cur][k] == n_feat[k] && ub[k] <= h->graph_ub[cur][k] &&
-                   h->map_exact[k] <= h->graph_mub[cur][k];
+                   h->map_exact[k] <= h->graph_mub[cur][k] && qh[k] <= h->graph_q[cur][k] &&
+                   h->graph_q[cur][k] <= 4 * qh[k] + 8192;      // captured before the first read-back: sized by the raw bound
         if (!fits) {
-            int gub[kKinds], gmub[kKinds];
+            int gub[kKinds], gmub[kKinds], gq[kKinds];
             for (int k = 0; k < kKinds; ++k) {
                 const bool live = k < h->nk;
                 gub[k] = live ? (ub[k] + ub[k] / 4 + 1024 < h->fcap ? ub[k] + ub[k] / 4 + 1024 : h->fcap) : 0;   // headroom: scans differ in size
+                gq[k] = qh[k] + qh[k] / 4 + 1024 < gub[k] ? qh[k] + qh[k] / 4 + 1024 : gub[k];
                 const long long want = 2ll * h->map_exact[k] + 65536;
                 gmub[k] = live ? (int)(want < h->bufcap ? want : h->bufcap) : 0;
             }
@@ -607,7 +625,7 @@ int enqueue_update(pf_odom* h, const float4* const feat_in[kKinds], const int* c
             const uint64_t l0 = h->ws.launches;
             bool ok = cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
             if (ok) {
-                const int rc = record_update(h, feat, n_feat, gub, gmub, passes, true, app, overlap);
+                const int rc = record_update(h, feat, n_feat, gub, gmub, gq, passes, true, app, overlap);
                 ok = cudaStreamEndCapture(h->stream, &graph) == cudaSuccess && rc == PF_OK && graph != nullptr;
             }
             if (ok) ok = cudaGraphInstantiate(&h->graph_exec[cur], graph, 0) == cudaSuccess;
@@ -623,7 +641,7 @@ int enqueue_update(pf_odom* h, const float4* const feat_in[kKinds], const int* c
                 h->graph_overlap[cur] = overlap;
                 for (int k = 0; k < kKinds; ++k) {
                     h->graph_feat[cur][k] = feat[k]; h->graph_nfeat[cur][k] = n_feat[k];
-                    h->graph_ub[cur][k] = gub[k]; h->graph_mub[cur][k] = gmub[k];
+                    h->graph_ub[cur][k] = gub[k]; h->graph_mub[cur][k] = gmub[k]; h->graph_q[cur][k] = gq[k];
                 }
             }
         }
@@ -634,7 +652,7 @@ int enqueue_update(pf_odom* h, const float4* const feat_in[kKinds], const int* c
             replayed = true;
         }
     }
-    if (!replayed) PF_CHECK(record_update(h, feat, n_feat, ub, mub, passes, h->sorted_known, app, overlap));
+    if (!replayed) PF_CHECK(record_update(h, feat, n_feat, ub, mub, qh, passes, h->sorted_known, app, overlap));
     PF_CUDA(cudaEventRecord(h->ev_upd_done[cur], h->stream));
     h->ev_upd_set[cur] = true;
     h->sorted_known = true;
@@ -674,6 +692,7 @@ int finish_frame(pf_odom* h, double pose_out[7]) {
     if (pose_out) memcpy(pose_out, h->h_sh->pose, sizeof(double) * 7);
     if (h->inited) {
         for (int k = 0; k < kKinds; ++k) { h->map_ub[k] = h->h_sh->n_map[k]; h->map_exact[k] = h->h_sh->n_map[k]; }
+        if (h->frame - 1 > 0) for (int k = 0; k < kKinds; ++k) h->nds_known[k] = h->h_sh->n_ds[k];
         h->known_frame = h->frame - 1;
     }
     return PF_OK;
@@ -693,6 +712,7 @@ int odom_create(const pf_odom_params* p, int device, bool bpf, pf_odom** out) {
     PF_CUDA(cudaGetDeviceProperties(&prop, device));
     PF_REQUIRE(prop.major == 10, "pfilter_b200 needs an sm_100a device, found sm_%d%d", prop.major, prop.minor);
     pf_odom* h = new pf_odom();
+    odom_handles_changed(+1);
     h->device = device;
     h->prm = *p;
     if (bpf) {      // beam, pillar: line residuals at map_resolution; facade: plane residuals at 2 x map_resolution (:658-660)
@@ -764,6 +784,7 @@ extern "C" int pf_odom_destroy(pf_odom* h) {
     for (int b = 0; b < 2; ++b) if (h->ev_done[b]) cudaEventDestroy(h->ev_done[b]);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
+    odom_handles_changed(-1);
     return PF_OK;
 }
 

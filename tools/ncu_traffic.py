@@ -1,5 +1,5 @@
 """DRAM traffic (dram__bytes_read.sum + dram__bytes_write.sum) per launch of the roofline kernels, from ncu --set full captures;
-writes profiles/traffic_r1.json, which bench.py reports as roofline.traffic.
+writes profiles/traffic_r2.json, which bench.py reports as roofline.traffic.
 usage: ncu_traffic.py k1.ncu-rep k9.ncu-rep k4.ncu-rep"""
 import csv
 import json
@@ -44,6 +44,6 @@ a, b = first(k9, "k_mm_count"), first(k9, "k_mm_write")
 out["k9"] = {"count": a, "write": b, "bytes_per_update": a["dram_read"] + a["dram_write"] + b["dram_read"] + b["dram_write"]}
 q = first(k4, "k_knn5_tap")
 out["k4"] = {"knn": q, "bytes_per_launch": q["dram_read"] + q["dram_write"]}
-with open(os.path.join(ROOT, "profiles", "traffic_r1.json"), "w") as f:
+with open(os.path.join(ROOT, "profiles", "traffic_r2.json"), "w") as f:
     json.dump(out, f, indent=1)
 print(json.dumps(out, indent=1))
