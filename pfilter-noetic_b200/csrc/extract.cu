@@ -1164,10 +1164,10 @@ extern "C" int pf_extract_kernel_launches(pf_extract* h, uint64_t* launches) {
     return PF_OK;
 }
 
-// Enqueue H2D + kernels for one scan; results stay on the device (used by pf_extract_run and the frame pipeline).
-// device_input: xyzi is a device pointer (no copy).  The count travels as a kernel argument, so consecutive frames
-// can be enqueued without a host synchronisation in between.
-int pf_extract_enqueue_single(pf_extract* h, const float* xyzi, int n, int device_input, int want_label) {
+// The two halves of pf_extract_enqueue_single: `pre` hands over what changes from scan to scan (the count, the H2D copy, the output
+// slot), `kernels` enqueues the three kernels, whose launch geometry and arguments depend on the handle and the slot only -- the
+// frame pipeline captures them in a CUDA graph together with the down-sampling that follows (odom.cu: front graph).
+int pf_extract_enqueue_pre(pf_extract* h, const float* xyzi, int n, int device_input, const float4** src_out) {
     PF_REQUIRE(h && (xyzi || n == 0), "null argument");
     PF_REQUIRE(n >= 0 && n <= h->stride, "scan of %d points exceeds max_points %d", n, h->stride);
     PF_CUDA(cudaSetDevice(h->device));
@@ -1180,11 +1180,24 @@ int pf_extract_enqueue_single(pf_extract* h, const float* xyzi, int n, int devic
         PF_CUDA(cudaMemcpyAsync(h->d_pts, xyzi, (size_t)n * 16, cudaMemcpyHostToDevice, h->stream));
     }
     h->slot ^= 1;
-    PF_CHECK(extract_launch(h, src ? src : h->d_pts, h->d_n, 1, h->stride, h->out_edge(), h->out_n_edge(), h->edge_stride, h->out_surf(),
-                            h->out_n_surf(), want_label ? h->d_label : nullptr));
     h->last_valid = 1;
     h->last_n = n;
+    *src_out = src ? src : h->d_pts;
     return PF_OK;
+}
+int pf_extract_enqueue_kernels(pf_extract* h, const float4* src, int want_label) {
+    return extract_launch(h, src, h->d_n, 1, h->stride, h->out_edge(), h->out_n_edge(), h->edge_stride, h->out_surf(), h->out_n_surf(),
+                          want_label ? h->d_label : nullptr);
+}
+void pf_extract_count_launches(pf_extract* h, int n) { h->launches += (uint64_t)n; }
+
+// Enqueue H2D + kernels for one scan; results stay on the device (used by pf_extract_run and the frame pipeline).
+// device_input: xyzi is a device pointer (no copy).  The count travels as a kernel argument, so consecutive frames
+// can be enqueued without a host synchronisation in between.
+int pf_extract_enqueue_single(pf_extract* h, const float* xyzi, int n, int device_input, int want_label) {
+    const float4* src = nullptr;
+    PF_CHECK(pf_extract_enqueue_pre(h, xyzi, n, device_input, &src));
+    return pf_extract_enqueue_kernels(h, src, want_label);
 }
 
 // accessors for the device-resident hand-off (odom.cu)

@@ -178,6 +178,9 @@ using namespace pf;
 void pf_extract_device_outputs(pf_extract* h, const float4** edge, const int** n_edge, const float4** surf, const int** n_surf,
                                cudaStream_t* stream, int* edge_cap, int* surf_cap, int* slot, const unsigned** err_word);
 int pf_extract_enqueue_single(pf_extract* h, const float* xyzi, int n, int device_input, int want_label);
+int pf_extract_enqueue_pre(pf_extract* h, const float* xyzi, int n, int device_input, const float4** src_out);
+int pf_extract_enqueue_kernels(pf_extract* h, const float4* src, int want_label);
+void pf_extract_count_launches(pf_extract* h, int n);
 
 struct pf_odom {
     int device = 0;
@@ -258,6 +261,20 @@ struct pf_odom {
     uint64_t graph_launches[2] = {0, 0};
     bool graph_overlap[2] = {false, false};   // whether the graph was captured without the down-sampling (it ran on the second stream)
     int graph_captures = 0;
+    // Front graph (pf_frame_submit): the extraction kernels and the down-sampling of one frame, captured once per (extractor output
+    // slot, map buffer) and replayed on the extractor's stream.  With the update graph a queued frame costs the host a dozen driver
+    // calls instead of ~25; a host thread that feeds several sequences spends its time in exactly those calls.  PF_FRAME_GRAPH=0: off.
+    struct FrontGraph {
+        cudaGraphExec_t exec = nullptr;
+        pf_extract* ex = nullptr;
+        const float4* src = nullptr;
+        int ub[2] = {0, 0};              // feature bounds the down-sampling was sized for
+        int ex_launches = 0, ds_launches = 0;
+    };
+    FrontGraph front[2][2];
+    cudaEvent_t ev_front_fork = nullptr, ev_front_join = nullptr;
+    bool use_front = true;
+    int front_captures = 0;
     int map_exact[kKinds] = {};          // last exactly known map sizes (read-backs); map_ub may run ahead of them when frames are queued
     int nds_known[kKinds] = {};          // down-sampled feature counts of the newest frame read back (0: none yet): launch geometry hint
     int graph_q[2][kKinds] = {};         // query-count hints the graph was sized for
@@ -564,8 +581,9 @@ int record_update(pf_odom* h, const float4* const feat[kKinds], const int* const
 // feat_ready: event after which the feature clouds may be read (null: they are ordered on h->stream already)
 // overlap: down-sample on the second stream (frames queued back to back); a caller that blocks on every frame gains nothing from it
 // and saves the stream hops by keeping it in line
+// ds_done: the down-sampling of this frame has already been enqueued (front graph), ev_ds_done[cur] marks its end
 int enqueue_update(pf_odom* h, const float4* const feat_in[kKinds], const int* const n_feat_in[kKinds], const int ub_in[kKinds],
-                   cudaEvent_t feat_ready, bool overlap) {
+                   cudaEvent_t feat_ready, bool overlap, bool ds_done = false) {
     overlap = overlap && h->overlap_ds;
     if (h->optimization_count > 2) h->optimization_count--;   // :232-233
     ring_refresh(h);
@@ -589,7 +607,9 @@ int enqueue_update(pf_odom* h, const float4* const feat_in[kKinds], const int* c
     const int passes = h->optimization_count;
     h->last_passes = passes;
     const int cur = h->cur;
-    if (overlap) {
+    if (overlap && ds_done) {
+        PF_CUDA(cudaStreamWaitEvent(h->stream, h->ev_ds_done[cur], 0));
+    } else if (overlap) {
         // down-sampling on its own stream: after the features are there and after the update that last read this slot
         if (!feat_ready) { PF_CUDA(cudaEventRecord(h->ev_feat, h->stream)); feat_ready = h->ev_feat; }
         PF_CUDA(cudaStreamWaitEvent(h->stream_ds, feat_ready, 0));
@@ -734,6 +754,9 @@ int odom_create(const pf_odom_params* p, int device, bool bpf, pf_odom** out) {
     PF_CUDA(cudaStreamCreateWithFlags(&h->stream_grid, cudaStreamNonBlocking));
     PF_CUDA(cudaStreamCreateWithFlags(&h->stream_ds, cudaStreamNonBlocking));
     PF_CUDA(cudaEventCreateWithFlags(&h->ev_feat, cudaEventDisableTiming));
+    PF_CUDA(cudaEventCreateWithFlags(&h->ev_front_fork, cudaEventDisableTiming));
+    PF_CUDA(cudaEventCreateWithFlags(&h->ev_front_join, cudaEventDisableTiming));
+    { const char* g = getenv("PF_FRAME_GRAPH"); h->use_front = !(g && g[0] == '0'); }
     for (int b = 0; b < 2; ++b) {
         PF_CUDA(cudaEventCreateWithFlags(&h->ev_ds_done[b], cudaEventDisableTiming));
         PF_CUDA(cudaEventCreateWithFlags(&h->ev_upd_done[b], cudaEventDisableTiming));
@@ -764,6 +787,9 @@ extern "C" int pf_odom_destroy(pf_odom* h) {
     workspace_destroy(h->ws_ds);
     if (h->stream_ds) cudaStreamDestroy(h->stream_ds);
     if (h->ev_feat) cudaEventDestroy(h->ev_feat);
+    if (h->ev_front_fork) cudaEventDestroy(h->ev_front_fork);
+    if (h->ev_front_join) cudaEventDestroy(h->ev_front_join);
+    for (int a = 0; a < 2; ++a) for (int b = 0; b < 2; ++b) if (h->front[a][b].exec) cudaGraphExecDestroy(h->front[a][b].exec);
     for (int b = 0; b < 2; ++b) { if (h->ev_ds_done[b]) cudaEventDestroy(h->ev_ds_done[b]); if (h->ev_upd_done[b]) cudaEventDestroy(h->ev_upd_done[b]); }
     if (h->stream_grid) cudaStreamDestroy(h->stream_grid);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
@@ -871,6 +897,65 @@ static int process_extracted(pf_odom* h, pf_extract* ex, double pose_out[7], boo
     return sync ? finish_frame(h, pose_out) : PF_OK;
 }
 
+// pf_frame_submit in steady state: `pre` (count + H2D copy) has been enqueued on the extractor's stream; extraction kernels and
+// down-sampling follow as one graph launch on that stream, the update as the other on the odometry's.
+static int process_front_graph(pf_odom* h, pf_extract* ex, const float4* src) {
+    PF_CUDA(cudaSetDevice(h->device));
+    const float4* feat[kKinds] = {};
+    const int* nf[kKinds] = {};
+    int ub[kKinds] = {0, 0, 0, 0};
+    cudaStream_t exs;
+    int slot = 0;
+    const unsigned* exerr = nullptr;
+    pf_extract_device_outputs(ex, &feat[0], &nf[0], &feat[1], &nf[1], &exs, &ub[0], &ub[1], &slot, &exerr);
+    set_extract_err(h, exerr);
+    PF_REQUIRE(ub[1] <= h->fcap, "scan of %d points exceeds max_features %d", ub[1], h->fcap);
+    const int cur = h->cur;
+    // this frame's extraction writes output slot `slot` (last read by the frame before last, on this stream unless that frame took
+    // the plain path) and its down-sampling writes d_ds[cur] (last read by the update of the frame before last)
+    if (h->ev_done_set[slot]) { PF_CUDA(cudaStreamWaitEvent(exs, h->ev_done[slot], 0)); h->ev_done_set[slot] = false; }
+    if (h->ev_upd_set[cur]) PF_CUDA(cudaStreamWaitEvent(exs, h->ev_upd_done[cur], 0));
+    pf_odom::FrontGraph& G = h->front[slot][cur];
+    if (!(G.exec && G.ex == ex && G.src == src && ub[0] <= G.ub[0] && ub[1] <= G.ub[1])) {
+        if (G.exec) { cudaGraphExecDestroy(G.exec); G.exec = nullptr; }
+        int gub[kKinds] = {0, 0, 0, 0};
+        for (int k = 0; k < 2; ++k) gub[k] = ub[k] + ub[k] / 4 + 1024 < h->fcap ? ub[k] + ub[k] / 4 + 1024 : h->fcap;
+        cudaGraph_t graph = nullptr;
+        const uint64_t l0 = h->ws_ds.launches;
+        bool ok = cudaStreamBeginCapture(exs, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+        if (ok) {
+            int rc = pf_extract_enqueue_kernels(ex, src, 0);
+            pf_extract_count_launches(ex, -3);                    // counted per replay below
+            if (rc == PF_OK) rc = cudaEventRecord(h->ev_front_fork, exs) == cudaSuccess ? PF_OK : PF_ERR_CUDA;
+            if (rc == PF_OK) rc = cudaStreamWaitEvent(h->stream_ds, h->ev_front_fork, 0) == cudaSuccess ? PF_OK : PF_ERR_CUDA;
+            if (rc == PF_OK) rc = workspace_begin_step(h->ws_ds);
+            if (rc == PF_OK) rc = record_downsample(h, h->ws_ds, feat, nf, gub, cur);
+            if (rc == PF_OK) rc = cudaEventRecord(h->ev_front_join, h->stream_ds) == cudaSuccess ? PF_OK : PF_ERR_CUDA;
+            if (rc == PF_OK) rc = cudaStreamWaitEvent(exs, h->ev_front_join, 0) == cudaSuccess ? PF_OK : PF_ERR_CUDA;
+            ok = cudaStreamEndCapture(exs, &graph) == cudaSuccess && rc == PF_OK && graph != nullptr;
+        }
+        if (ok) ok = cudaGraphInstantiate(&G.exec, graph, 0) == cudaSuccess;
+        if (graph) cudaGraphDestroy(graph);
+        G.ds_launches = (int)(h->ws_ds.launches - l0);
+        h->ws_ds.launches = l0;
+        h->front_captures += 1;
+        if (!ok) {          // not capturable here: the plain launch sequence from now on
+            cudaGetLastError();
+            G.exec = nullptr;
+            h->use_front = false;
+            PF_CHECK(pf_extract_enqueue_kernels(ex, src, 0));
+            return process_extracted(h, ex, nullptr, false);
+        }
+        G.ex = ex; G.src = src; G.ub[0] = gub[0]; G.ub[1] = gub[1]; G.ex_launches = 3;
+    }
+    PF_CUDA(cudaGraphLaunch(G.exec, exs));
+    pf_extract_count_launches(ex, G.ex_launches);
+    h->ws_ds.launches += (uint64_t)G.ds_launches;
+    h->ws.launches += (uint64_t)G.ds_launches;
+    PF_CUDA(cudaEventRecord(h->ev_ds_done[cur], exs));
+    return enqueue_update(h, feat, nf, ub, nullptr, true, true);
+}
+
 extern "C" int pf_odom_process_extracted(pf_odom* h, pf_extract* ex, double pose_out[7]) {
     return process_extracted(h, ex, pose_out, true);
 }
@@ -897,8 +982,14 @@ extern "C" int pf_frame_submit(pf_extract* ex, pf_odom* od, const float* xyzi, i
         set_error("%d frames are outstanding: pf_frame_wait for frame %lld first", pf_odom::kRing, od->waited_upto + 1);
         return PF_ERR_STATE;
     }
-    PF_CHECK(pf_extract_enqueue_single(ex, xyzi, n, 0, 0));
-    PF_CHECK(process_extracted(od, ex, nullptr, false));
+    if (od->inited && od->use_front && od->use_graph && od->overlap_ds && od->nk == 2) {
+        const float4* src = nullptr;
+        PF_CHECK(pf_extract_enqueue_pre(ex, xyzi, n, 0, &src));
+        PF_CHECK(process_front_graph(od, ex, src));
+    } else {
+        PF_CHECK(pf_extract_enqueue_single(ex, xyzi, n, 0, 0));
+        PF_CHECK(process_extracted(od, ex, nullptr, false));
+    }
     if (frame_id) *frame_id = od->frame - 1;
     return PF_OK;
 }
