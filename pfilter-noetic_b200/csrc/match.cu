@@ -15,53 +15,48 @@
 
 namespace pf {
 
-// A warp takes kAssocBatch consecutive queries: the 5-NN search of each one is warp-cooperative (one after the other), then
-// lane g fits the geometry of query g.  The fp64 line / plane fit is ~3000 dependent instructions; run redundantly by all 32
-// lanes of a warp per query it made the kernel bound by fp64 issue (ncu: 37 us for 7.6 k queries); packed one query per lane it
-// costs a fraction of that pipe time per query.
-#ifndef PF_ASSOC_BATCH
-#define PF_ASSOC_BATCH 4
-#endif
-constexpr int kAssocBatch = PF_ASSOC_BATCH;
-__global__ void __launch_bounds__(256) k_assoc_match(AssocParams P) {
+// The search and the fit are two kernels.  k_assoc_knn: a half warp per query (two searches side by side per warp: a search is a
+// chain of dependent memory round trips, not a throughput problem), 40 registers, every query of the frame in flight at once; it
+// leaves the five map indices (or -1: fewer than five neighbours within 1 m).  k_assoc_fit: one THREAD per query runs the fp64 line /
+// plane fit (~3000 dependent instructions, 128 registers).  Fused in one kernel (round 1: a warp searched four queries, then four
+// of its lanes fitted them) the fit's registers and its 12 us chain were paid by every search warp: 522 CTAs at two per SM held
+// the whole GPU for 35 us per pass -- nothing for one sequence, but the ceiling of several sequences sharing the GPU.
+__global__ void __launch_bounds__(256) k_assoc_knn(AssocParams P) {
     PF_PDL_ENTRY();
     const int kind = blockIdx.y;
     const AssocCloud& c = P.c[kind];
     const unsigned lane = lane_id();
     const int nq = *c.n_q;
-    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    const int nhalf = (gridDim.x * blockDim.x) >> 4;
+    const bool guard = P.guard == nullptr || *P.guard != 0;   // :247
+    if (!guard) return;                                        // k_assoc_fit clears the flags
+    for (int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 4; q < nq; q += nhalf) {      // uniform within the half warp
+        const Pt qp = c.queries[q];
+        const D3 pw = pose_apply(P.pose, d3((double)qp.x, (double)qp.y, (double)qp.z));
+        int idx[5];
+        float d2[5];
+        const bool found = knn5_group<16>(c.grid, (float)pw.x, (float)pw.y, (float)pw.z, idx, d2);   // :299-300 / :447-451
+        const int j = (int)(lane & 15u);
+        if (j < 5) c.nn_idx[5 * q + j] = found ? idx[j] : -1;
+    }
+}
+
+__global__ void __launch_bounds__(128) k_assoc_fit(AssocParams P) {
+    PF_PDL_ENTRY();
+    const int kind = blockIdx.y;
+    const AssocCloud& c = P.c[kind];
+    const int nq = *c.n_q;
     if (P.weight_type != 0 && blockIdx.x == 0 && threadIdx.x < 4)     // min / max slots of this pass (read by k_assoc_persist, which follows)
         P.w_minmax[4 * kind + threadIdx.x] = (threadIdx.x & 1) ? 0ull : ~0ull;
     const bool guard = P.guard == nullptr || *P.guard != 0;   // :247
-    for (int q0 = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * kAssocBatch; q0 < nq; q0 += nwarps * kAssocBatch) {
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += gridDim.x * blockDim.x) {
         int my_idx[5] = {-1, -1, -1, -1, -1};
-        bool my_found = false;
-        // Batch entry b is searched by half warp (b & 1) in round (b >> 1) -- two searches side by side: a search is a chain of dependent
-        // memory round trips, not a throughput problem -- and fitted by lane fit_lane(b) = 16 (b & 1) + (b >> 1) of that half warp.
-        const int half = (int)(lane >> 4), hl = (int)(lane & 15u);
-        const int my_b = 2 * hl + half;                      // the batch entry this lane fits (if < kAssocBatch)
         if (guard) {
-#pragma unroll 1
-            for (int rnd = 0; rnd < (kAssocBatch + 1) / 2; ++rnd) {
-                const int b = 2 * rnd + half;
-                const int q = q0 + b;
-                if (b < kAssocBatch && q < nq) {             // uniform within the half warp
-                    const Pt qp = c.queries[q];
-                    const D3 pw = pose_apply(P.pose, d3((double)qp.x, (double)qp.y, (double)qp.z));
-                    int idx[5];
-                    float d2[5];
-                    const bool found = knn5_group<16>(c.grid, (float)pw.x, (float)pw.y, (float)pw.z, idx, d2);   // :299-300 / :447-451
-                    if (hl == rnd) {
-                        my_found = found;
 #pragma unroll
-                        for (int j = 0; j < 5; ++j) my_idx[j] = idx[j];
-                    }
-                }
-            }
+            for (int j = 0; j < 5; ++j) my_idx[j] = c.nn_idx[5 * q + j];
         }
-        __syncwarp();
-        const int q = q0 + my_b;
-        if (my_b < kAssocBatch && q < nq) {
+        const bool my_found = my_idx[0] >= 0;
+        {
             unsigned flag = 0;
             if (my_found) {
                 D3 nb[5];
@@ -206,12 +201,13 @@ __global__ void __launch_bounds__(128) k_assoc_persist(AssocParams P) {
 int associate_pass(cudaStream_t stream, const AssocParams& P, int qcap0, int qcap1, uint64_t* launches) {
     const int qcap = qcap0 > qcap1 ? qcap0 : qcap1;
     if (qcap <= 0) return PF_OK;
-    int gm = div_up(qcap, 8 * kAssocBatch), gp = div_up(qcap, 128);
-    if (gm > 8 * kSMs) gm = 8 * kSMs;
+    int gk = div_up(qcap, 16), gp = div_up(qcap, 128);      // a half warp per query / a thread per query
+    if (gk > 8 * kSMs) gk = 8 * kSMs;
     if (gp > 4 * kSMs) gp = 4 * kSMs;
-    PF_CUDA(launch_pdl(k_assoc_match, dim3(gm, 2), dim3(256), 0, stream, P));
+    PF_CUDA(launch_pdl(k_assoc_knn, dim3(gk, 2), dim3(256), 0, stream, P));
+    PF_CUDA(launch_pdl(k_assoc_fit, dim3(gp, 2), dim3(128), 0, stream, P));
     PF_CUDA(launch_pdl(k_assoc_persist, dim3(gp, 2), dim3(128), 0, stream, P));
-    if (launches) *launches += 2;
+    if (launches) *launches += 3;
     PF_CUDA(cudaGetLastError());
     return PF_OK;
 }
