@@ -39,11 +39,13 @@ MAX_POINTS = 115200
 
 def _traffic():
     """DRAM bytes per launch of the roofline kernels from the committed ncu capture (tools/ncu_traffic.py), or {}."""
-    try:
-        with open(os.path.join(ROOT, "profiles", "traffic_r1.json")) as f:
-            return json.load(f)
-    except Exception:
-        return {}
+    for name in ("traffic_r2.json", "traffic_r1.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                return json.load(f)
+        except Exception:
+            pass
+    return {}
 
 
 def _peaks():
@@ -262,8 +264,9 @@ def roofline_leg(pfb, capi, torch, scans, dev):
     return {"bound": "hbm", "kernel": "k_ring_classify + k_ring_index + k_sector_extract (K1, batched: %d scans, %.0f MB in > L2)" % (batch, 16e-6 * pts),
             "achieved": achieved, "peak": peak, "peak_source": how, "unit": "GB/s", "frac": achieved / peak,
             "traffic": tr.get("bytes_per_launch_group"), "algorithmic_bytes": 32.0 * pts,
-            "limiter": "instruction issue, not DRAM: ~290 warp instructions per 32 points in k_sector_extract (greedy pick 1/3, curvature 1/4) at "
-                       "2.4-2.6 IPC with 28 resident warps per SM; k_ring_classify runs at 78 % of DRAM peak (profiles/k1_extract_r1z_ncu_summary.txt)",
+            "limiter": "instruction issue and the look-back, not DRAM: ~280 warp instructions per 32 points in k_sector_extract (greedy pick 1/3, "
+                       "curvature 1/4) at 2.5 IPC with 28 resident warps per SM; k_ring_classify runs at 78 % of DRAM peak "
+                       "(profiles/k1_extract_r2_ncu_summary.txt; what was tried and dropped: profiles/k1_r2_experiments.txt)",
             "kernel_share_of_group": tr.get("share_of_group_time"),
             "bytes_per_point": 32, "achieved_io_bytes": (16.0 * pts + 16.0 * out_pts) / (ms * 1e-3) / 1e9,
             "ms_per_launch_group": ms, "launches_per_group": launches, "scans_per_s_extract_only": batch / ms * 1e3}
@@ -299,8 +302,13 @@ def extra_kernel_legs(capi, dev_index):
     q[:, :3] += rng.normal(0, 0.2, (nq, 3)).astype(np.float32)
     idx, d2, ms_build, ms_query = capi.knn5_timed(m0, q, reps=4, device=dev_index)
     valid = float((idx[:, 4] >= 0).mean())
-    k4 = {"kernel": "k_knn5 (K4 exact 5-NN over the 1 m grid, one warp per query)", "map_points": int(len(m0)), "queries": nq,
+    # the same queries in the order the frame loop presents them (sorted by the 0.4 m voxel of the down-sampling)
+    vk = np.floor(q[:, :3] / np.float32(0.4)).astype(np.int64)
+    qv = np.ascontiguousarray(q[np.lexsort((vk[:, 0], vk[:, 1], vk[:, 2]))])
+    _, _, _, ms_query_v = capi.knn5_timed(m0, qv, reps=4, device=dev_index)
+    k4 = {"kernel": "k_knn5 (K4 exact 5-NN over the 1 m grid, half a warp per query)", "map_points": int(len(m0)), "queries": nq,
           "queries_per_s": nq / (ms_query * 1e-3), "ms_query_kernel": ms_query, "ms_grid_build": ms_build,
+          "queries_per_s_voxel_order": nq / (ms_query_v * 1e-3), "query_order": "random (queries_per_s) / sorted by down-sampling voxel (queries_per_s_voxel_order)",
           "valid_fraction": valid, "algorithmic_gbs": 136.0 * nq / (ms_query * 1e-3) / 1e9,
           "traffic": _traffic().get("k4", {}).get("bytes_per_launch"), "l2_hit_pct": _traffic().get("k4", {}).get("knn", {}).get("l2_hit_pct"),
           "grid_build_gbs": 36.0 * len(m0) / (ms_build * 1e-3) / 1e9}
