@@ -25,6 +25,7 @@
 #include <math.h>
 
 #include <algorithm>
+#include <atomic>
 #include <vector>
 
 #include "common.cuh"
@@ -825,6 +826,7 @@ __global__ void __launch_bounds__(kSecWarps * 32, kRefOrder ? 8 : 14) k_sector_e
 // ------------------------------------------------------------------------------------------------------------
 struct pf_extract {
     int device = 0;
+    uint64_t uid = 0;                 // unique per handle ever created in this process (a captured graph is tied to it, not to the address)
     cudaStream_t stream = nullptr;
     pf_lidar_params lidar{};
     int stride = 0, tiles = 0, max_batch = 0, rcap = 0, scap = 0, edge_stride = 0;
@@ -1019,6 +1021,7 @@ extern "C" int pf_extract_create(const pf_lidar_params* lidar, const pf_extract_
     PF_REQUIRE(prop.major == 10, "pfilter_b200 needs an sm_100a device, found sm_%d%d", prop.major, prop.minor);
 
     pf_extract* h = new pf_extract();
+    { static std::atomic<uint64_t> next_uid{1}; h->uid = next_uid.fetch_add(1); }
     h->device = device;
     h->lidar = *lidar;
     h->stride = div_up(cfg->max_points, kTile) * kTile;
@@ -1190,6 +1193,7 @@ int pf_extract_enqueue_kernels(pf_extract* h, const float4* src, int want_label)
                           want_label ? h->d_label : nullptr);
 }
 void pf_extract_count_launches(pf_extract* h, int n) { h->launches += (uint64_t)n; }
+uint64_t pf_extract_uid(const pf_extract* h) { return h->uid; }
 
 // Enqueue H2D + kernels for one scan; results stay on the device (used by pf_extract_run and the frame pipeline).
 // device_input: xyzi is a device pointer (no copy).  The count travels as a kernel argument, so consecutive frames

@@ -181,6 +181,7 @@ int pf_extract_enqueue_single(pf_extract* h, const float* xyzi, int n, int devic
 int pf_extract_enqueue_pre(pf_extract* h, const float* xyzi, int n, int device_input, const float4** src_out);
 int pf_extract_enqueue_kernels(pf_extract* h, const float4* src, int want_label);
 void pf_extract_count_launches(pf_extract* h, int n);
+uint64_t pf_extract_uid(const pf_extract* h);
 
 struct pf_odom {
     int device = 0;
@@ -266,7 +267,7 @@ struct pf_odom {
     // calls instead of ~25; a host thread that feeds several sequences spends its time in exactly those calls.  PF_FRAME_GRAPH=0: off.
     struct FrontGraph {
         cudaGraphExec_t exec = nullptr;
-        pf_extract* ex = nullptr;
+        uint64_t ex_uid = 0;             // the extractor it was captured with
         const float4* src = nullptr;
         int ub[2] = {0, 0};              // feature bounds the down-sampling was sized for
         int ex_launches = 0, ds_launches = 0;
@@ -916,7 +917,7 @@ static int process_front_graph(pf_odom* h, pf_extract* ex, const float4* src) {
     if (h->ev_done_set[slot]) { PF_CUDA(cudaStreamWaitEvent(exs, h->ev_done[slot], 0)); h->ev_done_set[slot] = false; }
     if (h->ev_upd_set[cur]) PF_CUDA(cudaStreamWaitEvent(exs, h->ev_upd_done[cur], 0));
     pf_odom::FrontGraph& G = h->front[slot][cur];
-    if (!(G.exec && G.ex == ex && G.src == src && ub[0] <= G.ub[0] && ub[1] <= G.ub[1])) {
+    if (!(G.exec && G.ex_uid == pf_extract_uid(ex) && G.src == src && ub[0] <= G.ub[0] && ub[1] <= G.ub[1])) {
         if (G.exec) { cudaGraphExecDestroy(G.exec); G.exec = nullptr; }
         int gub[kKinds] = {0, 0, 0, 0};
         for (int k = 0; k < 2; ++k) gub[k] = ub[k] + ub[k] / 4 + 1024 < h->fcap ? ub[k] + ub[k] / 4 + 1024 : h->fcap;
@@ -946,7 +947,7 @@ static int process_front_graph(pf_odom* h, pf_extract* ex, const float4* src) {
             PF_CHECK(pf_extract_enqueue_kernels(ex, src, 0));
             return process_extracted(h, ex, nullptr, false);
         }
-        G.ex = ex; G.src = src; G.ub[0] = gub[0]; G.ub[1] = gub[1]; G.ex_launches = 3;
+        G.ex_uid = pf_extract_uid(ex); G.src = src; G.ub[0] = gub[0]; G.ub[1] = gub[1]; G.ex_launches = 3;
     }
     PF_CUDA(cudaGraphLaunch(G.exec, exs));
     pf_extract_count_launches(ex, G.ex_launches);

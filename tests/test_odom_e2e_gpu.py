@@ -135,3 +135,45 @@ def test_pipelined_submit_wait_equals_synchronous_calls(pfb, capi):
     ex2.close(); od2.close()
     with pytest.raises(capi.PfError):
         capi.frame_wait(od, 10_000)
+
+
+def test_front_graph_recapture_new_extractor_and_several_handles(pfb, capi, monkeypatch):
+    """pf_frame_submit replays extraction + down-sampling as a captured graph (csrc/odom.cu: front graph).  Scans that outgrow the
+    size it was captured for, an extractor that is destroyed and replaced in mid-sequence, and a second sequence alive in the same
+    process (programmatic launch edges then default to off) must not change a bit of the poses or the maps."""
+    p = pfb.synth.config("cfg2")
+    scans = [pfb.synth.scan(p, f) for f in range(26)]
+    for k in range(12, 20):                       # shorter scans first, the full ones afterwards: the captured bound is outgrown
+        scans[k] = np.ascontiguousarray(scans[k][: 60000 + 4000 * (k - 12)])
+
+    def run(front, second_handle):
+        monkeypatch.setenv("PF_FRAME_GRAPH", front)
+        other = None
+        if second_handle:
+            other = (capi.Extractor(num_lines=64, max_points=131072), capi.Odometry(0.4, 0, 0.4, 75, max_map_points=262144))
+        ex, od = capi.Extractor(num_lines=64, max_points=131072), capi.Odometry(0.4, 0, 0.4, 75, max_map_points=262144)
+        out, ids = [], []
+        for k, s in enumerate(scans):
+            if k == 16:                           # the extractor is replaced: nothing captured with the old one may be replayed
+                out += [capi.frame_wait(od, i) for i in ids]
+                ids = []
+                ex.close()
+                ex = capi.Extractor(num_lines=64, max_points=131072)
+            ids.append(capi.frame_submit(ex, od, s))
+            if other is not None and k < 6:
+                capi.frame_wait(other[1], capi.frame_submit(other[0], other[1], scans[k]))
+            if len(ids) > 2:
+                out.append(capi.frame_wait(od, ids.pop(0)))
+        out += [capi.frame_wait(od, i) for i in ids]
+        maps = [od.map_part(0), od.map_part(1)]
+        ex.close(); od.close()
+        if other is not None:
+            other[0].close(); other[1].close()
+        return np.array(out), maps
+
+    a, ma = run("1", False)
+    b, mb = run("0", False)
+    c, mc = run("1", True)
+    assert a.tobytes() == b.tobytes() == c.tobytes()
+    for k in range(2):
+        assert ma[k].tobytes() == mb[k].tobytes() == mc[k].tobytes()
