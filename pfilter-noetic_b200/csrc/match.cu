@@ -186,11 +186,17 @@ __global__ void __launch_bounds__(128) k_assoc_persist(AssocParams P) {
             atomicMax(mm + 3, (unsigned long long)__double_as_longlong(spa));
         }
     }
-    // release the lists; the last reader of a map point commits its counter and empties the list
+    // release the lists; the last reader of a map point commits its counter and empties the list.  Every value this thread read
+    // from the lists has been consumed above (the walk ends on them), so one fence orders all its reads before the five releases,
+    // and the five decrements (five different map points: the neighbours of a query are distinct) travel together instead of
+    // fence - round trip - fence - round trip ...: that serial tail was more than half of the kernel.
+    __threadfence();
+    int left[5];
+#pragma unroll
+    for (int j = 0; j < 5; ++j) left[j] = atomicSub(&c.hits[m[j]], 1);
 #pragma unroll
     for (int j = 0; j < 5; ++j) {
-        __threadfence();
-        if (atomicSub(&c.hits[m[j]], 1) == 1) {
+        if (left[j] == 1) {
             reinterpret_cast<uint8_t*>(c.map + m[j])[13] = (uint8_t)min(255, g0[j] + len[j]);   // g = min(255, g + 1) per hit (:345-346)
             c.head[m[j]] = -1;
         }
