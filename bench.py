@@ -217,13 +217,13 @@ def run_reference(args):
 # ----------------------------------------------------------------------------------------------------------------
 # our arm
 # ----------------------------------------------------------------------------------------------------------------
-def roofline_leg(pfb, capi, torch, scans, dev):
+def roofline_leg(pfb, capi, torch, scans, dev, batch=None):
     """Batched extraction (K1) with a working set larger than L2, CUDA-event timed on the extractor's stream."""
     # 512 scans per launch group: the persistent extract kernel keeps ~4100 sectors in flight, and a sector's output offset needs the
     # counts of the sectors in front of it in the SAME scan; the more scans share the grid, the longer those have been running
     # (128 scans: 0.285 ms per 128, 512: 0.246, 1024: 0.244).  max_ring_points = 1920 is the capacity for this sensor (1800 azimuth
     # steps per ring); it sizes the per-warp shared memory and so the occupancy.
-    batch, stride = int(os.environ.get('PF_BENCH_BATCH', '512')), MAX_POINTS
+    batch, stride = batch or int(os.environ.get('PF_BENCH_BATCH', '512')), MAX_POINTS
     ex = capi.Extractor(num_lines=64, max_points=stride, max_batch=batch, max_ring_points=int(os.environ.get('PF_BENCH_RCAP', '1920')))
     x = np.zeros((batch, stride, 4), np.float32)
     n = np.zeros(batch, np.int32)
@@ -261,6 +261,9 @@ def roofline_leg(pfb, capi, torch, scans, dev):
     peak, how = _peaks()
     achieved = 32.0 * pts / (ms * 1e-3) / 1e9
     tr = _traffic().get("k1", {})
+    ex.close()
+    del dx, dedge, dsurf, dne, dns, dn, x
+    torch.cuda.empty_cache()
     return {"bound": "hbm", "kernel": "k_ring_classify + k_ring_index + k_sector_extract (K1, batched: %d scans, %.0f MB in > L2)" % (batch, 16e-6 * pts),
             "achieved": achieved, "peak": peak, "peak_source": how, "unit": "GB/s", "frac": achieved / peak,
             "traffic": tr.get("bytes_per_launch_group"), "algorithmic_bytes": 32.0 * pts,
@@ -560,6 +563,11 @@ def run_ours(args):
 
     if rank == 0:
         roof = roofline_leg(pfb, capi, torch, scans[:8], dev)
+        try:      # the same launch group over four times as many scans (the look-back waits shrink with the number of scans in flight)
+            big = roofline_leg(pfb, capi, torch, scans[:8], dev, batch=2048)
+            roof["larger_batch"] = {"scans": 2048, "frac": big["frac"], "achieved": big["achieved"], "ms_per_launch_group": big["ms_per_launch_group"]}
+        except Exception as e:      # noqa: BLE001  (memory of a shared box: the primary leg stands on its own)
+            roof["larger_batch"] = {"scans": 2048, "skipped": str(e)[:120]}
         extra = extra_kernel_legs(capi, local)
         sys.path.insert(0, os.path.join(ROOT, "oracle"))
         import oracle as O
