@@ -1,7 +1,8 @@
 // K4-K6: association pass.  See match.cuh; arithmetic spec in SURVEY.md appendix A.2.
 //
-// k_assoc_match   one warp per query: transform by the current pose (pointAssociateToMap :162-168), exact 5-NN in the
-//                 1 m grid, then the geometric fit in fp64 registers -- line: centroid + 3x3 covariance + symmetric
+// k_assoc_knn     half a warp per query: transform by the current pose (pointAssociateToMap :162-168), exact 5-NN in the
+//                 1 m grid; leaves the five map indices (or -1).
+// k_assoc_fit     one thread per query: the geometric fit in fp64 registers -- line: centroid + 3x3 covariance + symmetric
 //                 eigen-solve, lambda2 > 3 lambda1 (:302-331); plane: 5x3 column-pivoted Householder least squares,
 //                 5 x |n.p + d| <= 0.2 (:449-476).  Geometry-valid queries push their 5 hits on per-map-point lists.
 // k_assoc_persist one thread per geometry-valid query: the reference updates the neighbours' observe counter g inside
