@@ -113,7 +113,7 @@ __device__ double gradient_max_norm(const double* x, const double* g) {
     return m;
 }
 
-__device__ void lm_finish(const LmParams& P, LmState* S, bool writer = true) {
+__device__ __noinline__ void lm_finish(const LmParams& P, LmState* S, bool writer = true) {
     S->phase = 2;
     if (writer && P.iter_poses && S->pass < 16)
         for (int k = 0; k < 7; ++k) P.iter_poses[7 * S->pass + k] = S->x[k];
@@ -315,6 +315,7 @@ __global__ void __cluster_dims__(kLmCluster, 1, 1) __launch_bounds__(kLmThreads)
         double acc[kAcc];
 #pragma unroll
         for (int k = 0; k < kAcc; ++k) acc[k] = 0.0;
+#pragma unroll 1
         for (int k = tid; k < n_list; k += kLmThreads) {
             const unsigned e = (unsigned)s_list[k];
             const int src = (int)(e >> 30), i = (int)(e & 0x3fffffffu);
@@ -326,20 +327,31 @@ __global__ void __cluster_dims__(kLmCluster, 1, 1) __launch_bounds__(kLmThreads)
             const double weight = P.weight_type != 0 ? residual_weight(P.weight_type, (double)R.w_obs[i], R.w_spa[i], s_mm + 4 * src) : 0.0;
             eval_one(kind, p, R.geom + 8 * (size_t)i, Rm, tv, weight, acc);
         }
-        // warp reduction, fixed tree (skipped by warps that evaluated nothing: their partial is exactly zero)
+        // Warp reduction, fixed tree (skipped by warps that evaluated nothing: their partial is exactly zero).  Transposed: at
+        // distance 16 a lane keeps one half of the 32 slots and hands the other half to its partner, at distance 8 a quarter, ...:
+        // 31 exchanges instead of 29 x 5, and lane l ends up with the total of slot l.  The pairing of the partial sums is that of
+        // the shuffle-down tree this replaces ((l, l ^ 16), then (l, l ^ 8), ...), so the sums are the same bit for bit -- but the
+        // unrolled 145-step tree was 55 KB of the kernel's code and a third of the instructions it executes.
+        double tot = 0.0;
         if (__any_sync(0xffffffffu, acc[28] != 0.0)) {
+            double v16[16], v8[8], v4[4], v2[2];
+            const bool b4 = (lane & 16) != 0, b3 = (lane & 8) != 0, b2 = (lane & 4) != 0, b1 = (lane & 2) != 0, b0 = (lane & 1) != 0;
 #pragma unroll
-            for (int k = 0; k < kAcc; ++k) {
-#pragma unroll
-                for (int o = 16; o >= 1; o >>= 1) acc[k] += __shfl_down_sync(0xffffffffu, acc[k], o);
+            for (int i = 0; i < 16; ++i) {
+                const double lo = acc[i], hi = i + 16 < kAcc ? acc[i + 16] : 0.0;
+                v16[i] = (b4 ? hi : lo) + __shfl_xor_sync(0xffffffffu, b4 ? lo : hi, 16);
             }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v8[i] = (b3 ? v16[i + 8] : v16[i]) + __shfl_xor_sync(0xffffffffu, b3 ? v16[i] : v16[i + 8], 8);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) v4[i] = (b2 ? v8[i + 4] : v8[i]) + __shfl_xor_sync(0xffffffffu, b2 ? v8[i] : v8[i + 4], 4);
+#pragma unroll
+            for (int i = 0; i < 2; ++i) v2[i] = (b1 ? v4[i + 2] : v4[i]) + __shfl_xor_sync(0xffffffffu, b1 ? v4[i] : v4[i + 2], 2);
+            tot = (b0 ? v2[1] : v2[0]) + __shfl_xor_sync(0xffffffffu, b0 ? v2[0] : v2[1], 1);
         }
         const int cnt_edge = __reduce_add_sync(0xffffffffu, my_edges);
-        if (lane == 0) {
-#pragma unroll
-            for (int k = 0; k < kAcc; ++k) s_red[w][k] = acc[k];
-            s_cnt[w] = cnt_edge;
-        }
+        if (lane < kAcc) s_red[w][lane] = tot;
+        if (lane == 0) s_cnt[w] = cnt_edge;
         __syncthreads();
         const int par = round & 1;
         if (tid < kAcc) {
