@@ -100,14 +100,17 @@ __device__ double vec_norm7(const double* x) {
 
 // gradient_max_norm of Ceres: | x - Plus(x, -g) |_inf.  The tolerance is 1e-10: the exponential map is only evaluated
 // when the plain max-norm of g is anywhere near it (|x - Plus(x,-g)| <= |g| (1 + |x|) for such tiny g).
-__device__ double gradient_max_norm(const double* x, const double* g) {
+// one copy of the exponential map (two sincos, ~10 KB inlined) for the step and the gradient test
+__device__ __noinline__ void se3_plus_once(const double* x, const double* d, double* out) { se3_plus(x, d, out); }
+
+__device__ __noinline__ double gradient_max_norm(const double* x, const double* g) {
     double gm = 0;
 #pragma unroll
     for (int k = 0; k < 6; ++k) gm = fmax(gm, fabs(g[k]));
     if (gm > 1e-6) return gm;
     double ng[6], xp[7];
     for (int k = 0; k < 6; ++k) ng[k] = -g[k];
-    se3_plus(x, ng, xp);
+    se3_plus_once(x, ng, xp);
     double m = 0;
     for (int k = 0; k < 7; ++k) m = fmax(m, fabs(x[k] - xp[k]));
     return m;
@@ -181,7 +184,7 @@ __device__ __noinline__ void lm_propose(const LmParams& P, LmState* S, bool writ
         S->model_cost_change = mcc;
         double delta[6];
         for (int a = 0; a < 6; ++a) delta[a] = S->step[a] * S->scale[a];
-        se3_plus(S->x, delta, S->xc);
+        se3_plus_once(S->x, delta, S->xc);
         S->phase = 1;
         return;
     }
@@ -306,6 +309,7 @@ __global__ void __cluster_dims__(kLmCluster, 1, 1) __launch_bounds__(kLmThreads)
     for (int r = 0; r < kLmCluster; ++r) part_of[r] = cluster.map_shared_rank(&s_part[0][0], r);
     __syncthreads();
 
+#pragma unroll 1     // (left to itself nvcc unrolls the eight rounds: eight copies of the evaluation, 150 KB of code on a 32 KB instruction cache)
     for (int round = 0; round < 8; ++round) {
         if (s_state.phase == 2) break;        // identical in every CTA
         const double* x = s_state.phase == 1 ? s_state.xc : s_state.x;
