@@ -229,9 +229,10 @@ struct TileRange { int lo, hi, ntiles; };
 __device__ __forceinline__ TileRange tile_range(int mA) {
     TileRange r;
     r.ntiles = mA / kMergeTile + 1;     // the last tile also takes the inserts behind the last map point
-    const int per = (r.ntiles + (int)gridDim.x - 1) / (int)gridDim.x;
-    r.lo = min(r.ntiles, (int)blockIdx.x * per);
-    r.hi = min(r.ntiles, r.lo + per);
+    // proportional split: every CTA gets floor or ceil of ntiles / grid tiles (with ceil-sized shares 8020 tiles on 2368 CTAs left
+    // 363 CTAs without work and the second wave of resident CTAs a third empty)
+    r.lo = (int)((long long)blockIdx.x * r.ntiles / (int)gridDim.x);
+    r.hi = (int)((long long)(blockIdx.x + 1) * r.ntiles / (int)gridDim.x);
     return r;
 }
 
@@ -496,8 +497,9 @@ int map_merge(Workspace& ws, const MapMergeParams& P_in, int capB0, int capB1, i
     int tblk = div_up(mtiles_all + 1, 256);
     if (tblk > 2 * kSMs) tblk = 2 * kSMs;
     PF_CUDA(launch_pdl(k_mm_tiles, dim3(tblk, 2), dim3(256), 0, ws.stream, P));
+    static const int grid_mult = [] { const char* e = getenv("PF_MM_GRID"); const int v = e ? atoi(e) : 16; return v < 1 ? 1 : (v > 16 ? 16 : v); }();
     int grid = mtiles_all;
-    if (grid > kMergeMaxGrid) grid = kMergeMaxGrid;
+    if (grid > grid_mult * kSMs) grid = grid_mult * kSMs;
 
     if (ws.ev_a) cudaEventRecord(ws.ev_a, ws.stream);
     {
