@@ -224,3 +224,17 @@ def test_extract_large_mixed_batches(capi, oracle, pfb, cfg2_scans):
     ex32 = capi.Extractor(num_lines=32, max_points=65536, max_batch=16)
     for b, o in zip(b32, ex32.run_batch(b32, want_label=False)):
         _check_points(b, o, oracle.extract(b, num_lines=32, order=1))
+
+
+def test_extract_batch_of_256_scans_at_bench_scale(capi, oracle, pfb):
+    """The look-back between the sectors of a scan only gets busy when hundreds of scans share the persistent kernel (the bench's
+    roofline leg runs 512): every one of 256 scans (eight distinct ones, repeated) must still come out bit-identical."""
+    p = pfb.synth.config("cfg2")
+    base = [pfb.synth.scan(p, f) for f in range(8)]
+    refs = [oracle.extract(s, order=1) for s in base]
+    ex = capi.Extractor(num_lines=64, max_points=115200, max_batch=256, max_ring_points=1920)
+    for rep in range(2):
+        outs = ex.run_batch([base[i % 8] for i in range(256)], want_label=False)
+        for i, o in enumerate(outs):
+            _check_points(base[i % 8], o, refs[i % 8])
+    ex.close()

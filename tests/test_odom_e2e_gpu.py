@@ -177,3 +177,31 @@ def test_front_graph_recapture_new_extractor_and_several_handles(pfb, capi, monk
     assert a.tobytes() == b.tobytes() == c.tobytes()
     for k in range(2):
         assert ma[k].tobytes() == mb[k].tobytes() == mc[k].tobytes()
+
+
+def test_two_sequences_from_two_host_threads(pfb, capi):
+    """configs[4] with fewer GPUs than sequences: several sequences share a GPU, each with its own handle pair, served by its own
+    host thread (stream capture is thread-local, the library keeps no global mutable state besides the handle count).  Poses must
+    equal those of the sequences run alone."""
+    from concurrent.futures import ThreadPoolExecutor
+    seqs = []
+    for i in range(2):
+        p = pfb.synth.config(f"cfg5.{i}")
+        seqs.append([pfb.synth.scan(p, f) for f in range(24)])
+
+    def run(scans):
+        ex, od = capi.Extractor(num_lines=64, max_points=131072), capi.Odometry(0.4, 0, 0.4, 75, max_map_points=262144)
+        ids, out = [], []
+        for s in scans:
+            ids.append(capi.frame_submit(ex, od, s))
+            if len(ids) > 1:
+                out.append(capi.frame_wait(od, ids.pop(0)))
+        out += [capi.frame_wait(od, i) for i in ids]
+        ex.close(); od.close()
+        return np.array(out)
+
+    alone = [run(s) for s in seqs]
+    with ThreadPoolExecutor(2) as tp:
+        together = list(tp.map(run, seqs))
+    for a, b in zip(alone, together):
+        assert a.tobytes() == b.tobytes()
