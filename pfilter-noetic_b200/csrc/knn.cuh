@@ -105,10 +105,14 @@ __device__ __forceinline__ bool knn5_group(const KnnGrid& g, float qx, float qy,
         const int total = __shfl_sync(gm, incl, 8, W);
         const int excl = incl - len;
         for (int i = (int)lane; i < ((total + W - 1) & ~(W - 1)); i += W) {
-            // row r with excl[r] <= i < excl[r] + len[r]
-            int r = 0;
+            // row r with excl[r] <= i < excl[r] + len[r]: the last of the nine rows whose offset does not exceed i (offsets ascend:
+            // four probes of a binary search, each lane reading the lane that holds the row it asks about, instead of eight compares)
+            int r = (i >= __shfl_sync(gm, excl, 8, W)) ? 8 : 0;
 #pragma unroll
-            for (int k = 1; k < 9; ++k) r += (i >= __shfl_sync(gm, excl, k, W)) ? 1 : 0;
+            for (int st = 4; st >= 1; st >>= 1) {
+                const int probe = r + st;                                 // <= 7 unless r == 8 (then the probes read rows 9..15: empty)
+                if (i >= __shfl_sync(gm, excl, probe, W) && probe < 9) r = probe;
+            }
             const int rbase = __shfl_sync(gm, rs, r, W), rex = __shfl_sync(gm, excl, r, W);
             if (i < total) {
                 const float4 p = __ldg(g.pts + rbase + (i - rex));
